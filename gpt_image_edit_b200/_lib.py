@@ -1,0 +1,79 @@
+"""ctypes binding of libb2f.so (the C ABI declared in include/b2f.h).
+
+The library is the product: there is no Python/torch fallback for any entry point.  If the
+shared object is missing or a call returns a negative code, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+
+import torch  # noqa: F401  (loads libcudart.so.12 into the process before libb2f.so)
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libb2f.so"
+HEADER_PATH = _HERE.parent / "include" / "b2f.h"
+
+
+class B2FError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise B2FError(
+            f"{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()). "
+            "There is no fallback path."
+        )
+    return C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_NOW", 2))
+
+
+lib = _load()
+
+_vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int
+
+_SIGNATURES = {
+    "b2f_strerror": (C.c_char_p, [_i32]),
+    "b2f_version": (_i32, []),
+    "b2f_device_info": (_i32, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_size_t)]),
+    "b2f_launch_count": (C.c_uint64, []),
+    "b2f_gemm_bf16": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Every function name include/b2f.h declares (used by the CPU-side export test)."""
+    text = HEADER_PATH.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2f_[a-z0-9_]+)\s*\(", text)))
+
+
+def _bind() -> None:
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind()
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib.b2f_strerror(code).decode()
+        raise B2FError(f"libb2f {what} failed: {msg} (code {code})")
+
+
+def stream_ptr(stream: "torch.cuda.Stream | None" = None) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+def ptr(t: "torch.Tensor | None") -> int | None:
+    return None if t is None else int(t.data_ptr())
+
+
+def launch_count() -> int:
+    return int(lib.b2f_launch_count())

@@ -1,0 +1,326 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  out[M,N] = epi(A[M,K] · W[N,K]^T + bias).
+//
+//   warp 0 (1 lane)  TMA producer      cp.async.bulk.tensor → 128B-swizzled smem ring
+//   warp 1 (1 lane)  MMA issuer        tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16
+//   warps 2..5       epilogue          tcgen05.ld (32 lanes x 32 cols) → bias/act/gate/resid → global
+//
+// Accumulators live in TMEM (2 stages x BN fp32 columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Both operands are K-major ([rows, K] row-major), which is what
+// nn.Linear stores — no transposes anywhere.
+//
+// Replaces: torch.nn.functional.linear → cuBLASLt (diffusers FluxTransformer2DModel linears,
+// reference call site univa/utils/flux_pipeline.py:1067).
+#include <atomic>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace b2f {
+
+extern std::atomic<uint64_t> g_launch_count;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  int M, N, K;
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* out;
+  long long ldc;
+  int epi;
+  const __nv_bfloat16* resid;
+  long long ldr;
+  const __nv_bfloat16* gate;
+  long long gate_ld;
+  int rows_per_batch;
+  int num_m_blocks, num_n_blocks, panel_n;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_blk, int& n_blk) {
+  // Panels of `panel_n` n-blocks; inside a panel n runs fastest so that the W panel stays in L2
+  // while A streams through once per panel.
+  const int panel_tiles = p.panel_n * p.num_m_blocks;
+  const int panel = t / panel_tiles;
+  const int r = t - panel * panel_tiles;
+  const int w = min(p.panel_n, p.num_n_blocks - panel * p.panel_n);
+  m_blk = r / w;
+  n_blk = panel * p.panel_n + (r - m_blk * w);
+}
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(p, t, m_blk, n_blk);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_sdesc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+            const uint64_t db = make_sdesc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int row_in_tile = q * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(p, t, m_blk, n_blk);
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const long long row = (long long)m_blk * BLOCK_M + row_in_tile;
+      const bool row_ok = row < p.M;
+      const int bidx = (p.epi == B2F_EPI_GATE_RESID && row_ok) ? int(row / p.rows_per_batch) : 0;
+      const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
+      __nv_bfloat16* out_row = p.out + row * p.ldc;
+      const __nv_bfloat16* res_row = p.resid ? p.resid + row * p.ldr : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[32];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+        B2F_TMEM_LD_X32(taddr, acc);
+        tmem_wait_ld();
+        if (c0 + 32 == BN) {
+          // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        const int n0 = n_blk * BN + c0;
+        if (!row_ok || n0 >= p.N) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n0 + g * 8;
+          if (n >= p.N) break;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+          if (p.bias) {
+            const uint4 bq = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+            const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 b2 = unpack_bf16x2(bw[j]);
+              v[2 * j] += b2.x;
+              v[2 * j + 1] += b2.y;
+            }
+          }
+          if (p.epi == B2F_EPI_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(bf16r(v[j]));
+          } else if (p.epi == B2F_EPI_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = silu_f(bf16r(v[j]));
+          } else if (p.epi == B2F_EPI_GATE_RESID) {
+            const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+            const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
+            const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 g2 = unpack_bf16x2(gw[j]);
+              const float2 r2 = unpack_bf16x2(rw[j]);
+              v[2 * j] = r2.x + bf16r(g2.x * bf16r(v[2 * j]));
+              v[2 * j + 1] = r2.y + bf16r(g2.y * bf16r(v[2 * j + 1]));
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]);
+          o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]);
+          o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(out_row + n) = o;
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_err(e, "gemm smem attribute");
+    attr_set = true;
+  }
+  p.num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_blocks = (p.N + BN - 1) / BN;
+  p.panel_n = BN == 256 ? 16 : 32;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = num_tiles < device_info().num_sms ? num_tiles : device_info().num_sms;
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("gemm_bf16_kernel");
+  return B2F_OK;
+}
+
+}  // namespace
+
+int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
+              int64_t ldc, int M, int N, int K, int epilogue, const void* resid, int64_t ldr,
+              const void* gate, int64_t gate_ld, int rows_per_batch, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (M <= 0 || N <= 0 || K <= 0 || !A || !W || !out) return B2F_ERR_INVALID;
+  if ((K & 7) || (N & 7) || (lda & 7) || (ldw & 7) || (ldc & 7)) return B2F_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) |
+       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
+       reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(gate)) & 15)
+    return B2F_ERR_ALIGN;
+  if (epilogue < 0 || epilogue > B2F_EPI_GATE_RESID) return B2F_ERR_INVALID;
+  if (epilogue == B2F_EPI_GATE_RESID) {
+    if (!resid || !gate || rows_per_batch <= 0 || (ldr & 7) || (gate_ld & 7)) return B2F_ERR_INVALID;
+  }
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldc = ldc;
+  p.epi = epilogue;
+  p.resid = static_cast<const __nv_bfloat16*>(resid);
+  p.ldr = ldr;
+  p.gate = static_cast<const __nv_bfloat16*>(gate);
+  p.gate_ld = gate_ld;
+  p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
+
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const bool use256 = (long long)num_m * ((N + 255) / 256) >= device_info().num_sms && N >= 256;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M, BLOCK_K);
+  if (rc != B2F_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, use256 ? 256 : 128,
+                         BLOCK_K);
+  if (rc != B2F_OK) return rc;
+  return use256 ? launch_gemm<256>(tmA, tmB, p, stream) : launch_gemm<128>(tmA, tmB, p, stream);
+}
+
+}  // namespace b2f

@@ -1,0 +1,90 @@
+// Device facts + TMA tensor-map encoding (driver entry point fetched at run time).
+#include "host_common.h"
+
+#include <atomic>
+#include <mutex>
+
+namespace b2f {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+const DeviceInfo& device_info() {
+  static DeviceInfo info;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      return;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&info.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&info.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    info.ok = (major == 10) && info.num_sms > 0;
+  });
+  return info;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                      uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return B2F_ERR_CUDA;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[b2f] cuTensorMapEncodeTiled(2d) failed: %d (rows=%llu cols=%llu ld=%llu)\n",
+            int(r), (unsigned long long)rows, (unsigned long long)cols,
+            (unsigned long long)ld_elems);
+    return B2F_ERR_CUDA;
+  }
+  return B2F_OK;
+}
+
+int make_tmap_4d_bf16(CUtensorMap* out, const void* gptr, uint64_t n, uint64_t h, uint64_t w,
+                      uint64_t c, uint32_t box_h, uint32_t box_w, uint32_t box_c) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return B2F_ERR_CUDA;
+  cuuint64_t dims[4] = {c, w, h, n};
+  cuuint64_t strides[3] = {c * 2, w * c * 2, h * w * c * 2};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[b2f] cuTensorMapEncodeTiled(4d) failed: %d\n", int(r));
+    return B2F_ERR_CUDA;
+  }
+  return B2F_OK;
+}
+
+}  // namespace b2f

@@ -1,0 +1,40 @@
+// Host-side helpers shared by the launchers: error codes, TMA tensor-map encoding through the
+// driver entry point (no -lcuda link, so the library loads on a box without a driver).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/b2f.h"
+
+namespace b2f {
+
+struct DeviceInfo {
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  bool ok = false;
+};
+const DeviceInfo& device_info();
+
+// 2-D bf16 tensor map: global [rows, cols] with row pitch ld_elems, box [box_rows, box_cols],
+// SWIZZLE_128B (box_cols * 2 bytes must be 128).
+int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols,
+                      uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
+// 4-D bf16 tensor map for NHWC activations: global [n, h, w, c], box [1, box_h, box_w, box_c].
+int make_tmap_4d_bf16(CUtensorMap* out, const void* gptr, uint64_t n, uint64_t h, uint64_t w,
+                      uint64_t c, uint32_t box_h, uint32_t box_w, uint32_t box_c);
+
+inline int cuda_err(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return B2F_OK;
+  fprintf(stderr, "[b2f] CUDA error in %s: %s\n", what, cudaGetErrorString(e));
+  return B2F_ERR_CUDA;
+}
+
+#define B2F_CHECK_LAUNCH(name)                              \
+  do {                                                      \
+    cudaError_t _e = cudaGetLastError();                    \
+    if (_e != cudaSuccess) return b2f::cuda_err(_e, name);  \
+  } while (0)
+
+}  // namespace b2f

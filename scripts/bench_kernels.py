@@ -1,0 +1,63 @@
+"""Developer micro-benchmark (not bench.py): times libb2f kernels against the library kernels the
+reference reaches (cuBLAS via torch.matmul, SDPA) on the same shapes.  Run under gpurun."""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from gpt_image_edit_b200 import ops  # noqa: E402
+
+
+def timeit(fn, iters=20, warmup=5, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ts = sorted(s.elapsed_time(e) for s, e in evs)
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="gemm")
+    args = ap.parse_args()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = []
+    if "gemm" in args.what:
+        shapes = [
+            (8736, 3072, 3072), (8736, 9216, 3072), (8736, 12288, 3072), (8736, 21504, 3072),
+            (8736, 3072, 12288), (8736, 3072, 15360), (8192, 8192, 8192), (544, 9216, 3072),
+            (28, 18432, 3072),
+        ]
+        for M, N, K in shapes:
+            x = torch.randn(M, K, device="cuda").bfloat16()
+            w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+            b = torch.randn(N, device="cuda").bfloat16()
+            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            t_b2f = timeit(lambda: ops.linear(x, w, b, out=out), flush=flush)
+            t_lib = timeit(lambda: torch.nn.functional.linear(x, w, b), flush=flush)
+            fl = 2.0 * M * N * K
+            r = dict(kind="gemm", M=M, N=N, K=K, b2f_ms=t_b2f, cublas_ms=t_lib,
+                     b2f_tflops=fl / t_b2f / 1e9, cublas_tflops=fl / t_lib / 1e9)
+            print(json.dumps(r), flush=True)
+            res.append(r)
+    Path("gpurun_out").mkdir(exist_ok=True)
+    with open(f"gpurun_out/bench_kernels_{args.what}.json", "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,93 @@
+"""GPU parity: b2f_gemm_bf16 (tcgen05) against a torch fp32 reference of the same op.
+
+Tolerance: inputs are bf16, accumulation fp32, one bf16 rounding on the output, so the result must
+match round_bf16(fp32 reference) to within 1 bf16 ulp of the largest magnitude in the row-block
+(rel-L2 <= 4e-3, i.e. about one bf16 rounding: 2^-8 = 3.9e-3).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)).item()
+
+
+def _mk(M, N, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    return x, w, b
+
+
+@pytest.mark.parametrize(
+    "M,N,K",
+    [
+        (128, 128, 64),      # single tile, single k-block
+        (128, 256, 128),
+        (256, 512, 256),
+        (544, 3072, 4096),   # context_embedder
+        (1000, 136, 72),     # ragged everything (M, N, K tails)
+        (8736, 3072, 3072),  # to_q at C1024
+        (28, 18432, 3072),   # hoisted AdaLN (weight streaming)
+        (4096, 64, 3072),    # proj_out
+        (8192, 3072, 64),    # x_embedder
+    ],
+)
+def test_gemm_bias(M, N, K):
+    from gpt_image_edit_b200 import ops
+
+    x, w, b = _mk(M, N, K)
+    out = ops.linear(x, w, b)
+    ref = (x.float() @ w.float().t() + b.float())
+    assert out.shape == (M, N)
+    err = _rel_l2(out, ref)
+    assert err < 4e-3, f"rel-L2 {err}"
+    # against the bf16-rounded reference nearly everything is identical
+    max_abs = (out.float() - ref).abs().max().item()
+    assert max_abs <= 2.0 ** -7 * ref.abs().max().item() + 1e-3
+
+
+def test_gemm_no_bias_and_pitched_output():
+    from gpt_image_edit_b200 import ops
+
+    x, w, _ = _mk(300, 256, 192, seed=1)
+    big = torch.zeros(300, 1024, device="cuda", dtype=torch.bfloat16)
+    view = big[:, 512:768]
+    ops.linear(x, w, None, out=view)
+    ref = x.float() @ w.float().t()
+    assert _rel_l2(view, ref) < 4e-3
+    assert big[:, :512].abs().max().item() == 0 and big[:, 768:].abs().max().item() == 0
+
+
+def test_gemm_gelu_silu():
+    from gpt_image_edit_b200 import ops
+
+    x, w, b = _mk(640, 768, 512, seed=2)
+    lin = (x.float() @ w.float().t() + b.float()).bfloat16()
+    out = ops.linear(x, w, b, epilogue=ops.EPI_GELU_TANH)
+    ref = torch.nn.functional.gelu(lin.float(), approximate="tanh")
+    assert _rel_l2(out, ref) < 6e-3
+    out = ops.linear(x, w, b, epilogue=ops.EPI_SILU)
+    ref = torch.nn.functional.silu(lin.float())
+    assert _rel_l2(out, ref) < 6e-3
+
+
+def test_gemm_gate_resid():
+    from gpt_image_edit_b200 import ops
+
+    B, S, N, K = 2, 300, 384, 256
+    x, w, b = _mk(B * S, N, K, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    resid = torch.randn(B * S, N, device="cuda", generator=g).bfloat16()
+    gate = torch.randn(B, N, device="cuda", generator=g).bfloat16()
+    out = ops.linear(x, w, b, epilogue=ops.EPI_GATE_RESID, resid=resid, gate=gate, rows_per_batch=S)
+    lin = (x.float() @ w.float().t() + b.float()).bfloat16()
+    ref = resid.float() + (gate.float().repeat_interleave(S, 0) * lin.float()).bfloat16().float()
+    assert _rel_l2(out, ref) < 6e-3
+    # in-place residual (resid aliases out)
+    r2 = resid.clone()
+    ops.linear(x, w, b, epilogue=ops.EPI_GATE_RESID, resid=r2, gate=gate, rows_per_batch=S, out=r2)
+    assert torch.equal(r2, out)
