@@ -40,6 +40,7 @@ _SIGNATURES = {
     "b2f_device_info": (_i32, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_size_t)]),
     "b2f_launch_count": (C.c_uint64, []),
     "b2f_gemm_bf16": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "b2f_attention_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, _i32, _vp]),
 }
 
 

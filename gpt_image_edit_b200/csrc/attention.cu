@@ -1,0 +1,365 @@
+// Fused non-causal / causal softmax attention for sm_100a, head_dim 128, bf16 in/out.
+//
+//   O[b, q, h, :] = softmax(Q[b, q, h, :] · K[b, :, hk, :]^T * scale) · V[b, :, hk, :]
+//
+// One CTA owns TWO 128-row query tiles of one (batch, head) and streams K/V in 128-row blocks:
+//   warp 0 (1 lane)  TMA producer: Q tiles once, K/V blocks through a 4-slot 32 KB ring
+//   warp 1 (1 lane)  tcgen05.mma issuer:  S_t = Q_t·K_j^T (SS),  O_t += P_t·V_j (A = P from TMEM)
+//   warps 2..5       softmax warpgroup of tile 0   } one thread per query row: tcgen05.ld S,
+//   warps 6..9       softmax warpgroup of tile 1   } online max/sum, exp2, P -> TMEM (bf16) over S
+// TMEM (512 cols): S0|P0 [0,128)  S1|P1 [128,256)  O0 [256,384)  O1 [384,512).
+// While one warpgroup runs softmax on its tile, the tensor core works on the other tile.
+// O is rescaled lazily (only when the running max grows by more than 2^8), by the softmax
+// warpgroup itself, between "S ready" (which also proves the previous P·V finished) and "P ready".
+//
+// Replaces F.scaled_dot_product_attention as reached by diffusers FluxAttnProcessor2_0
+// (reference call site univa/utils/flux_pipeline.py:1067) and flash_attn as reached
+// through transformers' attn_implementation="flash_attention_2" (univa/serve/cli.py:40).
+#include <atomic>
+#include <cmath>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace b2f {
+
+extern std::atomic<uint64_t> g_launch_count;
+
+namespace {
+
+constexpr int DH = 128;
+constexpr int BQ = 128;   // rows per query tile
+constexpr int BKV = 128;  // rows per K/V block
+constexpr int KV_SLOTS = 4;
+constexpr int TILE_BYTES = 128 * DH * 2;  // 32 KB
+constexpr int ATTN_THREADS = 320;
+constexpr int ATTN_SMEM = (2 + KV_SLOTS) * TILE_BYTES + 256 + 1024;
+
+struct AttnParams {
+  int B, H, Hkv, Sq, Skv;
+  float scale_log2;
+  int causal;
+  __nv_bfloat16* out;
+  long long ldo;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* q_smem = smem;                       // 2 tiles
+  uint8_t* kv_smem = smem + 2 * TILE_BYTES;     // KV_SLOTS tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + KV_SLOTS) * TILE_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // KV_SLOTS
+  uint64_t* kv_empty = kv_full + KV_SLOTS;
+  uint64_t* s_full = kv_empty + KV_SLOTS;  // 2
+  uint64_t* p_full = s_full + 2;           // 2
+  uint64_t* o_done = p_full + 2;           // 2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qpair = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.H / p.Hkv);
+  const int q0 = qpair * 2 * BQ;
+
+  // K/V blocks this CTA needs (causal: only up to its last query row; Sq == Skv assumed then)
+  int kv_len = p.Skv;
+  if (p.causal) kv_len = min(p.Skv, q0 + 2 * BQ);
+  const int n_kv = (kv_len + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KV_SLOTS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      for (int t = 0; t < 2; ++t)
+        for (int half = 0; half < 2; ++half)
+          tma_load_3d(q_smem + t * TILE_BYTES + half * (TILE_BYTES / 2), &tmQ, q_full,
+                      h * DH + half * 64, q0 + t * BQ, b);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
+          mbar_wait(&kv_empty[slot], phase ^ 1);
+          mbar_expect_tx(&kv_full[slot], TILE_BYTES);
+          uint8_t* dst = kv_smem + slot * TILE_BYTES;
+          const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
+          tma_load_3d(dst, tm, &kv_full[slot], hk * DH, j * BKV, b);
+          tma_load_3d(dst + TILE_BYTES / 2, tm, &kv_full[slot], hk * DH + 64, j * BKV, b);
+          if (++slot == KV_SLOTS) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0);  // B = K tile, K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 1);   // B = V tile, MN-major
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t kv_addr = smem_u32(kv_smem);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto issue_qk = [&](int t, uint32_t k_addr) {
+        const uint32_t d = tmem_base + uint32_t(t * 128);
+        const uint32_t qa = q_addr + t * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          // dh 0..63 live in the first 16 KB sub-tile, 64..127 in the second
+          const uint32_t off = (k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32;
+          umma_ss(d, make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(k_addr + off, 16, 1024),
+                  idesc_qk, k != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, uint32_t v_addr, bool first) {
+        const uint32_t d = tmem_base + 256 + uint32_t(t * 128);
+        const uint32_t pa = tmem_base + uint32_t(t * 128);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          // 16 kv rows per step = 2 KB; N (dh) halves are 16 KB apart (LBO), 8-row groups 1 KB (SBO)
+          umma_ts(d, pa + k * 8, make_sdesc_sw128(v_addr + k * 2048, TILE_BYTES / 2, 1024),
+                  idesc_pv, (first && k == 0) ? 0u : 1u);
+        }
+      };
+      auto advance = [&]() {
+        if (++slot == KV_SLOTS) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      mbar_wait(q_full, 0);
+      // prologue: S_t = Q_t K_0^T for both tiles
+      mbar_wait(&kv_full[slot], phase);
+      tc_fence_after();
+      {
+        const uint32_t k_addr = kv_addr + slot * TILE_BYTES;
+        issue_qk(0, k_addr);
+        umma_commit(&s_full[0]);
+        issue_qk(1, k_addr);
+        umma_commit(&s_full[1]);
+        umma_commit(&kv_empty[slot]);
+        advance();
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const int v_slot = slot;
+        const uint32_t v_phase = phase;
+        advance();
+        const int k_slot = slot;  // K_{j+1} (if any)
+        const uint32_t k_phase = phase;
+        const bool more = (j + 1 < n_kv);
+        if (more) advance();
+        mbar_wait(&kv_full[v_slot], v_phase);
+        const uint32_t v_addr = kv_addr + v_slot * TILE_BYTES;
+        const uint32_t k_addr = kv_addr + k_slot * TILE_BYTES;
+        // tile 0
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, v_addr, j == 0);
+        if (more) {
+          mbar_wait(&kv_full[k_slot], k_phase);
+          tc_fence_after();
+          issue_qk(0, k_addr);
+          umma_commit(&s_full[0]);
+        }
+        // tile 1
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, v_addr, j == 0);
+        umma_commit(&kv_empty[v_slot]);
+        if (more) {
+          issue_qk(1, k_addr);
+          umma_commit(&s_full[1]);
+          umma_commit(&kv_empty[k_slot]);
+        }
+      }
+      umma_commit(&o_done[0]);
+      umma_commit(&o_done[1]);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + t * BQ + row_in_tile;  // query index inside the sequence
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_addr + uint32_t(t * 128);
+    const uint32_t o_tmem = tmem_base + lane_addr + 256 + uint32_t(t * 128);
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t sr[128];
+      B2F_TMEM_LD_X32(s_tmem + 0, (sr + 0));
+      B2F_TMEM_LD_X32(s_tmem + 32, (sr + 32));
+      B2F_TMEM_LD_X32(s_tmem + 64, (sr + 64));
+      B2F_TMEM_LD_X32(s_tmem + 96, (sr + 96));
+      tmem_wait_ld();
+      const int kv0 = j * BKV;
+      const bool need_mask = (kv0 + BKV > p.Skv) || (p.causal && kv0 + BKV > q0 + t * BQ);
+      if (need_mask) {
+        const int limit = p.causal ? min(p.Skv, q_row + 1) : p.Skv;
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (kv0 + c >= limit) sr[c] = 0xff800000u;  // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      // lazy rescale: keep the stale max unless it grew by more than 2^8 (P stays < 256)
+      const bool grow = (m_new - m) > 8.0f;
+      const float m_use = grow ? m_new : m;
+      const float alpha = grow ? ex2(m - m_use) : 1.0f;
+      const float neg_m = (m_use == -INFINITY) ? 0.f : -m_use;  // fully masked row (causal tail)
+      float sum = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float p0 = ex2(fmaf(__uint_as_float(sr[half * 64 + 2 * c]), p.scale_log2, neg_m));
+          const float p1 =
+              ex2(fmaf(__uint_as_float(sr[half * 64 + 2 * c + 1]), p.scale_log2, neg_m));
+          sum += p0 + p1;
+          pk[c] = pack_bf16x2(p0, p1);
+        }
+        B2F_TMEM_ST_X32(s_tmem + half * 32, pk);
+      }
+      l = l * alpha + sum;
+      m = m_use;
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        // S_t(j) being ready proves P_t·V_{j-1} completed, so O_t is stable here
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t o[32];
+          B2F_TMEM_LD_X32(o_tmem + c0, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          B2F_TMEM_ST_X32(o_tmem + c0, o);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+    // ---------------------------------------------------------------- epilogue: O / l -> bf16
+    mbar_wait(&o_done[t], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const bool row_ok = q_row < p.Sq;
+    __nv_bfloat16* out_row =
+        p.out + ((long long)b * p.Sq + q_row) * p.ldo + (long long)h * DH;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t o[32];
+      __syncwarp();
+      B2F_TMEM_LD_X32(o_tmem + c0, o);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(out_row + c0 + g * 8) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                  int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                  int head_dim, float scale, int causal, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!q || !k || !v || !out || B <= 0 || H <= 0 || Hkv <= 0 || Sq <= 0 || Skv <= 0)
+    return B2F_ERR_INVALID;
+  if (head_dim != DH) return B2F_ERR_UNSUPPORTED;
+  if (H % Hkv) return B2F_ERR_INVALID;
+  if (causal && Sq != Skv) return B2F_ERR_UNSUPPORTED;
+  if ((ldq & 7) || (ldk & 7) || (ldv & 7) || (ldo & 7)) return B2F_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return B2F_ERR_ALIGN;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+    if (e != cudaSuccess) return cuda_err(e, "attention smem attribute");
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = make_tmap_3d_rows(&tmQ, q, (uint64_t)H * DH, Sq, B, ldq, (uint64_t)Sq * ldq);
+  if (rc) return rc;
+  rc = make_tmap_3d_rows(&tmK, k, (uint64_t)Hkv * DH, Skv, B, ldk, (uint64_t)Skv * ldk);
+  if (rc) return rc;
+  rc = make_tmap_3d_rows(&tmV, v, (uint64_t)Hkv * DH, Skv, B, ldv, (uint64_t)Skv * ldv);
+  if (rc) return rc;
+  AttnParams p{};
+  p.B = B;
+  p.H = H;
+  p.Hkv = Hkv;
+  p.Sq = Sq;
+  p.Skv = Skv;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
+  attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("attn_fwd_kernel");
+  return B2F_OK;
+}
+
+}  // namespace b2f

@@ -8,6 +8,9 @@ extern std::atomic<uint64_t> g_launch_count;
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
               int64_t ldc, int M, int N, int K, int epilogue, const void* resid, int64_t ldr,
               const void* gate, int64_t gate_ld, int rows_per_batch, cudaStream_t stream);
+int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                  int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                  int head_dim, float scale, int causal, cudaStream_t stream);
 }  // namespace b2f
 
 extern "C" {
@@ -53,6 +56,13 @@ int b2f_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
                   b2f_stream_t stream) {
   return b2f::gemm_bf16(A, lda, W, ldw, bias, out, ldc, M, N, K, epilogue, resid, ldr, gate,
                         gate_ld, rows_per_batch, static_cast<cudaStream_t>(stream));
+}
+
+int b2f_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                      int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                      int head_dim, float scale, int causal, b2f_stream_t stream) {
+  return b2f::attention_fwd(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale,
+                            causal, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,277 @@
+// HBM-bound fused row kernels of the MMDiT block (SURVEY.md §2b "ATen elementwise / norm kernels").
+// Each replaces a chain of separate torch-eager kernels in diffusers; every intermediate that torch
+// would have rounded to bf16 is rounded here too, so results track the reference's rounding chain.
+#include <atomic>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace b2f {
+
+extern std::atomic<uint64_t> g_launch_count;
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_bf16x2(w[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  q.x = pack_bf16x2(f[0], f[1]);
+  q.y = pack_bf16x2(f[2], f[3]);
+  q.z = pack_bf16x2(f[4], f[5]);
+  q.w = pack_bf16x2(f[6], f[7]);
+  return q;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AdaLN modulate:  y = bf16( bf16( bf16(LN(x)) * bf16(1 + scale[b]) ) + shift[b] )
+// LN: no affine, eps, biased variance, fp32 statistics (torch.nn.functional.layer_norm on bf16).
+// One warp per row, the row lives in registers (D <= 256*MAXC), two-pass statistics.
+// Algorithmic bytes per row: 2*D*2 (+ 2*D*2 of scale/shift shared by all rows of a batch item).
+constexpr int LN_MAXC = 20;  // D up to 5120
+
+struct LnModParams {
+  const __nv_bfloat16* x;
+  long long ldx, x_batch_stride;
+  const __nv_bfloat16* scale;
+  const __nv_bfloat16* shift;
+  long long mod_ld;  // stride between batch items of scale/shift
+  __nv_bfloat16* out;
+  long long ldo, out_batch_stride;
+  int batch, rows, D;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long grow = (long long)blockIdx.x * 8 + warp;
+  if (grow >= (long long)p.batch * p.rows) return;
+  const int b = int(grow / p.rows);
+  const int r = int(grow - (long long)b * p.rows);
+  const __nv_bfloat16* xr = p.x + b * p.x_batch_stride + r * p.ldx;
+  __nv_bfloat16* orow = p.out + b * p.out_batch_stride + r * p.ldo;
+  const int nchunk = p.D >> 8;
+  float v[LN_MAXC][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    if (c < nchunk) {
+      const uint4 q = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
+      unpack8(q, v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    }
+  }
+  const float mean = warp_sum(s) / float(p.D);
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    if (c < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / float(p.D) + p.eps);
+  const __nv_bfloat16* sc = p.scale + (long long)b * p.mod_ld;
+  const __nv_bfloat16* sh = p.shift + (long long)b * p.mod_ld;
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    if (c < nchunk) {
+      float a[8], h[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sc + c * 256 + lane * 8)), a);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(sh + c * 256 + lane * 8)), h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = bf16r((v[c][j] - mean) * rstd);
+        o[j] = bf16r(y * bf16r(1.0f + a[j])) + h[j];
+      }
+      *reinterpret_cast<uint4*>(orow + c * 256 + lane * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-head RMSNorm (eps, weight) + interleaved-pair RoPE, in place on the Q and K column blocks of
+// a fused QKV projection buffer [batch, S, >= 2*H*128]:
+//   y = bf16(x * rsqrt(mean(x^2) + eps));  z = bf16(y * w);  out = bf16(z*cos + rot(z)*sin)
+// (diffusers RMSNorm + apply_rotary_emb).  Half a warp owns one 128-wide head vector
+// (8 elements = 4 RoPE pairs per lane); lanes 0-15 do Q, lanes 16-31 do K of the same head.
+// The first `n_a` tokens of every batch item use weight set A (norm_added_q/k: text tokens), the
+// rest weight set B (norm_q/k).
+// Algorithmic bytes per token: 2 (Q,K) * H*128 * 2 B read + the same written.
+struct NormRopeParams {
+  __nv_bfloat16* q;
+  __nv_bfloat16* k;
+  long long ld, batch_stride;
+  const __nv_bfloat16 *wq_a, *wk_a, *wq_b, *wk_b;
+  const float* cos;  // [S, 128]
+  const float* sin;
+  int batch, S, H, n_a;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const NormRopeParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tok = (long long)blockIdx.x * 8 + warp;
+  if (tok >= (long long)p.batch * p.S) return;
+  const int b = int(tok / p.S);
+  const int s = int(tok - (long long)b * p.S);
+  const int is_k = lane >> 4;
+  const int l16 = lane & 15;
+  __nv_bfloat16* base = (is_k ? p.k : p.q) + b * p.batch_stride + s * p.ld + l16 * 8;
+  const bool set_a = s < p.n_a;
+  const __nv_bfloat16* wptr = is_k ? (set_a ? p.wk_a : p.wk_b) : (set_a ? p.wq_a : p.wq_b);
+  float w[8], cs[8], sn[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(wptr + l16 * 8)), w);
+  {
+    const float4* c4 = reinterpret_cast<const float4*>(p.cos + (long long)s * 128 + l16 * 8);
+    const float4* s4 = reinterpret_cast<const float4*>(p.sin + (long long)s * 128 + l16 * 8);
+    const float4 c0 = __ldg(c4), c1 = __ldg(c4 + 1), s0 = __ldg(s4), s1 = __ldg(s4 + 1);
+    cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w;
+    cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+    sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w;
+    sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
+  }
+#pragma unroll 4
+  for (int h = 0; h < p.H; ++h) {
+    __nv_bfloat16* ptr = base + h * 128;
+    float x[8];
+    unpack8(*reinterpret_cast<const uint4*>(ptr), x);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += x[j] * x[j];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float r = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+    float z[8], o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = bf16r(bf16r(x[j] * r) * w[j]);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      o8[j] = z[j] * cs[j] - z[j + 1] * sn[j];
+      o8[j + 1] = z[j + 1] * cs[j + 1] + z[j] * sn[j + 1];
+    }
+    *reinterpret_cast<uint4*>(ptr) = pack8(o8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flow-matching Euler update (diffusers FlowMatchEulerDiscreteScheduler.step):
+//   x <- bf16( float(x) + float( bf16(dt * v) ) )      with dt = sigma[i+1] - sigma[i] in fp32
+// v is the model output restricted to the first `cols`... both are [rows, cols] with pitches.
+struct EulerParams {
+  __nv_bfloat16* x;
+  long long ldx;
+  const __nv_bfloat16* v;
+  long long ldv;
+  long long rows;
+  int cols;
+  float dt;
+};
+__global__ void __launch_bounds__(256) euler_step_kernel(const EulerParams p) {
+  const int vec_per_row = p.cols >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.rows * vec_per_row) return;
+  const long long r = i / vec_per_row;
+  const int c = int(i - r * vec_per_row) * 8;
+  float x[8], v[8];
+  unpack8(*reinterpret_cast<const uint4*>(p.x + r * p.ldx + c), x);
+  unpack8(*reinterpret_cast<const uint4*>(p.v + r * p.ldv + c), v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = x[j] + bf16r(p.dt * v[j]);
+  *reinterpret_cast<uint4*>(p.x + r * p.ldx + c) = pack8(x);
+}
+
+// y = silu(x) elementwise on a small [rows, cols] bf16 matrix (AdaLN: linear(silu(temb))).
+__global__ void __launch_bounds__(256) silu_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float f[8];
+  unpack8(reinterpret_cast<const uint4*>(x)[i], f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+  reinterpret_cast<uint4*>(y)[i] = pack8(f);
+}
+
+}  // namespace
+
+int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
+                const void* shift, int64_t mod_ld, void* out, int64_t ldo, int64_t out_batch_stride,
+                int batch, int rows, int D, float eps, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!x || !scale || !shift || !out || batch <= 0 || rows <= 0) return B2F_ERR_INVALID;
+  if (D <= 0 || (D & 255) || D > 256 * LN_MAXC) return B2F_ERR_UNSUPPORTED;
+  if ((ldx & 7) || (ldo & 7) || (mod_ld & 7) || (x_batch_stride & 7) || (out_batch_stride & 7))
+    return B2F_ERR_ALIGN;
+  LnModParams p{static_cast<const __nv_bfloat16*>(x), ldx, x_batch_stride,
+                static_cast<const __nv_bfloat16*>(scale), static_cast<const __nv_bfloat16*>(shift),
+                mod_ld, static_cast<__nv_bfloat16*>(out), ldo, out_batch_stride, batch, rows, D, eps};
+  const long long total = (long long)batch * rows;
+  ln_modulate_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("ln_modulate_kernel");
+  return B2F_OK;
+}
+
+int rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void* wq_a,
+                 const void* wk_a, const void* wq_b, const void* wk_b, const float* cos,
+                 const float* sin, int batch, int S, int H, int head_dim, int n_a, float eps,
+                 cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!q || !k || !wq_b || !wk_b || !cos || !sin || batch <= 0 || S <= 0 || H <= 0)
+    return B2F_ERR_INVALID;
+  if (head_dim != 128) return B2F_ERR_UNSUPPORTED;
+  if (n_a > 0 && (!wq_a || !wk_a)) return B2F_ERR_INVALID;
+  if ((ld & 7) || (batch_stride & 7)) return B2F_ERR_ALIGN;
+  NormRopeParams p{static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k), ld, batch_stride,
+                   static_cast<const __nv_bfloat16*>(wq_a), static_cast<const __nv_bfloat16*>(wk_a),
+                   static_cast<const __nv_bfloat16*>(wq_b), static_cast<const __nv_bfloat16*>(wk_b),
+                   cos, sin, batch, S, H, n_a, eps};
+  const long long total = (long long)batch * S;
+  rmsnorm_rope_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("rmsnorm_rope_kernel");
+  return B2F_OK;
+}
+
+int euler_step(void* x, int64_t ldx, const void* v, int64_t ldv, int64_t rows, int cols, float dt,
+               cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!x || !v || rows <= 0 || cols <= 0) return B2F_ERR_INVALID;
+  if ((cols & 7) || (ldx & 7) || (ldv & 7)) return B2F_ERR_ALIGN;
+  EulerParams p{static_cast<__nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(v), ldv, rows,
+                cols, dt};
+  const long long n = rows * (cols >> 3);
+  euler_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("euler_step_kernel");
+  return B2F_OK;
+}
+
+int silu(const void* x, void* y, int64_t n, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!x || !y || n <= 0 || (n & 7)) return B2F_ERR_INVALID;
+  const long long n8 = n >> 3;
+  silu_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n8);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("silu_kernel");
+  return B2F_OK;
+}
+
+}  // namespace b2f

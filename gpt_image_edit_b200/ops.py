@@ -58,3 +58,35 @@ def linear(
         "b2f_gemm_bf16",
     )
     return out if x.dim() == 2 else out.reshape(*x.shape[:-1], N)
+
+
+def attention(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    *,
+    out: torch.Tensor | None = None,
+    causal: bool = False,
+    scale: float | None = None,
+) -> torch.Tensor:
+    """softmax(q k^T * scale) v via b2f_attention_fwd.  q [B,Sq,H,128], k/v [B,Skv,Hkv,128] as
+    (possibly strided) views whose last two dims are contiguous; out [B,Sq,H*128]."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, n)
+        if t.dim() != 4 or t.stride(2) != t.shape[3] or t.stride(0) != t.shape[1] * t.stride(1):
+            raise _lib.B2FError(f"{n}: expected a [B,S,H,dh] view with contiguous heads and batch stride S*ld")
+    B, Sq, H, dh = q.shape
+    Skv, Hkv = k.shape[1], k.shape[2]
+    if out is None:
+        out = torch.empty((B, Sq, H * dh), device=q.device, dtype=torch.bfloat16)
+    _req(out, "out")
+    if scale is None:
+        scale = dh ** -0.5
+    check(
+        _lib.lib.b2f_attention_fwd(
+            ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1), ptr(out), out.stride(1),
+            B, H, Hkv, Sq, Skv, dh, float(scale), int(causal), stream_ptr(),
+        ),
+        "b2f_attention_fwd",
+    )
+    return out

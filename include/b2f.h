@@ -64,6 +64,25 @@ int b2f_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
                   int64_t ldr, const void* gate, int64_t gate_ld, int rows_per_batch,
                   b2f_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused softmax attention, head_dim 128:  O = softmax(Q K^T * scale [+ causal mask]) V.
+ * tcgen05 QK^T and PV with S/P/O in TMEM, K/V streamed by TMA, online softmax (FA-style).
+ * Replaces F.scaled_dot_product_attention in diffusers' FluxAttnProcessor2_0 (joint [txt;img]
+ * attention of FluxTransformerBlock / FluxSingleTransformerBlock; reference call
+ * site univa/utils/flux_pipeline.py:1067) and flash_attn reached through
+ * attn_implementation="flash_attention_2" (univa/serve/cli.py:40) for the Qwen2.5-VL prefill.
+ *
+ * Layout: token-major.  q points at element [b=0, s=0, head 0, 0]; head h of token s of batch b
+ * is at q + (b*Sq + s)*ldq + h*128 (same for k, v with Skv, ldk/ldv and Hkv heads; GQA maps
+ * query head h to kv head h / (H/Hkv)).  out is [B, Sq, H*128] with row pitch ldo.  This lets
+ * Q/K/V be column slices of one fused QKV projection buffer and lets out be a column slice of
+ * the single-stream [attn | mlp] buffer — no transposes or concatenations.
+ * causal != 0 requires Sq == Skv.
+ */
+int b2f_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                      int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                      int head_dim, float scale, int causal, b2f_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,30 @@ def main():
                      b2f_tflops=fl / t_b2f / 1e9, cublas_tflops=fl / t_lib / 1e9)
             print(json.dumps(r), flush=True)
             res.append(r)
+    if "attn" in args.what:
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        for (B, H, S) in [(1, 24, 8736), (1, 24, 2592), (4, 24, 8736)]:
+            qkv = torch.randn(B, S, 3 * H * 128, device="cuda").bfloat16()
+            q = qkv[:, :, : H * 128].unflatten(-1, (H, 128))
+            k = qkv[:, :, H * 128 : 2 * H * 128].unflatten(-1, (H, 128))
+            v = qkv[:, :, 2 * H * 128 :].unflatten(-1, (H, 128))
+            out = torch.empty(B, S, H * 128, device="cuda", dtype=torch.bfloat16)
+            t_b2f = timeit(lambda: ops.attention(q, k, v, out=out), iters=10, warmup=3, flush=flush)
+            fl = 4.0 * B * H * S * S * 128
+            r = dict(kind="attn", B=B, H=H, S=S, b2f_ms=t_b2f, b2f_tflops=fl / t_b2f / 1e9)
+            qt, kt, vt = (x.permute(0, 2, 1, 3).contiguous() for x in (q, k, v))
+            for name, be in (("flash", SDPBackend.FLASH_ATTENTION), ("cudnn", SDPBackend.CUDNN_ATTENTION),
+                             ("efficient", SDPBackend.EFFICIENT_ATTENTION)):
+                try:
+                    with sdpa_kernel(be):
+                        t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt),
+                                   iters=10, warmup=3, flush=flush)
+                    r[f"sdpa_{name}_ms"] = t
+                    r[f"sdpa_{name}_tflops"] = fl / t / 1e9
+                except Exception as e:  # backend unavailable for this shape
+                    r[f"sdpa_{name}_err"] = str(e)[:80]
+            print(json.dumps(r), flush=True)
+            res.append(r)
     Path("gpurun_out").mkdir(exist_ok=True)
     with open(f"gpurun_out/bench_kernels_{args.what}.json", "w") as f:
         json.dump(res, f, indent=1)
