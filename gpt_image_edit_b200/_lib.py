@@ -34,12 +34,34 @@ lib = _load()
 
 _vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int
 
+class FluxCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "num_heads", "head_dim", "num_double", "num_single", "in_channels", "out_channels",
+        "joint_dim", "pooled_dim", "guidance_embeds", "mlp_ratio")]
+
+
 _SIGNATURES = {
     "b2f_strerror": (C.c_char_p, [_i32]),
     "b2f_version": (_i32, []),
     "b2f_device_info": (_i32, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_size_t)]),
     "b2f_launch_count": (C.c_uint64, []),
-    "b2f_gemm_bf16": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "b2f_gemm_bf16": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "b2f_ln_modulate": (_i32, [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, C.c_float, _vp]),
+    "b2f_rmsnorm_rope": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, C.c_float, _vp]),
+    "b2f_euler_step": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, C.c_float, _vp]),
+    "b2f_silu": (_i32, [_vp, _vp, _i64, _vp]),
+    "b2f_rope_tables": (_i32, [_vp, _i32, C.POINTER(_i32), C.c_double, _vp, _vp, _vp]),
+    "b2f_flux_create": (_i32, [C.POINTER(_vp), _vp]),
+    "b2f_flux_destroy": (None, [_vp]),
+    "b2f_flux_bind_weight": (_i32, [_vp, C.c_char_p, _vp, _i64]),
+    "b2f_flux_finalize": (_i32, [_vp]),
+    "b2f_flux_mod_width": (_i64, [_vp]),
+    "b2f_flux_set_rope": (_i32, [_vp, _vp, _vp, _i32]),
+    "b2f_flux_workspace_bytes": (C.c_size_t, [_vp, _i32, _i32, _i32]),
+    "b2f_flux_temb_workspace_bytes": (C.c_size_t, [_vp, _i32]),
+    "b2f_flux_temb": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "b2f_flux_modulation": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "b2f_flux_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, C.c_size_t, _i32, _i32, _vp]),
     "b2f_attention_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, _i32, _vp]),
 }
 

@@ -5,9 +5,22 @@
 
 namespace b2f {
 extern std::atomic<uint64_t> g_launch_count;
-int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
-              int64_t ldc, int M, int N, int K, int epilogue, const void* resid, int64_t ldr,
-              const void* gate, int64_t gate_ld, int rows_per_batch, cudaStream_t stream);
+int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
+              const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M, int N,
+              int K, int epilogue, const void* resid, int64_t ldr, int64_t resid_bs, const void* gate,
+              int64_t gate_ld, cudaStream_t stream);
+int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
+                const void* shift, int64_t mod_ld, void* out, int64_t ldo, int64_t out_batch_stride,
+                int batch, int rows, int D, float eps, cudaStream_t stream);
+int rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void* wq_a,
+                 const void* wk_a, const void* wq_b, const void* wk_b, const float* cos,
+                 const float* sin, int batch, int S, int H, int head_dim, int n_a, float eps,
+                 cudaStream_t stream);
+int euler_step(void* x, int64_t ldx, const void* v, int64_t ldv, int64_t rows, int cols, float dt,
+               cudaStream_t stream);
+int silu(const void* x, void* y, int64_t n, cudaStream_t stream);
+int rope_tables(const float* ids, int S, const int* axes_dim, double theta, float* cos, float* sin,
+                cudaStream_t stream);
 int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                   int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
                   int head_dim, float scale, int causal, cudaStream_t stream);
@@ -50,12 +63,44 @@ int b2f_device_info(int* num_sms, int* cc_major, int* cc_minor, size_t* smem_opt
 
 uint64_t b2f_launch_count(void) { return b2f::g_launch_count.load(); }
 
-int b2f_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
-                  void* out, int64_t ldc, int M, int N, int K, int epilogue, const void* resid,
-                  int64_t ldr, const void* gate, int64_t gate_ld, int rows_per_batch,
+int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
+                  const void* bias, void* out, int64_t ldc, int64_t out_batch_stride, int batch,
+                  int M, int N, int K, int epilogue, const void* resid, int64_t ldr,
+                  int64_t resid_batch_stride, const void* gate, int64_t gate_ld,
                   b2f_stream_t stream) {
-  return b2f::gemm_bf16(A, lda, W, ldw, bias, out, ldc, M, N, K, epilogue, resid, ldr, gate,
-                        gate_ld, rows_per_batch, static_cast<cudaStream_t>(stream));
+  return b2f::gemm_bf16(A, lda, a_batch_stride, W, ldw, bias, out, ldc, out_batch_stride, batch, M,
+                        N, K, epilogue, resid, ldr, resid_batch_stride, gate, gate_ld,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int b2f_ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
+                    const void* shift, int64_t mod_ld, void* out, int64_t ldo,
+                    int64_t out_batch_stride, int batch, int rows, int D, float eps,
+                    b2f_stream_t stream) {
+  return b2f::ln_modulate(x, ldx, x_batch_stride, scale, shift, mod_ld, out, ldo, out_batch_stride,
+                          batch, rows, D, eps, static_cast<cudaStream_t>(stream));
+}
+
+int b2f_rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void* wq_a,
+                     const void* wk_a, const void* wq_b, const void* wk_b, const float* cos,
+                     const float* sin, int batch, int S, int H, int head_dim, int n_a, float eps,
+                     b2f_stream_t stream) {
+  return b2f::rmsnorm_rope(q, k, ld, batch_stride, wq_a, wk_a, wq_b, wk_b, cos, sin, batch, S, H,
+                           head_dim, n_a, eps, static_cast<cudaStream_t>(stream));
+}
+
+int b2f_euler_step(void* x, int64_t ldx, const void* v, int64_t ldv, int64_t rows, int cols,
+                   float dt, b2f_stream_t stream) {
+  return b2f::euler_step(x, ldx, v, ldv, rows, cols, dt, static_cast<cudaStream_t>(stream));
+}
+
+int b2f_rope_tables(const float* ids, int S, const int* axes_dim, double theta, float* cos,
+                    float* sin, b2f_stream_t stream) {
+  return b2f::rope_tables(ids, S, axes_dim, theta, cos, sin, static_cast<cudaStream_t>(stream));
+}
+
+int b2f_silu(const void* x, void* y, int64_t n, b2f_stream_t stream) {
+  return b2f::silu(x, y, n, static_cast<cudaStream_t>(stream));
 }
 
 int b2f_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

@@ -54,19 +54,20 @@ struct LnModParams {
   float eps;
 };
 
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
+template <int MAXC>
+__global__ void __launch_bounds__(128) ln_modulate_kernel(const LnModParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long grow = (long long)blockIdx.x * 8 + warp;
+  const long long grow = (long long)blockIdx.x * 4 + warp;
   if (grow >= (long long)p.batch * p.rows) return;
   const int b = int(grow / p.rows);
   const int r = int(grow - (long long)b * p.rows);
   const __nv_bfloat16* xr = p.x + b * p.x_batch_stride + r * p.ldx;
   __nv_bfloat16* orow = p.out + b * p.out_batch_stride + r * p.ldo;
   const int nchunk = p.D >> 8;
-  float v[LN_MAXC][8];
+  float v[MAXC][8];
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
+  for (int c = 0; c < MAXC; ++c) {
     if (c < nchunk) {
       const uint4 q = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
       unpack8(q, v[c]);
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
   const float mean = warp_sum(s) / float(p.D);
   float ss = 0.f;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
+  for (int c = 0; c < MAXC; ++c) {
     if (c < nchunk) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
   const __nv_bfloat16* sc = p.scale + (long long)b * p.mod_ld;
   const __nv_bfloat16* sh = p.shift + (long long)b * p.mod_ld;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
+  for (int c = 0; c < MAXC; ++c) {
     if (c < nchunk) {
       float a[8], h[8], o[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(sc + c * 256 + lane * 8)), a);
@@ -172,7 +173,9 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const NormRopeParams 
 
 // ------------------------------------------------------------------------------------------------
 // Flow-matching Euler update (diffusers FlowMatchEulerDiscreteScheduler.step):
-//   x <- bf16( float(x) + float( bf16(dt * v) ) )      with dt = sigma[i+1] - sigma[i] in fp32
+//   x <- bf16( float(x) + float( bf16( bf16(dt) * v ) ) )   with dt = sigma[i+1] - sigma[i] in fp32.
+// torch evaluates `dt * model_output` (0-dim fp32 tensor x bf16 tensor) in the common dtype bf16:
+// the 0-dim operand is cast to bf16 FIRST, the product is rounded to bf16, the sum is fp32.
 // v is the model output restricted to the first `cols`... both are [rows, cols] with pitches.
 struct EulerParams {
   __nv_bfloat16* x;
@@ -192,8 +195,9 @@ __global__ void __launch_bounds__(256) euler_step_kernel(const EulerParams p) {
   float x[8], v[8];
   unpack8(*reinterpret_cast<const uint4*>(p.x + r * p.ldx + c), x);
   unpack8(*reinterpret_cast<const uint4*>(p.v + r * p.ldv + c), v);
+  const float dtb = bf16r(p.dt);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = x[j] + bf16r(p.dt * v[j]);
+  for (int j = 0; j < 8; ++j) x[j] = x[j] + bf16r(dtb * v[j]);
   *reinterpret_cast<uint4*>(p.x + r * p.ldx + c) = pack8(x);
 }
 
@@ -208,7 +212,105 @@ __global__ void __launch_bounds__(256) silu_kernel(const __nv_bfloat16* x, __nv_
   reinterpret_cast<uint4*>(y)[i] = pack8(f);
 }
 
+// Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[r] = [cos(t*f) | sin(t*f)],
+// f_j = exp(-ln(10000) * j / 128), fp32 math, bf16 output.
+__global__ void __launch_bounds__(128) temb_sinusoid_kernel(const float* t, __nv_bfloat16* out, int rows) {
+  const int r = blockIdx.x, j = threadIdx.x;
+  if (r >= rows) return;
+  const float f = expf(-9.210340371976184f * (float)j / 128.0f);
+  const float a = t[r] * f;
+  out[(long long)r * 256 + j] = __float2bfloat16_rn(cosf(a));
+  out[(long long)r * 256 + 128 + j] = __float2bfloat16_rn(sinf(a));
+}
+
+// temb = bf16(bf16(t + g) + txt);  silu_temb = bf16(silu(temb))   (CombinedTimestepGuidanceTextProjEmbeddings)
+__global__ void __launch_bounds__(256) temb_combine_kernel(const __nv_bfloat16* t, const __nv_bfloat16* g,
+                                                           const __nv_bfloat16* txt, __nv_bfloat16* temb,
+                                                           __nv_bfloat16* silu_temb, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float a[8], b[8], c[8], o[8], s8[8];
+  unpack8(reinterpret_cast<const uint4*>(t)[i], a);
+  unpack8(reinterpret_cast<const uint4*>(txt)[i], c);
+  if (g) {
+    unpack8(reinterpret_cast<const uint4*>(g)[i], b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = bf16r(a[j] + b[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o[j] = bf16r(a[j] + c[j]);
+    s8[j] = o[j] / (1.0f + __expf(-o[j]));
+  }
+  reinterpret_cast<uint4*>(temb)[i] = pack8(o);
+  reinterpret_cast<uint4*>(silu_temb)[i] = pack8(s8);
+}
+
+// FluxPosEmbed: per axis a with dim D_a, pair i: w = theta^(-2i/D_a) in float64,
+// ang = pos * w, cos/sin in float64 -> fp32, each repeated twice (repeat_interleave(2)).
+struct RopeTabParams {
+  const float* ids;  // [S, 3]
+  float* cos;
+  float* sin;  // [S, 128]
+  int S;
+  int axes[3];
+  double theta;
+};
+__global__ void __launch_bounds__(64) rope_tables_kernel(const RopeTabParams p) {
+  const int s = blockIdx.x, i = threadIdx.x;  // pair index 0..63
+  if (s >= p.S) return;
+  int a = 0, li = i;
+  while (a < 2 && li >= p.axes[a] / 2) {
+    li -= p.axes[a] / 2;
+    ++a;
+  }
+  const double dim = (double)p.axes[a];
+  const double w = 1.0 / pow(p.theta, (double)(2 * li) / dim);
+  const double ang = (double)p.ids[s * 3 + a] * w;
+  const float c = (float)cos(ang), sn = (float)sin(ang);
+  p.cos[(long long)s * 128 + 2 * i] = c;
+  p.cos[(long long)s * 128 + 2 * i + 1] = c;
+  p.sin[(long long)s * 128 + 2 * i] = sn;
+  p.sin[(long long)s * 128 + 2 * i + 1] = sn;
+}
+
 }  // namespace
+
+int rope_tables(const float* ids, int S, const int* axes_dim, double theta, float* cos, float* sin,
+                cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!ids || !cos || !sin || !axes_dim || S <= 0) return B2F_ERR_INVALID;
+  if (axes_dim[0] + axes_dim[1] + axes_dim[2] != 128 || (axes_dim[0] | axes_dim[1] | axes_dim[2]) & 1)
+    return B2F_ERR_UNSUPPORTED;
+  RopeTabParams p{ids, cos, sin, S, {axes_dim[0], axes_dim[1], axes_dim[2]}, theta};
+  rope_tables_kernel<<<S, 64, 0, stream>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("rope_tables_kernel");
+  return B2F_OK;
+}
+
+int temb_sinusoid(const float* t, void* out, int rows, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!t || !out || rows <= 0) return B2F_ERR_INVALID;
+  temb_sinusoid_kernel<<<rows, 128, 0, stream>>>(t, static_cast<__nv_bfloat16*>(out), rows);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("temb_sinusoid_kernel");
+  return B2F_OK;
+}
+
+int temb_combine(const void* t, const void* g, const void* txt, void* temb, void* silu_temb,
+                 int64_t n, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!t || !txt || !temb || !silu_temb || n <= 0 || (n & 7)) return B2F_ERR_INVALID;
+  const long long n8 = n >> 3;
+  temb_combine_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(t), static_cast<const __nv_bfloat16*>(g),
+      static_cast<const __nv_bfloat16*>(txt), static_cast<__nv_bfloat16*>(temb),
+      static_cast<__nv_bfloat16*>(silu_temb), n8);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("temb_combine_kernel");
+  return B2F_OK;
+}
 
 int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
                 const void* shift, int64_t mod_ld, void* out, int64_t ldo, int64_t out_batch_stride,
@@ -222,7 +324,13 @@ int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* 
                 static_cast<const __nv_bfloat16*>(scale), static_cast<const __nv_bfloat16*>(shift),
                 mod_ld, static_cast<__nv_bfloat16*>(out), ldo, out_batch_stride, batch, rows, D, eps};
   const long long total = (long long)batch * rows;
-  ln_modulate_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(p);
+  const unsigned grid = (unsigned)((total + 3) / 4);
+  if (D <= 1024)
+    ln_modulate_kernel<4><<<grid, 128, 0, stream>>>(p);
+  else if (D <= 3072)
+    ln_modulate_kernel<12><<<grid, 128, 0, stream>>>(p);
+  else
+    ln_modulate_kernel<LN_MAXC><<<grid, 128, 0, stream>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("ln_modulate_kernel");
   return B2F_OK;

@@ -27,16 +27,16 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 
 struct GemmParams {
-  int M, N, K;
+  int batch, M, N, K;  // M rows per batch item
   const __nv_bfloat16* bias;
   __nv_bfloat16* out;
-  long long ldc;
+  long long ldc, out_bs;
   int epi;
   const __nv_bfloat16* resid;
-  long long ldr;
+  long long ldr, resid_bs;
   const __nv_bfloat16* gate;
   long long gate_ld;
-  int rows_per_batch;
+  int m_blocks_per_batch;
   int num_m_blocks, num_n_blocks, panel_n;
 };
 
@@ -125,7 +125,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          const int bb = m_blk / p.m_blocks_per_batch;
+          const int mb = m_blk - bb * p.m_blocks_per_batch;
+          tma_load_3d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, mb * BLOCK_M, bb);
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
           if (++stage == Cfg::STAGES) {
             stage = 0;
@@ -180,12 +182,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tile_coords(p, t, m_blk, n_blk);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const long long row = (long long)m_blk * BLOCK_M + row_in_tile;
+      const int bidx = m_blk / p.m_blocks_per_batch;
+      const long long row = (long long)(m_blk - bidx * p.m_blocks_per_batch) * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.M;
-      const int bidx = (p.epi == B2F_EPI_GATE_RESID && row_ok) ? int(row / p.rows_per_batch) : 0;
       const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
-      __nv_bfloat16* out_row = p.out + row * p.ldc;
-      const __nv_bfloat16* res_row = p.resid ? p.resid + row * p.ldr : nullptr;
+      __nv_bfloat16* out_row = p.out + bidx * p.out_bs + row * p.ldc;
+      const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t acc[32];
@@ -271,7 +273,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cu
     if (e != cudaSuccess) return cuda_err(e, "gemm smem attribute");
     attr_set = true;
   }
-  p.num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.m_blocks_per_batch = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_blocks = p.batch * p.m_blocks_per_batch;
   p.num_n_blocks = (p.N + BN - 1) / BN;
   p.panel_n = BN == 256 ? 16 : 32;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
@@ -284,38 +287,43 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cu
 
 }  // namespace
 
-int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
-              int64_t ldc, int M, int N, int K, int epilogue, const void* resid, int64_t ldr,
-              const void* gate, int64_t gate_ld, int rows_per_batch, cudaStream_t stream) {
+int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
+              const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M, int N,
+              int K, int epilogue, const void* resid, int64_t ldr, int64_t resid_bs, const void* gate,
+              int64_t gate_ld, cudaStream_t stream) {
   if (!device_info().ok) return B2F_ERR_NODEVICE;
-  if (M <= 0 || N <= 0 || K <= 0 || !A || !W || !out) return B2F_ERR_INVALID;
-  if ((K & 7) || (N & 7) || (lda & 7) || (ldw & 7) || (ldc & 7)) return B2F_ERR_ALIGN;
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0 || !A || !W || !out) return B2F_ERR_INVALID;
+  if ((K & 7) || (N & 7) || (lda & 7) || (ldw & 7) || (ldc & 7) || (a_bs & 7) || (out_bs & 7))
+    return B2F_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) |
        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
        reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(gate)) & 15)
     return B2F_ERR_ALIGN;
   if (epilogue < 0 || epilogue > B2F_EPI_GATE_RESID) return B2F_ERR_INVALID;
   if (epilogue == B2F_EPI_GATE_RESID) {
-    if (!resid || !gate || rows_per_batch <= 0 || (ldr & 7) || (gate_ld & 7)) return B2F_ERR_INVALID;
+    if (!resid || !gate || (ldr & 7) || (gate_ld & 7) || (resid_bs & 7)) return B2F_ERR_INVALID;
   }
   GemmParams p{};
+  p.batch = batch;
   p.M = M;
   p.N = N;
   p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldc = ldc;
+  p.out_bs = out_bs;
   p.epi = epilogue;
   p.resid = static_cast<const __nv_bfloat16*>(resid);
   p.ldr = ldr;
+  p.resid_bs = resid_bs;
   p.gate = static_cast<const __nv_bfloat16*>(gate);
   p.gate_ld = gate_ld;
-  p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
 
-  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
-  const bool use256 = (long long)num_m * ((N + 255) / 256) >= device_info().num_sms && N >= 256;
+  const long long num_m = (long long)batch * ((M + BLOCK_M - 1) / BLOCK_M);
+  const bool use256 = num_m * ((N + 255) / 256) >= device_info().num_sms && N >= 256;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BLOCK_M, BLOCK_K);
+  int rc = make_tmap_3d_rows(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)lda,
+                             batch > 1 ? (uint64_t)a_bs : (uint64_t)M * lda);
   if (rc != B2F_OK) return rc;
   rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, use256 ? 256 : 128,
                          BLOCK_K);

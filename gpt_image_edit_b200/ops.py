@@ -5,6 +5,8 @@ the current CUDA stream to libb2f.  No function here computes anything in torch.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _lib
@@ -13,67 +15,58 @@ from ._lib import check, ptr, stream_ptr
 EPI_BIAS, EPI_GELU_TANH, EPI_SILU, EPI_GATE_RESID = 0, 1, 2, 3
 
 
-def _req(t: torch.Tensor, name: str) -> None:
+def _req(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise _lib.B2FError(f"{name}: expected a tensor, got {type(t)}")
     if not t.is_cuda:
         raise _lib.B2FError(f"{name}: libb2f runs on CUDA tensors only (got {t.device}); there is no CPU path")
-    if t.dtype != torch.bfloat16:
-        raise _lib.B2FError(f"{name}: expected bfloat16, got {t.dtype}")
+    if t.dtype != dtype:
+        raise _lib.B2FError(f"{name}: expected {dtype}, got {t.dtype}")
     if t.stride(-1) != 1:
         raise _lib.B2FError(f"{name}: innermost dimension must be contiguous")
 
 
-def linear(
-    x: torch.Tensor,
-    weight: torch.Tensor,
-    bias: torch.Tensor | None = None,
-    *,
-    epilogue: int = EPI_BIAS,
-    out: torch.Tensor | None = None,
-    resid: torch.Tensor | None = None,
-    gate: torch.Tensor | None = None,
-    rows_per_batch: int = 0,
-) -> torch.Tensor:
-    """out[M,N] = epilogue(x[M,K] @ weight[N,K]^T + bias) via b2f_gemm_bf16 (tcgen05)."""
+def _as3(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dim() == 3 else t.unsqueeze(0)
+
+
+def linear(x, weight, bias=None, *, epilogue: int = EPI_BIAS, out=None, resid=None, gate=None) -> torch.Tensor:
+    """out = epilogue(x @ weight^T + bias) via b2f_gemm_bf16 (tcgen05).
+
+    x: [M,K] or [B,M,K] (any batch/row pitch); weight [N,K]; gate [B,N] for EPI_GATE_RESID."""
     _req(x, "x")
     _req(weight, "weight")
-    x2 = x.reshape(-1, x.shape[-1]) if x.dim() != 2 else x
-    M, K = x2.shape
+    x3 = _as3(x)
+    B, M, K = x3.shape
     N = weight.shape[0]
     if out is None:
-        out = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
-    out2 = out.reshape(-1, out.shape[-1]) if out.dim() != 2 else out
-    gate_ld = 0
-    ldr = 0
+        out = torch.empty((*x.shape[:-1], N), device=x.device, dtype=torch.bfloat16)
+    _req(out, "out")
+    o3 = _as3(out)
+    ldr = rbs = gld = 0
     if epilogue == EPI_GATE_RESID:
         _req(resid, "resid")
         _req(gate, "gate")
-        resid2 = resid.reshape(-1, resid.shape[-1]) if resid.dim() != 2 else resid
-        ldr = resid2.stride(0)
-        gate_ld = gate.stride(0) if gate.dim() == 2 else 0
+        r3 = _as3(resid)
+        ldr, rbs = r3.stride(1), r3.stride(0)
+        gld = gate.stride(0) if gate.dim() == 2 else 0
     check(
         _lib.lib.b2f_gemm_bf16(
-            ptr(x2), x2.stride(0), ptr(weight), weight.stride(0), ptr(bias), ptr(out2), out2.stride(0),
-            M, N, K, epilogue, ptr(resid), ldr, ptr(gate), gate_ld, rows_per_batch, stream_ptr(),
+            ptr(x3), x3.stride(1), x3.stride(0), ptr(weight), weight.stride(0), ptr(bias),
+            ptr(o3), o3.stride(1), o3.stride(0), B, M, N, K, epilogue,
+            ptr(resid), ldr, rbs, ptr(gate), gld, stream_ptr(),
         ),
         "b2f_gemm_bf16",
     )
-    return out if x.dim() == 2 else out.reshape(*x.shape[:-1], N)
+    return out
 
 
-def attention(
-    q: torch.Tensor,
-    k: torch.Tensor,
-    v: torch.Tensor,
-    *,
-    out: torch.Tensor | None = None,
-    causal: bool = False,
-    scale: float | None = None,
-) -> torch.Tensor:
+def attention(q, k, v, *, out=None, causal: bool = False, scale: float | None = None) -> torch.Tensor:
     """softmax(q k^T * scale) v via b2f_attention_fwd.  q [B,Sq,H,128], k/v [B,Skv,Hkv,128] as
     (possibly strided) views whose last two dims are contiguous; out [B,Sq,H*128]."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, n)
-        if t.dim() != 4 or t.stride(2) != t.shape[3] or t.stride(0) != t.shape[1] * t.stride(1):
+        if t.dim() != 4 or t.stride(2) != t.shape[3] or (t.shape[0] > 1 and t.stride(0) != t.shape[1] * t.stride(1)):
             raise _lib.B2FError(f"{n}: expected a [B,S,H,dh] view with contiguous heads and batch stride S*ld")
     B, Sq, H, dh = q.shape
     Skv, Hkv = k.shape[1], k.shape[2]
@@ -90,3 +83,69 @@ def attention(
         "b2f_attention_fwd",
     )
     return out
+
+
+def ln_modulate(x, scale, shift, *, out=None, eps: float = 1e-6) -> torch.Tensor:
+    """LayerNorm(x)*(1+scale[b])+shift[b]; x [B,rows,D] view, scale/shift [B,D] views."""
+    _req(x, "x")
+    _req(scale, "scale")
+    _req(shift, "shift")
+    x3 = _as3(x)
+    B, rows, D = x3.shape
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    o3 = _as3(out)
+    if scale.dim() != 2 or shift.stride(0) != scale.stride(0):
+        raise _lib.B2FError("scale/shift must be [B,D] views with equal pitch")
+    check(
+        _lib.lib.b2f_ln_modulate(ptr(x3), x3.stride(1), x3.stride(0), ptr(scale), ptr(shift), scale.stride(0),
+                                 ptr(o3), o3.stride(1), o3.stride(0), B, rows, D, eps, stream_ptr()),
+        "b2f_ln_modulate",
+    )
+    return out
+
+
+def rmsnorm_rope_(qkv, H: int, wq, wk, cos, sin, *, wq_added=None, wk_added=None, n_added: int = 0, eps: float = 1e-6):
+    """In place on qkv [B,S,>=2*H*128] (Q block then K block): per-head RMSNorm + RoPE."""
+    _req(qkv, "qkv")
+    _req(cos, "cos", torch.float32)
+    _req(sin, "sin", torch.float32)
+    B, S, _ = qkv.shape
+    k = qkv[:, :, H * 128:]
+    check(
+        _lib.lib.b2f_rmsnorm_rope(ptr(qkv), ptr(k), qkv.stride(1), qkv.stride(0), ptr(wq_added), ptr(wk_added),
+                                  ptr(wq), ptr(wk), ptr(cos), ptr(sin), B, S, H, 128, n_added, eps, stream_ptr()),
+        "b2f_rmsnorm_rope",
+    )
+    return qkv
+
+
+def euler_step_(x, v, dt: float):
+    """x <- bf16(float(x) + bf16(bf16(dt)*v)) in place; x, v [..., rows, cols] row views of equal shape."""
+    _req(x, "x")
+    _req(v, "v")
+    if x.shape != v.shape:
+        raise _lib.B2FError(f"euler_step_: shape mismatch {tuple(x.shape)} vs {tuple(v.shape)}")
+    if x.dim() == 3:
+        collapsible = all(t.stride(0) == t.shape[1] * t.stride(1) for t in (x, v))
+        if not collapsible:
+            for b in range(x.shape[0]):
+                euler_step_(x[b], v[b], dt)
+            return x
+        rows, ldx, ldv = x.shape[0] * x.shape[1], x.stride(1), v.stride(1)
+    else:
+        rows, ldx, ldv = x.shape[0], x.stride(0), v.stride(0)
+    check(_lib.lib.b2f_euler_step(ptr(x), ldx, ptr(v), ldv, rows, x.shape[-1], float(dt), stream_ptr()), "b2f_euler_step")
+    return x
+
+
+def rope_tables(ids: torch.Tensor, axes_dim=(16, 56, 56), theta: float = 10000.0):
+    """FluxPosEmbed: ids fp32 [S,3] -> (cos, sin) fp32 [S,128]."""
+    _req(ids, "ids", torch.float32)
+    ids = ids.contiguous()
+    S = ids.shape[0]
+    cos = torch.empty((S, 128), device=ids.device, dtype=torch.float32)
+    sin = torch.empty_like(cos)
+    axes = (C.c_int * 3)(*axes_dim)
+    check(_lib.lib.b2f_rope_tables(ptr(ids), S, axes, float(theta), ptr(cos), ptr(sin), stream_ptr()), "b2f_rope_tables")
+    return cos, sin

@@ -1,0 +1,281 @@
+"""FluxKontextPipeline — the sampling loop of the reference (univa/utils/flux_pipeline.py:732-1138),
+re-hosted over libb2f components.  Same constructor keywords, `__call__` keywords, static helpers
+(`_pack_latents`, `_unpack_latents`, `_prepare_latent_image_ids`, `prepare_latents` — also used by
+train_denoiser.py:446-454, 1009-1027) and output type as the reference.
+
+The components are protocol objects exactly as in the reference:
+  transformer  `B200FluxTransformer2DModel`  (C ABI: b2f_flux_forward)
+  scheduler    `FlowMatchEulerDiscreteScheduler` (C ABI: b2f_euler_step)
+  vae          object with .encode(x).latent_dist.mode(), .decode(z, return_dict=False)[0], .config
+What this file adds over the reference loop, without changing results:
+  * the AdaLN modulation of all steps is hoisted into one weight-streaming GEMM before the loop
+    (`transformer.prepare_schedule`), when the transformer offers it;
+  * the transformer is asked for the target tokens only (the reference slices them afterwards,
+    flux_pipeline.py:1078), so the Euler update reads a contiguous tensor.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+PREFERRED_KONTEXT_RESOLUTIONS = [
+    (672, 1568), (688, 1504), (720, 1456), (752, 1392), (800, 1328), (832, 1248), (880, 1184), (944, 1104),
+    (1024, 1024), (1104, 944), (1184, 880), (1248, 832), (1328, 800), (1392, 752), (1456, 720), (1504, 688),
+    (1568, 672),
+]
+
+
+def calculate_shift(image_seq_len, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
+                    max_shift: float = 1.15):
+    """mu is linear in the number of target tokens through (256, 0.5) and (4096, 1.15) (reference :106-116)."""
+    slope = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    return image_seq_len * slope + (base_shift - slope * base_seq_len)
+
+
+def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timesteps=None, sigmas=None, **kwargs):
+    """Reference :120-176 reduced to the two branches FLUX uses (sigmas= or a plain step count)."""
+    if timesteps is not None:
+        raise ValueError("custom `timesteps` are not supported by FlowMatchEulerDiscreteScheduler; pass `sigmas`")
+    if sigmas is not None:
+        scheduler.set_timesteps(sigmas=sigmas, device=device, **kwargs)
+    else:
+        scheduler.set_timesteps(num_inference_steps, device=device, **kwargs)
+    return scheduler.timesteps, len(scheduler.timesteps)
+
+
+class FluxPipelineOutput(SimpleNamespace):
+    pass
+
+
+class VaeImageProcessor:
+    """The three behaviours of diffusers' VaeImageProcessor the reference reaches with tensor inputs
+    (SURVEY.md A.4): nearest resize, [-1,1] pass-through, postprocess to uint8/PIL."""
+
+    def __init__(self, vae_scale_factor: int = 16):
+        self.vae_scale_factor = vae_scale_factor
+
+    @staticmethod
+    def get_default_height_width(image):
+        return int(image.shape[-2]), int(image.shape[-1])
+
+    @staticmethod
+    def resize(image: torch.Tensor, height: int, width: int) -> torch.Tensor:
+        if image.shape[-2] == height and image.shape[-1] == width:
+            return image
+        return torch.nn.functional.interpolate(image, size=(height, width))
+
+    @staticmethod
+    def preprocess(image: torch.Tensor, height=None, width=None) -> torch.Tensor:
+        if image.dim() == 3:
+            image = image[None]
+        if image.min() >= 0:  # [0,1] inputs are normalised; [-1,1] inputs pass through
+            image = 2.0 * image - 1.0
+        return image
+
+    @staticmethod
+    def postprocess(image: torch.Tensor, output_type: str = "pil"):
+        if output_type == "latent" or output_type == "pt_raw":
+            return image
+        img = (image.float() / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return img
+        arr = img.permute(0, 2, 3, 1).cpu().numpy()
+        if output_type == "np":
+            return arr
+        from PIL import Image
+
+        arr8 = (arr * 255).round().astype("uint8")
+        return [Image.fromarray(a) for a in arr8]
+
+
+class FluxKontextPipeline:
+    def __init__(self, transformer, vae=None, scheduler=None, text_encoder=None, tokenizer=None, text_encoder_2=None,
+                 tokenizer_2=None, image_encoder=None, feature_extractor=None):
+        self.transformer = transformer
+        self.vae = vae
+        self.scheduler = scheduler
+        self.text_encoder, self.tokenizer = text_encoder, tokenizer
+        self.text_encoder_2, self.tokenizer_2 = text_encoder_2, tokenizer_2
+        boc = getattr(getattr(vae, "config", None), "block_out_channels", (128, 256, 512, 512))
+        self.vae_scale_factor = 2 ** (len(boc) - 1)
+        self.latent_channels = getattr(getattr(vae, "config", None), "latent_channels", 16)
+        self.image_processor = VaeImageProcessor(vae_scale_factor=self.vae_scale_factor * 2)
+        self.default_sample_size = 128
+        self._execution_device = getattr(transformer, "device", torch.device("cuda"))
+        self._interrupt = False
+
+    @classmethod
+    def from_pretrained(cls, flux_path, transformer=None, torch_dtype=torch.bfloat16, **kw):
+        """Reference univa/serve/cli.py:64-68.  Builds scheduler + VAE from `flux_path` when a
+        checkpoint directory exists (safetensors, diffusers key names); the transformer is always the
+        one handed in, as in the reference."""
+        from .checkpoint import load_pipeline_components
+
+        vae, scheduler = load_pipeline_components(flux_path, device=getattr(transformer, "device", "cuda"))
+        return cls(transformer=transformer, vae=vae, scheduler=scheduler)
+
+    def to(self, *a, **k):
+        for comp in (self.transformer, self.vae):
+            if comp is not None and hasattr(comp, "to"):
+                comp.to(*a, **k)
+        return self
+
+    # ------------------------------------------------------------------ layout helpers (reference :561-598)
+    @staticmethod
+    def _prepare_latent_image_ids(batch_size, height, width, device, dtype):
+        ids = torch.zeros(height, width, 3)
+        ids[..., 1] = ids[..., 1] + torch.arange(height)[:, None]
+        ids[..., 2] = ids[..., 2] + torch.arange(width)[None, :]
+        return ids.reshape(height * width, 3).to(device=device, dtype=dtype)
+
+    @staticmethod
+    def _pack_latents(latents, batch_size, num_channels_latents, height, width):
+        """[B,C,h,w] -> [B,(h/2)(w/2),C*4]; inside a token the order is (c, dy, dx)."""
+        x = latents.view(batch_size, num_channels_latents, height // 2, 2, width // 2, 2)
+        x = x.permute(0, 2, 4, 1, 3, 5)
+        return x.reshape(batch_size, (height // 2) * (width // 2), num_channels_latents * 4)
+
+    @staticmethod
+    def _unpack_latents(latents, height, width, vae_scale_factor):
+        batch_size, _, channels = latents.shape
+        height = 2 * (int(height) // (vae_scale_factor * 2))
+        width = 2 * (int(width) // (vae_scale_factor * 2))
+        x = latents.view(batch_size, height // 2, width // 2, channels // 4, 2, 2)
+        x = x.permute(0, 3, 1, 4, 2, 5)
+        return x.reshape(batch_size, channels // 4, height, width)
+
+    def _encode_vae_image(self, image, generator=None):
+        z = self.vae.encode(image.to(self.vae.dtype)).latent_dist.mode()
+        return (z - self.vae.config.shift_factor) * self.vae.config.scaling_factor
+
+    def prepare_latents(self, image, batch_size, num_channels_latents, height, width, dtype, device, generator=None,
+                        latents=None):
+        """Reference :648-708."""
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"got {len(generator)} generators for an effective batch size of {batch_size}")
+        height = 2 * (int(height) // (self.vae_scale_factor * 2))
+        width = 2 * (int(width) // (self.vae_scale_factor * 2))
+        shape = (batch_size, num_channels_latents, height, width)
+        image_latents = image_ids = None
+        if image is not None:
+            image = image.to(device=device, dtype=dtype)
+            image_latents = self._encode_vae_image(image, generator) if image.shape[1] != self.latent_channels else image
+            n = image_latents.shape[0]
+            if batch_size > n and batch_size % n == 0:
+                image_latents = torch.cat([image_latents] * (batch_size // n), dim=0)
+            elif batch_size > n:
+                raise ValueError(f"Cannot duplicate `image` of batch size {n} to {batch_size} text prompts.")
+            ih, iw = image_latents.shape[2:]
+            image_latents = self._pack_latents(image_latents, batch_size, num_channels_latents, ih, iw)
+            image_ids = self._prepare_latent_image_ids(batch_size, ih // 2, iw // 2, device, dtype)
+            image_ids[..., 0] = 1  # context image index
+        latent_ids = self._prepare_latent_image_ids(batch_size, height // 2, width // 2, device, dtype)
+        if latents is None:
+            noise = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+            latents = self._pack_latents(noise, batch_size, num_channels_latents, height, width)
+        else:
+            latents = latents.to(device=device, dtype=dtype)
+        return latents, image_latents, latent_ids, image_ids
+
+    # ------------------------------------------------------------------ sampling (reference :732-1138)
+    @torch.no_grad()
+    def __call__(self, image=None, prompt=None, prompt_2=None, negative_prompt=None, negative_prompt_2=None,
+                 true_cfg_scale: float = 1.0, height: Optional[int] = None, width: Optional[int] = None,
+                 num_inference_steps: int = 28, sigmas=None, guidance_scale: float = 3.5,
+                 num_images_per_prompt: int = 1, generator=None, latents=None, prompt_embeds=None,
+                 pooled_prompt_embeds=None, negative_prompt_embeds=None, negative_pooled_prompt_embeds=None,
+                 output_type: str = "pil", return_dict: bool = True, joint_attention_kwargs=None,
+                 callback_on_step_end: Optional[Callable] = None, callback_on_step_end_tensor_inputs=("latents",),
+                 max_sequence_length: int = 512, max_area: int = 1024 ** 2, _auto_resize: bool = True):
+        if prompt is not None or prompt_embeds is None or pooled_prompt_embeds is None:
+            raise ValueError("this pipeline is driven with `prompt_embeds` + `pooled_prompt_embeds` (as univa.serve.cli "
+                             "does, reference cli.py:239-248); string prompts need the T5/CLIP encoders")
+        if true_cfg_scale > 1 and negative_prompt_embeds is not None:
+            raise NotImplementedError("true-CFG second forward (reference :1080-1095) is off by default and not built")
+        height = height or self.default_sample_size * self.vae_scale_factor
+        width = width or self.default_sample_size * self.vae_scale_factor
+        # size rule: rescale to `max_area` keeping aspect, floor to a multiple of 16 (reference :874-889)
+        aspect = width / height
+        width = round((max_area * aspect) ** 0.5)
+        height = round((max_area / aspect) ** 0.5)
+        mult = self.vae_scale_factor * 2
+        width, height = width // mult * mult, height // mult * mult
+
+        batch_size = prompt_embeds.shape[0]
+        device = self._execution_device
+        dtype = prompt_embeds.dtype
+        if num_images_per_prompt != 1:
+            prompt_embeds = prompt_embeds.repeat_interleave(num_images_per_prompt, dim=0)
+            pooled_prompt_embeds = pooled_prompt_embeds.repeat_interleave(num_images_per_prompt, dim=0)
+        text_ids = torch.zeros(prompt_embeds.shape[1], 3, device=device, dtype=dtype)
+
+        if image is not None and not (isinstance(image, torch.Tensor) and image.size(1) == self.latent_channels):
+            ih, iw = self.image_processor.get_default_height_width(image)
+            if _auto_resize:
+                a = iw / ih
+                _, iw, ih = min((abs(a - w / h), w, h) for w, h in PREFERRED_KONTEXT_RESOLUTIONS)
+            iw, ih = iw // mult * mult, ih // mult * mult
+            image = self.image_processor.preprocess(self.image_processor.resize(image, ih, iw), ih, iw)
+
+        B = batch_size * num_images_per_prompt
+        num_channels_latents = self.transformer.config.in_channels // 4
+        latents, image_latents, latent_ids, image_ids = self.prepare_latents(
+            image, B, num_channels_latents, height, width, dtype, device, generator, latents)
+        if image_ids is not None:
+            latent_ids = torch.cat([latent_ids, image_ids], dim=0)
+        latents = latents.contiguous()
+
+        sig = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps) if sigmas is None else sigmas
+        n_tgt = latents.shape[1]
+        cfgs = self.scheduler.config
+        mu = calculate_shift(n_tgt, cfgs.get("base_image_seq_len", 256), cfgs.get("max_image_seq_len", 4096),
+                             cfgs.get("base_shift", 0.5), cfgs.get("max_shift", 1.15))
+        timesteps, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, device, sigmas=sig, mu=mu)
+        self._num_timesteps = len(timesteps)
+
+        guidance = None
+        if self.transformer.config.guidance_embeds:
+            guidance = torch.full([1], guidance_scale, device=device, dtype=torch.float32).expand(B)
+
+        jak = dict(joint_attention_kwargs or {})
+        hoist = hasattr(self.transformer, "prepare_schedule")
+        if hoist:
+            # the loop passes timestep = t.to(dtype) / 1000 (reference :1065-1069): hoist with exactly those values
+            self.transformer.prepare_schedule(timesteps.to(dtype) / 1000, guidance, pooled_prompt_embeds)
+            jak["_b2f_out_rows"] = n_tgt
+
+        self.scheduler.set_begin_index(0)
+        for i, t in enumerate(timesteps):
+            if self._interrupt:
+                continue
+            x_in = latents if image_latents is None else torch.cat([latents, image_latents], dim=1)
+            timestep = t.expand(B).to(latents.dtype)
+            if hoist:
+                jak["_b2f_schedule_step"] = i
+            noise_pred = self.transformer(
+                hidden_states=x_in, timestep=timestep / 1000, guidance=guidance, pooled_projections=pooled_prompt_embeds,
+                encoder_hidden_states=prompt_embeds, txt_ids=text_ids, img_ids=latent_ids, joint_attention_kwargs=jak,
+                return_dict=False)[0]
+            noise_pred = noise_pred[:, :n_tgt]
+            latents = self.scheduler.step(noise_pred, t, latents, return_dict=False)[0]
+            if callback_on_step_end is not None:
+                out = callback_on_step_end(self, i, t, {"latents": latents})
+                latents = out.pop("latents", latents)
+
+        if output_type == "latent":
+            images = latents
+        else:
+            z = self._unpack_latents(latents, height, width, self.vae_scale_factor)
+            z = (z / self.vae.config.scaling_factor) + self.vae.config.shift_factor
+            images = self.vae.decode(z.to(self.vae.dtype), return_dict=False)[0]
+            images = self.image_processor.postprocess(images, output_type=output_type)
+        if not return_dict:
+            return (images,)
+        return FluxPipelineOutput(images=images)
+
+
+class FluxPipeline(FluxKontextPipeline):
+    """Alias kept by the reference for backward compatibility (flux_pipeline.py:1140)."""

@@ -46,12 +46,17 @@ uint64_t b2f_launch_count(void);
  * (FluxTransformer2DModel: x_embedder, context_embedder, to_q/k/v, to_out, ff.net.*, proj_mlp,
  * proj_out, norm*.linear — SURVEY.md Appendix A.1/A.6; call site univa/utils/flux_pipeline.py:1067).
  *
+ * Batched rows: A is [batch, M, K] (row pitch lda, batch pitch a_batch_stride), out/resid are
+ * [batch, M, N] views with their own pitches; gate is [batch, N] (pitch gate_ld).  batch = 1 is
+ * the plain 2-D case (batch strides ignored).  This lets one launch process the image rows (or
+ * the text rows) of every batch item of a joint [B, S_txt+S_img, d] buffer.
+ *
  * epilogue:
  *   B2F_EPI_BIAS        out = bf16(acc + bias)
  *   B2F_EPI_GELU_TANH   out = bf16(gelu_tanh(bf16(acc + bias)))     (ff.net.0 / proj_mlp)
  *   B2F_EPI_SILU        out = bf16(silu(bf16(acc + bias)))          (time_text_embed MLPs, MLP2)
  *   B2F_EPI_GATE_RESID  out = bf16(resid + bf16(gate[b,n] * bf16(acc + bias)))
- *                       with b = row / rows_per_batch                (x = x + gate * proj(...))
+ *                                                                    (x = x + gate * proj(...))
  * bias may be NULL.  resid may alias out.  K % 8 == 0, N % 8 == 0.
  */
 #define B2F_EPI_BIAS 0
@@ -59,10 +64,52 @@ uint64_t b2f_launch_count(void);
 #define B2F_EPI_SILU 2
 #define B2F_EPI_GATE_RESID 3
 
-int b2f_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
-                  void* out, int64_t ldc, int M, int N, int K, int epilogue, const void* resid,
-                  int64_t ldr, const void* gate, int64_t gate_ld, int rows_per_batch,
+int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
+                  const void* bias, void* out, int64_t ldc, int64_t out_batch_stride, int batch,
+                  int M, int N, int K, int epilogue, const void* resid, int64_t ldr,
+                  int64_t resid_batch_stride, const void* gate, int64_t gate_ld,
                   b2f_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * AdaLN modulate (HBM-bound): out = LayerNorm(x; eps, no affine) * (1 + scale[b]) + shift[b].
+ * Replaces nn.LayerNorm + the broadcast multiply/add of diffusers AdaLayerNormZero /
+ * AdaLayerNormZeroSingle / AdaLayerNormContinuous and the norm2 modulate inside
+ * FluxTransformerBlock.  x/out: [batch, rows, D] views; scale/shift: [batch, D]
+ * with pitch mod_ld.  D % 256 == 0, D <= 5120.
+ */
+int b2f_ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
+                    const void* shift, int64_t mod_ld, void* out, int64_t ldo,
+                    int64_t out_batch_stride, int batch, int rows, int D, float eps,
+                    b2f_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-head RMSNorm + interleaved-pair RoPE, in place on the Q and K blocks of a fused QKV buffer
+ * (HBM-bound).  Replaces diffusers RMSNorm (attn.norm_q/norm_k/norm_added_q/norm_added_k) and
+ * apply_rotary_emb(use_real_unbind_dim=-1) in FluxAttnProcessor2_0.
+ * q, k: pointers to head 0 of token 0 (token pitch ld, batch pitch batch_stride); H heads of 128.
+ * Tokens [0, n_a) of each batch item use weights (wq_a, wk_a) — the text stream's
+ * norm_added_q/k — the rest use (wq_b, wk_b).  cos/sin: fp32 [S, 128] (FluxPosEmbed layout).
+ */
+int b2f_rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void* wq_a,
+                     const void* wk_a, const void* wq_b, const void* wk_b, const float* cos,
+                     const float* sin, int batch, int S, int H, int head_dim, int n_a, float eps,
+                     b2f_stream_t stream);
+
+/* Flow-matching Euler update x <- bf16(float(x) + bf16(bf16(dt) * v)), in place (replaces
+ * FlowMatchEulerDiscreteScheduler.step, reference call site univa/utils/flux_pipeline.py:1099). */
+int b2f_euler_step(void* x, int64_t ldx, const void* v, int64_t ldv, int64_t rows, int cols,
+                   float dt, b2f_stream_t stream);
+
+/* FluxPosEmbed: 3-axis RoPE tables from token ids.  ids: fp32 DEVICE [S,3] (text ids first, then
+ * image ids: (image index, row, col), reference univa/utils/flux_pipeline.py:561-572, 694-698);
+ * axes_dim = {16,56,56}; angles in float64, output fp32 [S,128] with each pair value repeated
+ * (diffusers get_1d_rotary_pos_embed(repeat_interleave_real=True)). */
+int b2f_rope_tables(const float* ids, int S, const int* axes_dim, double theta, float* cos,
+                    float* sin, b2f_stream_t stream);
+
+/* y = silu(x) over n contiguous bf16 elements (n % 8 == 0): the nn.SiLU in front of every AdaLN
+ * linear. */
+int b2f_silu(const void* x, void* y, int64_t n, b2f_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused softmax attention, head_dim 128:  O = softmax(Q K^T * scale [+ causal mask]) V.
@@ -82,6 +129,74 @@ int b2f_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
 int b2f_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                       int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
                       int head_dim, float scale, int causal, b2f_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FLUX-Kontext MMDiT (diffusers FluxTransformer2DModel) as one object.
+ * Replaces `pipe.transformer(...)` — reference call sites univa/utils/flux_pipeline.py:1067-1077,
+ * univa/models/modeling_univa_denoise_tower.py:103-110, modeling_univa_qwen2p5vl.py:352-355.
+ *
+ * Weights are BORROWED device pointers (bf16) bound by name.  Names are the diffusers state-dict
+ * keys except that projections which this engine runs as one GEMM are bound as
+ * one row-concatenated tensor (the Python side stores them fused and exposes the diffusers names
+ * as views, so checkpoints interchange):
+ *   transformer_blocks.{i}.attn.qkv.{weight,bias}       rows [to_q; to_k; to_v]               [3d, d]
+ *   transformer_blocks.{i}.attn.add_qkv.{weight,bias}   rows [add_q_proj; add_k_proj; add_v_proj]
+ *   single_transformer_blocks.{i}.qkv_mlp.{weight,bias} rows [to_q; to_k; to_v; proj_mlp]     [7d, d]
+ *   adaln.{weight,bias}   rows, in order: for each double block i [norm1.linear (6d);
+ *                         norm1_context.linear (6d)], for each single block [norm.linear (3d)],
+ *                         then norm_out.linear (2d)                              [mod_width, d]
+ * All other keys keep their diffusers names (x_embedder, context_embedder, time_text_embed.*,
+ * attn.to_out.0, attn.to_add_out, attn.norm_*.weight, ff.net.0.proj, ff.net.2, ff_context.*,
+ * single proj_out, proj_out).
+ */
+typedef struct b2f_flux b2f_flux;
+typedef struct {
+  int num_heads;      /* 24 */
+  int head_dim;       /* 128 (only value supported) */
+  int num_double;     /* 19 */
+  int num_single;     /* 38 */
+  int in_channels;    /* 64 */
+  int out_channels;   /* 64 */
+  int joint_dim;      /* 4096 */
+  int pooled_dim;     /* 768 */
+  int guidance_embeds;/* 1 */
+  int mlp_ratio;      /* 4 */
+} b2f_flux_cfg;
+
+int b2f_flux_create(b2f_flux** out, const b2f_flux_cfg* cfg);
+void b2f_flux_destroy(b2f_flux* ctx);
+int b2f_flux_bind_weight(b2f_flux* ctx, const char* key, const void* dptr, int64_t numel);
+/* Checks that every weight is bound with the right element count. */
+int b2f_flux_finalize(b2f_flux* ctx);
+/* Columns of one modulation row = rows of adaln.weight. */
+int64_t b2f_flux_mod_width(const b2f_flux* ctx);
+/* RoPE tables (FluxPosEmbed output, fp32 [S_txt+S_img, 128], text rows first); borrowed. */
+int b2f_flux_set_rope(b2f_flux* ctx, const float* cos, const float* sin, int S);
+size_t b2f_flux_workspace_bytes(const b2f_flux* ctx, int B, int S_img, int S_txt);
+size_t b2f_flux_temb_workspace_bytes(const b2f_flux* ctx, int rows);
+/* CombinedTimestepGuidanceTextProjEmbeddings for `rows` (step, batch) pairs:
+ * timestep/guidance are fp32 DEVICE arrays already multiplied by 1000 in the reference's bf16
+ * arithmetic; pooled is bf16 [rows, pooled_dim].  Writes temb and silu(temb), bf16 [rows, d]. */
+int b2f_flux_temb(b2f_flux* ctx, const float* timestep, const float* guidance, const void* pooled,
+                  int64_t pooled_ld, int rows, void* temb, void* silu_temb, void* ws,
+                  size_t ws_bytes, b2f_stream_t stream);
+/* Every AdaLN linear of the model in ONE weight-streaming GEMM:
+ * mod[rows, mod_width] = silu_temb[rows, d] · adaln.weight^T + adaln.bias.  Hoistable over the
+ * whole sampling schedule (rows = steps * batch): the modulation depends only on (t, guidance,
+ * pooled), so the 6.46 GB of AdaLN weights are read once per image instead of once per step. */
+int b2f_flux_modulation(b2f_flux* ctx, const void* silu_temb, int rows, void* mod,
+                        b2f_stream_t stream);
+/* One MMDiT forward.  hidden [B,S_img,in_channels], enc [B,S_txt,joint_dim], mod: pointer to the
+ * first batch item's modulation row (pitch mod_ld between batch items), out
+ * [B,n_out_rows,out_channels] (the first n_out_rows image tokens; the pipeline only consumes the
+ * target tokens, flux_pipeline.py:1078).  Blocks [first_block, last_block) of the 57 run; pass
+ * (0, -1) for the whole model — partial ranges exist for block-level parity tests (the embedders
+ * run iff first_block == 0, norm_out/proj_out iff last_block covers the last block; activations
+ * persist in ws between calls).  No allocation, no host synchronisation: graph-capturable. */
+int b2f_flux_forward(b2f_flux* ctx, const void* hidden, const void* enc, const void* mod,
+                     int64_t mod_ld, void* out, int B, int S_img, int S_txt, int n_out_rows,
+                     void* ws, size_t ws_bytes, int first_block, int last_block,
+                     b2f_stream_t stream);
 
 #ifdef __cplusplus
 }

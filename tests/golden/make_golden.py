@@ -1,0 +1,203 @@
+"""Generates tests/golden/*.pt — run HERE (build container), commit the outputs.
+
+Pins for the oracle (the reference ships no golden vectors):
+  flux_toy_titan.pt   inputs + output of torchtitan.experiments.flux.FluxModel (an independent
+                      BFL-layout FLUX implementation that is importable in this image) in float64,
+                      with the oracle's synthetic diffusers-named weights mapped by SURVEY.md A.7.
+                      guidance_embeds=False because torchtitan has no guidance embedder.
+  flux_toy_oracle.pt  inputs + fp32 output of the oracle itself WITH guidance (regression pin for
+                      the pieces torchtitan cannot cover: guidance MLP, bf16 timestep chain).
+"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle import flux_oracle as fo  # noqa: E402
+
+HERE = Path(__file__).resolve().parent
+TOY = dict(num_layers=2, num_single_layers=2, attention_head_dim=128, num_attention_heads=2,
+           joint_attention_dim=256, pooled_projection_dim=64)
+
+
+def toy_inputs(cfg, B=1, S_txt=24, HL=6, WL=5, seed=1, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    n = HL * WL
+    ids = torch.zeros(HL, WL, 3)
+    ids[..., 1] += torch.arange(HL)[:, None]
+    ids[..., 2] += torch.arange(WL)[None, :]
+    ids = ids.reshape(-1, 3)
+    ctx = ids.clone()
+    ctx[:, 0] = 1
+    return dict(
+        hidden_states=torch.randn(B, 2 * n, cfg.in_channels, generator=g, dtype=dtype),
+        encoder_hidden_states=torch.randn(B, S_txt, cfg.joint_attention_dim, generator=g, dtype=dtype),
+        pooled_projections=torch.randn(B, cfg.pooled_projection_dim, generator=g, dtype=dtype),
+        timestep=torch.full((B,), 0.75, dtype=dtype),
+        guidance=torch.full((B,), 3.5, dtype=dtype),
+        img_ids=torch.cat([ids, ctx]),
+        txt_ids=torch.zeros(S_txt, 3),
+    )
+
+
+def titan_from_diffusers(cfg: fo.FluxConfig, sd: dict):
+    """Build torchtitan's FluxModel and load the diffusers-named weights through the A.7 mapping."""
+    from torchtitan.experiments.flux.model.args import FluxModelArgs
+    from torchtitan.experiments.flux.model.model import FluxModel
+
+    d = cfg.inner_dim
+    args = FluxModelArgs(in_channels=cfg.in_channels, out_channels=cfg.out_channels, vec_in_dim=cfg.pooled_projection_dim,
+                         context_in_dim=cfg.joint_attention_dim, hidden_size=d, num_heads=cfg.num_attention_heads,
+                         depth=cfg.num_layers, depth_single_blocks=cfg.num_single_layers, axes_dim=tuple(cfg.axes_dims_rope))
+    m = FluxModel(args).double()
+    cat = lambda *names: torch.cat([sd[n] for n in names], dim=0)
+    t = {}
+
+    def lin(dst, src):
+        t[dst + ".weight"], t[dst + ".bias"] = sd[src + ".weight"], sd[src + ".bias"]
+
+    lin("img_in", "x_embedder")
+    lin("txt_in", "context_embedder")
+    lin("time_in.in_layer", "time_text_embed.timestep_embedder.linear_1")
+    lin("time_in.out_layer", "time_text_embed.timestep_embedder.linear_2")
+    lin("vector_in.in_layer", "time_text_embed.text_embedder.linear_1")
+    lin("vector_in.out_layer", "time_text_embed.text_embedder.linear_2")
+    for i in range(cfg.num_layers):
+        s, p = f"transformer_blocks.{i}.", f"double_blocks.{i}."
+        lin(p + "img_mod.lin", s + "norm1.linear")
+        lin(p + "txt_mod.lin", s + "norm1_context.linear")
+        for kind in ("weight", "bias"):
+            t[p + f"img_attn.qkv.{kind}"] = cat(*(s + f"attn.{n}.{kind}" for n in ("to_q", "to_k", "to_v")))
+            t[p + f"txt_attn.qkv.{kind}"] = cat(*(s + f"attn.{n}.{kind}" for n in ("add_q_proj", "add_k_proj", "add_v_proj")))
+        t[p + "img_attn.norm.query_norm.weight"] = sd[s + "attn.norm_q.weight"]
+        t[p + "img_attn.norm.key_norm.weight"] = sd[s + "attn.norm_k.weight"]
+        t[p + "txt_attn.norm.query_norm.weight"] = sd[s + "attn.norm_added_q.weight"]
+        t[p + "txt_attn.norm.key_norm.weight"] = sd[s + "attn.norm_added_k.weight"]
+        lin(p + "img_attn.proj", s + "attn.to_out.0")
+        lin(p + "txt_attn.proj", s + "attn.to_add_out")
+        lin(p + "img_mlp.0", s + "ff.net.0.proj")
+        lin(p + "img_mlp.2", s + "ff.net.2")
+        lin(p + "txt_mlp.0", s + "ff_context.net.0.proj")
+        lin(p + "txt_mlp.2", s + "ff_context.net.2")
+    for i in range(cfg.num_single_layers):
+        s, p = f"single_transformer_blocks.{i}.", f"single_blocks.{i}."
+        lin(p + "modulation.lin", s + "norm.linear")
+        for kind in ("weight", "bias"):
+            t[p + f"linear1.{kind}"] = cat(*(s + f"attn.{n}.{kind}" for n in ("to_q", "to_k", "to_v")), s + f"proj_mlp.{kind}")
+        lin(p + "linear2", s + "proj_out")
+        t[p + "norm.query_norm.weight"] = sd[s + "attn.norm_q.weight"]
+        t[p + "norm.key_norm.weight"] = sd[s + "attn.norm_k.weight"]
+    lin("final_layer.linear", "proj_out")
+    # BFL chunks (shift, scale); diffusers AdaLayerNormContinuous chunks (scale, shift): swap halves
+    for kind in ("weight", "bias"):
+        a = sd[f"norm_out.linear.{kind}"]
+        t[f"final_layer.adaLN_modulation.1.{kind}"] = torch.cat([a[d:], a[:d]], dim=0)
+    missing, unexpected = m.load_state_dict({k: v.double() for k, v in t.items()}, strict=True)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.RMSNorm):
+            mod.eps = 1e-6  # diffusers RMSNorm eps (torchtitan default is finfo.eps)
+    return m.eval()
+
+
+VAE_TOY = dict(block_out_channels=(32, 64, 128, 128))
+
+
+def titan_ae_from_diffusers(vcfg, sd):
+    """torchtitan AutoEncoder (BFL layout) loaded with diffusers-named VAE weights."""
+    from torchtitan.experiments.flux.model.autoencoder import AutoEncoder, AutoEncoderParams
+
+    boc = vcfg.block_out_channels
+    ch = boc[0]
+    params = AutoEncoderParams(resolution=64, in_channels=3, ch=ch, out_ch=3, ch_mult=[b // ch for b in boc],
+                               num_res_blocks=vcfg.layers_per_block, z_channels=vcfg.latent_channels,
+                               scale_factor=vcfg.scaling_factor, shift_factor=vcfg.shift_factor)
+    ae = AutoEncoder(params).double()
+    t = {}
+    n = len(boc)
+
+    def cp(dst, src):
+        for kind in ("weight", "bias"):
+            t[f"{dst}.{kind}"] = sd[f"{src}.{kind}"]
+
+    def res(dst, src):
+        for a in ("norm1", "conv1", "norm2", "conv2"):
+            cp(f"{dst}.{a}", f"{src}.{a}")
+        if f"{src}.conv_shortcut.weight" in sd:
+            cp(f"{dst}.nin_shortcut", f"{src}.conv_shortcut")
+
+    def mid(dst, src):
+        res(f"{dst}.block_1", f"{src}.resnets.0")
+        res(f"{dst}.block_2", f"{src}.resnets.1")
+        cp(f"{dst}.attn_1.norm", f"{src}.attentions.0.group_norm")
+        for a, b in (("q", "to_q"), ("k", "to_k"), ("v", "to_v"), ("proj_out", "to_out.0")):
+            t[f"{dst}.attn_1.{a}.weight"] = sd[f"{src}.attentions.0.{b}.weight"][:, :, None, None]
+            t[f"{dst}.attn_1.{a}.bias"] = sd[f"{src}.attentions.0.{b}.bias"]
+
+    cp("encoder.conv_in", "encoder.conv_in")
+    for i in range(n):
+        for j in range(vcfg.layers_per_block):
+            res(f"encoder.down.{i}.block.{j}", f"encoder.down_blocks.{i}.resnets.{j}")
+        if i != n - 1:
+            cp(f"encoder.down.{i}.downsample.conv", f"encoder.down_blocks.{i}.downsamplers.0.conv")
+    mid("encoder.mid", "encoder.mid_block")
+    cp("encoder.norm_out", "encoder.conv_norm_out")
+    cp("encoder.conv_out", "encoder.conv_out")
+    cp("decoder.conv_in", "decoder.conv_in")
+    mid("decoder.mid", "decoder.mid_block")
+    for i in range(n):  # diffusers up_blocks[0] is the lowest resolution = BFL up[n-1]
+        for j in range(vcfg.layers_per_block + 1):
+            res(f"decoder.up.{n - 1 - i}.block.{j}", f"decoder.up_blocks.{i}.resnets.{j}")
+        if i != n - 1:
+            cp(f"decoder.up.{n - 1 - i}.upsample.conv", f"decoder.up_blocks.{i}.upsamplers.0.conv")
+    cp("decoder.norm_out", "decoder.conv_norm_out")
+    cp("decoder.conv_out", "decoder.conv_out")
+    ae.load_state_dict({k: v.double() for k, v in t.items()}, strict=True)
+    return ae.eval()
+
+
+def vae_golden():
+    from oracle import vae_oracle as vo
+
+    vcfg = vo.VaeConfig(**VAE_TOY)
+    sd = vo.make_synthetic_state_dict(vcfg, seed=21, dtype=torch.float64)
+    g = torch.Generator().manual_seed(22)
+    x = torch.rand(1, 3, 48, 64, generator=g, dtype=torch.float64) * 2 - 1
+    z = torch.randn(1, 16, 6, 8, generator=g, dtype=torch.float64)
+    ae = titan_ae_from_diffusers(vcfg, sd)
+    with torch.no_grad():
+        moments = ae.encoder(x)
+        mean = torch.chunk(moments, 2, dim=1)[0]
+        img = ae.decoder(z)
+    torch.save(dict(cfg=VAE_TOY, seed=21, x=x.float(), z=z.float(), mean=mean.float(), image=img.float()),
+               HERE / "vae_toy_titan.pt")
+    print("vae titan", mean.shape, mean.abs().mean().item(), img.shape, img.abs().mean().item())
+
+
+def main():
+    vae_golden()
+    cfg = fo.FluxConfig(**TOY, guidance_embeds=False)
+    sd = fo.make_synthetic_state_dict(cfg, seed=11, dtype=torch.float64)
+    inp = toy_inputs(cfg)
+    m = titan_from_diffusers(cfg, sd)
+    with torch.no_grad():
+        out = m(img=inp["hidden_states"], img_ids=inp["img_ids"][None].double(), txt=inp["encoder_hidden_states"],
+                txt_ids=inp["txt_ids"][None].double(), timesteps=inp["timestep"], y=inp["pooled_projections"])
+    torch.save(dict(cfg=TOY, seed=11, inputs={k: v.float() for k, v in inp.items()}, output=out.float()),
+               HERE / "flux_toy_titan.pt")
+    print("titan output", out.shape, out.abs().mean().item())
+
+    cfg2 = fo.FluxConfig(**TOY)
+    sd2 = fo.make_synthetic_state_dict(cfg2, seed=12, dtype=torch.float32)
+    inp2 = toy_inputs(cfg2, B=2, seed=2, dtype=torch.float32)
+    inp2["timestep"] = (torch.tensor([988.4086, 500.0]).bfloat16() / 1000)
+    with torch.no_grad():
+        out2 = fo.flux_forward(sd2, cfg2, inp2["hidden_states"], inp2["encoder_hidden_states"], inp2["pooled_projections"],
+                               inp2["timestep"], inp2["img_ids"], inp2["txt_ids"], guidance=inp2["guidance"].float())
+    torch.save(dict(cfg=TOY, seed=12, inputs=inp2, output=out2), HERE / "flux_toy_oracle.pt")
+    print("oracle output", out2.shape, out2.abs().mean().item())
+
+
+if __name__ == "__main__":
+    main()

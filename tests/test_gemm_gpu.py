@@ -75,19 +75,23 @@ def test_gemm_gelu_silu():
     assert _rel_l2(out, ref) < 6e-3
 
 
-def test_gemm_gate_resid():
+def test_gemm_gate_resid_batched_views():
+    """Batched rows: A, out and resid are row-slices of a wider [B, S_all, *] buffer (the joint
+    [txt;img] activation layout of the model), gate is per batch item."""
     from gpt_image_edit_b200 import ops
 
-    B, S, N, K = 2, 300, 384, 256
-    x, w, b = _mk(B * S, N, K, seed=3)
-    g = torch.Generator(device="cuda").manual_seed(9)
-    resid = torch.randn(B * S, N, device="cuda", generator=g).bfloat16()
+    B, S_all, S0, S, N, K = 2, 420, 40, 300, 384, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xa = torch.randn(B, S_all, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    ha = torch.randn(B, S_all, N, device="cuda", generator=g).bfloat16()
     gate = torch.randn(B, N, device="cuda", generator=g).bfloat16()
-    out = ops.linear(x, w, b, epilogue=ops.EPI_GATE_RESID, resid=resid, gate=gate, rows_per_batch=S)
+    x, h = xa[:, S0:S0 + S], ha[:, S0:S0 + S]
+    h_before = ha.clone()
     lin = (x.float() @ w.float().t() + b.float()).bfloat16()
-    ref = resid.float() + (gate.float().repeat_interleave(S, 0) * lin.float()).bfloat16().float()
-    assert _rel_l2(out, ref) < 6e-3
-    # in-place residual (resid aliases out)
-    r2 = resid.clone()
-    ops.linear(x, w, b, epilogue=ops.EPI_GATE_RESID, resid=r2, gate=gate, rows_per_batch=S, out=r2)
-    assert torch.equal(r2, out)
+    ref = h.float() + (gate.float()[:, None] * lin.float()).bfloat16().float()
+    ops.linear(x, w, b, epilogue=ops.EPI_GATE_RESID, resid=h, gate=gate, out=h)  # in place
+    assert _rel_l2(h, ref) < 6e-3
+    # rows outside the slice untouched
+    assert torch.equal(ha[:, :S0], h_before[:, :S0]) and torch.equal(ha[:, S0 + S:], h_before[:, S0 + S:])

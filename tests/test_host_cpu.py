@@ -1,0 +1,105 @@
+"""CPU tests of the host logic: sigma schedule, integer step indexing, packing, ids, size rules,
+and that libb2f loads and exports every symbol include/b2f.h declares (no compute without a GPU)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from gpt_image_edit_b200 import _lib
+
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(_lib.lib, name), f"libb2f.so does not export {name}"
+    assert set(declared) == set(_lib._SIGNATURES), "ctypes signatures out of sync with include/b2f.h"
+    assert _lib.lib.b2f_version() >= 1
+    assert _lib.lib.b2f_strerror(-5).decode() == "no sm_100 device"
+
+
+def test_no_cpu_fallback_paths():
+    """Without a GPU every compute entry point must refuse, not fall back."""
+    from gpt_image_edit_b200 import _lib, ops
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x = torch.zeros(8, 64, dtype=torch.bfloat16)
+    with pytest.raises(_lib.B2FError):
+        ops.linear(x, x)
+    with pytest.raises(_lib.B2FError):
+        from gpt_image_edit_b200.flux_transformer import B200FluxTransformer2DModel
+        B200FluxTransformer2DModel(device="cpu")
+    # raw ABI: no device -> B2F_ERR_NODEVICE
+    rc = _lib.lib.b2f_gemm_bf16(16, 64, 0, 16, 64, None, 16, 64, 0, 1, 8, 64, 64, 0, None, 0, 0, None, 0, None)
+    assert rc == -5
+
+
+def test_sigma_schedule_matches_survey_pins():
+    """mu(4096)=1.15, mu(256)=0.5; first 28-step timesteps 1000.0, 988.4086, 976.2225."""
+    from gpt_image_edit_b200.pipeline import calculate_shift
+    from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    from oracle.pipeline_oracle import EulerSchedulerOracle
+    from oracle.pipeline_oracle import calculate_shift as cs_oracle
+
+    assert math.isclose(calculate_shift(4096), 1.15, rel_tol=1e-12)
+    assert math.isclose(calculate_shift(256), 0.5, rel_tol=1e-12)
+    assert calculate_shift(1024) == cs_oracle(1024)
+    s = FlowMatchEulerDiscreteScheduler()
+    sig = np.linspace(1.0, 1 / 28, 28)
+    s.set_timesteps(sigmas=sig, mu=1.15)
+    assert torch.allclose(s.timesteps[:3], torch.tensor([1000.0, 988.4086, 976.2225]), atol=2e-4)
+    assert s.sigmas.shape == (29,) and s.sigmas[-1] == 0
+    o = EulerSchedulerOracle()
+    o.set_timesteps(sig, 1.15)
+    assert torch.equal(o.timesteps, s.timesteps) and torch.equal(o.sigmas, s.sigmas)
+    # sum of dt telescopes to -sigma_0
+    assert math.isclose(sum(s.dt(i) for i in range(28)), -1.0, abs_tol=1e-6)
+    # dt is the fp32 difference of fp32 sigmas (bit-exact with the 0-dim tensor subtraction)
+    for i in range(28):
+        assert s.dt(i) == float((o.sigmas[i + 1] - o.sigmas[i]).item())
+
+
+def test_integer_step_index_is_bit_exact():
+    from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
+
+    s = FlowMatchEulerDiscreteScheduler()
+    s.set_timesteps(sigmas=np.linspace(1.0, 1 / 4, 4), mu=0.5)
+    assert s.step_index is None and s.begin_index is None
+    s.set_begin_index(0)
+    assert s.begin_index == 0
+    s._init_step_index(s.timesteps[0])
+    assert s.step_index == 0
+    # without begin_index the index is looked up from the timestep value, as diffusers does
+    s2 = FlowMatchEulerDiscreteScheduler()
+    s2.set_timesteps(sigmas=np.linspace(1.0, 1 / 4, 4), mu=0.5)
+    s2._init_step_index(s2.timesteps[2])
+    assert s2.step_index == 2
+    with pytest.raises(Exception):
+        s2.step(torch.zeros(1, 4, 64), s2.timesteps[2], torch.zeros(1, 4, 64))  # CPU tensors: refused
+
+
+def test_pack_unpack_ids_match_oracle_and_roundtrip():
+    from gpt_image_edit_b200.pipeline import FluxKontextPipeline as P
+    from oracle import pipeline_oracle as po
+
+    x = torch.randn(2, 16, 12, 20)
+    packed = P._pack_latents(x, 2, 16, 12, 20)
+    assert packed.shape == (2, 60, 64)
+    assert torch.equal(packed, po.pack_latents(x))
+    # inside a token the order is (c, dy, dx)
+    assert packed[0, 0, 5].item() == x[0, 1, 0, 1].item()  # c=1,dy=0,dx=1 -> 1*4+0*2+1
+    back = P._unpack_latents(packed, 12 * 8, 20 * 8, 8)
+    assert torch.equal(back, x)
+    ids = P._prepare_latent_image_ids(1, 6, 10, "cpu", torch.float32)
+    assert torch.equal(ids, po.latent_image_ids(6, 10))
+    assert ids[13].tolist() == [0.0, 1.0, 3.0]
+
+
+def test_size_rule_rescales_to_max_area():
+    from oracle.pipeline_oracle import target_size
+
+    assert target_size(256, 256, 1024 ** 2) == (1024, 1024)     # reference quirk: 256 request -> 1 MP
+    assert target_size(256, 256, 256 * 256) == (256, 256)
+    assert target_size(720, 1280, 1024 ** 2) == (768, 1360)

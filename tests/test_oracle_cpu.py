@@ -1,0 +1,106 @@
+"""CPU tests that pin the oracle (the reference itself ships no tests or golden vectors).
+
+  * oracle == torchtitan's independent FLUX implementation (committed golden from
+    tests/golden/make_golden.py, float64 there) to fp32 round-off;
+  * oracle regression fixture including the guidance MLP / bf16 timestep chain;
+  * live cross-check against torchtitan when it is importable (it is in this image).
+"""
+import math
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def _rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def _run(fo, blob, dtype, guidance):
+    cfg = fo.FluxConfig(**blob["cfg"], guidance_embeds=guidance)
+    sd = fo.make_synthetic_state_dict(cfg, seed=blob["seed"], dtype=dtype)
+    i = blob["inputs"]
+    f = lambda t: t.to(dtype)
+    return fo.flux_forward(sd, cfg, f(i["hidden_states"]), f(i["encoder_hidden_states"]), f(i["pooled_projections"]),
+                           i["timestep"].to(dtype) if not guidance else i["timestep"], i["img_ids"], i["txt_ids"],
+                           guidance=i["guidance"].float() if guidance else None)
+
+
+def test_oracle_matches_torchtitan_golden():
+    from oracle import flux_oracle as fo
+
+    blob = torch.load(GOLD / "flux_toy_titan.pt")
+    out64 = _run(fo, blob, torch.float64, guidance=False)
+    # golden was produced in float64 then stored as fp32
+    assert _rel_l2(out64, blob["output"]) < 2e-6
+    out32 = _run(fo, blob, torch.float32, guidance=False)
+    assert _rel_l2(out32, blob["output"]) < 5e-5
+
+
+def test_oracle_regression_fixture_with_guidance():
+    from oracle import flux_oracle as fo
+
+    blob = torch.load(GOLD / "flux_toy_oracle.pt")
+    out = _run(fo, blob, torch.float32, guidance=True)
+    assert _rel_l2(out, blob["output"]) < 1e-5
+
+
+def test_live_crosscheck_against_torchtitan_if_available():
+    pytest.importorskip("torchtitan.experiments.flux.model.model")
+    sys.path.insert(0, str(GOLD))
+    import make_golden as mg
+    from oracle import flux_oracle as fo
+
+    cfg = fo.FluxConfig(**mg.TOY, guidance_embeds=False)
+    sd = fo.make_synthetic_state_dict(cfg, seed=123, dtype=torch.float64)
+    inp = mg.toy_inputs(cfg, B=2, S_txt=17, HL=4, WL=7, seed=9)
+    m = mg.titan_from_diffusers(cfg, sd)
+    with torch.no_grad():
+        ref = m(img=inp["hidden_states"], img_ids=inp["img_ids"][None].double().expand(2, -1, -1),
+                txt=inp["encoder_hidden_states"], txt_ids=inp["txt_ids"][None].double().expand(2, -1, -1),
+                timesteps=inp["timestep"], y=inp["pooled_projections"])
+        out = fo.flux_forward(sd, cfg, inp["hidden_states"], inp["encoder_hidden_states"], inp["pooled_projections"],
+                              inp["timestep"], inp["img_ids"], inp["txt_ids"], guidance=None)
+    assert _rel_l2(out, ref) < 1e-9
+
+
+def test_timestep_rounding_chain_matches_survey():
+    """fp32 timesteps reach time_proj as bf16-rounded values 1000, 988, 976, 964, 948."""
+    ts = torch.tensor([1000.0, 988.4086, 976.2225, 963.39, 949.87])
+    seen = ((ts.bfloat16() / 1000).bfloat16() * 1000).float()
+    assert seen.tolist() == [1000.0, 988.0, 976.0, 964.0, 948.0]
+    g = (torch.tensor([3.5]).bfloat16() * 1000).float()
+    assert g.item() == 3504.0
+
+
+def test_rope_tables_text_identity_and_layout():
+    from oracle import flux_oracle as fo
+
+    ids = torch.tensor([[0, 0, 0], [1, 3, 5]], dtype=torch.float32)
+    cos, sin = fo.rope_tables(ids)
+    assert cos.shape == (2, 128) and cos.dtype == torch.float32
+    assert torch.all(cos[0] == 1) and torch.all(sin[0] == 0)           # text ids -> identity rotation
+    assert torch.equal(cos[:, 0::2], cos[:, 1::2])                      # repeat_interleave(2)
+    # axis layout: 8 pairs idx | 28 pairs row | 28 pairs col
+    assert math.isclose(cos[1, 0].item(), math.cos(1.0), rel_tol=1e-6)
+    assert math.isclose(cos[1, 16].item(), math.cos(3.0), rel_tol=1e-6)
+    assert math.isclose(cos[1, 16 + 56].item(), math.cos(5.0), rel_tol=1e-6)
+
+
+def test_vae_oracle_matches_torchtitan_golden():
+    from oracle import vae_oracle as vo
+
+    blob = torch.load(GOLD / "vae_toy_titan.pt")
+    cfg = vo.VaeConfig(**blob["cfg"])
+    sd = vo.make_synthetic_state_dict(cfg, seed=blob["seed"], dtype=torch.float64)
+    mean = vo.encode_mode(sd, cfg, blob["x"].double())
+    img = vo.decode(sd, cfg, blob["z"].double())
+    assert mean.shape == blob["mean"].shape and img.shape == blob["image"].shape
+    assert _rel_l2(mean, blob["mean"]) < 2e-6
+    assert _rel_l2(img, blob["image"]) < 2e-6
+    # fp32 run stays within fp32 round-off of the float64 golden
+    sd32 = {k: v.float() for k, v in sd.items()}
+    assert _rel_l2(vo.decode(sd32, cfg, blob["z"]), blob["image"]) < 1e-4
