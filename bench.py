@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — edited images/sec at 1024x1024, 28 Euler steps (BASELINE.json metric), N GPUs of one box.
+
+  python bench.py --gpus 1 --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      CPU arm: the oracle restatement of the
+                                                            reference's diffusers path on host cores
+
+One "step" = one complete edit of one batch of synthetic (source image, instruction-embedding) pairs:
+the FluxKontextPipeline call (VAE-encode of the context image when a VAE is attached, 28 MMDiT
+forwards + Euler updates, VAE-decode).  Workload = BASELINE.json configs[1] ("C1024"):
+B=1 per GPU, S_txt=544, S_tgt=S_ctx=4096, d=3072, 19+38 blocks, bf16, seeded synthetic weights
+(no checkpoints exist offline).  Multi-GPU = batch sharding: every rank owns a full replica
+(weights broadcast once from rank 0 over NCCL) and its own batch items; no collective in the loop.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D_MODEL, N_DOUBLE, N_SINGLE, S_TXT = 3072, 19, 38, 544
+
+
+def flops_per_forward(S_img: int, S_txt: int, n_double=N_DOUBLE, n_single=N_SINGLE, d=D_MODEL, joint=4096) -> float:
+    """Algorithmic FLOPs of one MMDiT forward per sample (SURVEY.md §8d formula, generalised)."""
+    S = S_img + S_txt
+    nb = n_double + n_single
+    lin = nb * 24.0 * d * d * S                 # qkv/out/mlp projections of every block
+    attn = nb * 4.0 * S * S * d                 # QK^T and PV
+    emb = 2.0 * S_img * 64 * d * 2 + 2.0 * S_txt * joint * d
+    ada = 2.0 * (n_double * 12 + n_single * 3 + 2) * d * d
+    return lin + attn + emb + ada
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return dict(tensor_burst=j["bf16_tflops"], tensor_sustained=j["bf16_tflops_sustained"], hbm=j["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(tensor_burst=1590.0, tensor_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_sample(height: int, width: int, steps_28: int, threads: int | None = None) -> dict:
+    """Times the oracle (PyTorch restatement of the reference's diffusers arithmetic, fp32) on host
+    cores for ONE double-stream + ONE single-stream block at the full C1024 shapes, then extrapolates
+    x19 / x38 / x28 steps to seconds per image (labelled as extrapolated)."""
+    from oracle import flux_oracle as fo
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    S_img = 2 * (height // 16) * (width // 16)
+    cfg = fo.FluxConfig(num_layers=1, num_single_layers=1)
+    sd = fo.make_synthetic_state_dict(cfg, seed=0, dtype=torch.float32)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, S_img, D_MODEL, generator=g)
+    c = torch.randn(1, S_TXT, D_MODEL, generator=g)
+    temb = torch.randn(1, D_MODEL, generator=g)
+    ids = torch.zeros(S_TXT + S_img, 3)
+    cos, sin = fo.rope_tables(ids)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        c2, x2 = fo.double_block(sd, 0, cfg, x, c, temb, cos, sin)
+        t_d = time.perf_counter() - t0
+        h = torch.cat([c2, x2], 1)
+        t0 = time.perf_counter()
+        fo.single_block(sd, 0, cfg, h, temb, cos, sin)
+        t_s = time.perf_counter() - t0
+    sec_per_image = steps_28 * (N_DOUBLE * t_d + N_SINGLE * t_s)
+    return dict(value=1.0 / sec_per_image, unit="images/s", cores=threads, kind="port",
+                sample=f"oracle fp32: 1 double ({t_d:.2f}s) + 1 single ({t_s:.2f}s) block at S={S_TXT + S_img}, d={D_MODEL}; "
+                       f"extrapolated x{N_DOUBLE}/x{N_SINGLE} blocks x{steps_28} steps (VAE/conditioning excluded)",
+                sec_per_image_extrapolated=sec_per_image)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        last = cpu_reference_sample(args.height, args.width, args.num_inference_steps)
+        if i >= args.warmup:
+            times.append(last["sec_per_image_extrapolated"])
+        if time.perf_counter() - t0 > 120 and i + 1 >= args.warmup + 1:
+            break
+    sec = float(np.mean(times)) if times else last["sec_per_image_extrapolated"]
+    val = 1.0 / sec
+    cb = {k: last[k] for k in ("unit", "cores", "kind", "sample")}
+    cb["value"] = val
+    print(json.dumps({
+        "impl": "reference", "metric": "edited images/sec @1024px 28-step", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1), "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, world):
+    S_img = 2 * (args.height // 16) * (args.width // 16)
+    return {"workload": f"C{args.height}: FLUX.1-Kontext-dev MMDiT 19+38 blocks d=3072, {args.height}x{args.width}, "
+                        f"{args.num_inference_steps} Euler steps, S_txt={S_TXT}, S_img={S_img}, guidance 3.5",
+            "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world,
+            "parallelism": f"batch-sharded replicas x{world} (weights broadcast once over NCCL)",
+            "l2": "inputs larger than L2 (23.8 GB of weights stream every forward)",
+            "conditioning": "prompt_embeds/pooled are synthetic inputs (Qwen2.5-VL/T5/CLIP encoders not in the timed region)"}
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--num-inference-steps", type=int, default=28)
+    ap.add_argument("--layers", type=str, default=None, help="debug: 'D,S' block counts (invalidates the number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+
+    from gpt_image_edit_b200 import _lib
+    from gpt_image_edit_b200.flux_transformer import B200FluxTransformer2DModel, FluxTransformerConfig
+    from gpt_image_edit_b200.pipeline import FluxKontextPipeline
+    from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nd, ns = (N_DOUBLE, N_SINGLE) if not args.layers else map(int, args.layers.split(","))
+    model = B200FluxTransformer2DModel(FluxTransformerConfig(num_layers=nd, num_single_layers=ns), device=dev)
+    # rank 0 draws the synthetic weights (N(0, 0.02^2)), everyone else receives them
+    if rank == 0:
+        model.randomize_(seed=0)
+    if world > 1:
+        for t in model._store.values():
+            dist.broadcast(t, src=0)
+    try:
+        from gpt_image_edit_b200.vae import B200AutoencoderKL
+        vae = B200AutoencoderKL(device=dev)
+        if rank == 0:
+            vae.randomize_(seed=1)
+        if world > 1:
+            for t in vae.storage():
+                dist.broadcast(t, src=0)
+    except ImportError:
+        vae = None
+    pipe = FluxKontextPipeline(transformer=model, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler())
+
+    B, H, W = args.batch_per_gpu, args.height, args.width
+    S_img = 2 * (H // 16) * (W // 16)
+    g = torch.Generator().manual_seed(1 + rank)
+    src_u8 = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
+    src = (src_u8.float() / 127.5 - 1.0).pin_memory()                       # [-1,1] fp32 NCHW, as cli.py:99-116
+    g2 = torch.Generator().manual_seed(2 + rank)
+    pe_h = torch.randn(B, S_TXT, 4096, generator=g2).bfloat16().pin_memory()
+    pp_h = torch.randn(B, 768, generator=g2).bfloat16().pin_memory()
+    noise_h = torch.stack([torch.randn(S_img // 2, 64, generator=torch.Generator().manual_seed(42 + rank * B + i))
+                           for i in range(B)]).bfloat16().pin_memory()
+    ctx_lat_h = torch.randn(B, 16, H // 8, W // 8, generator=g2).bfloat16().pin_memory()  # only used without a VAE
+
+    def one_edit(from_host: bool):
+        nb = lambda t: t.to(dev, non_blocking=True)
+        if from_host:
+            pe, pp, noise = nb(pe_h), nb(pp_h), nb(noise_h)
+            image = nb(src) if vae is not None else nb(ctx_lat_h)
+        else:
+            pe, pp, noise = dev_in["pe"], dev_in["pp"], dev_in["noise"].clone()
+            image = dev_in["image"]
+        out = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pp, height=H, width=W,
+                   num_inference_steps=args.num_inference_steps, guidance_scale=3.5, latents=noise,
+                   max_area=H * W, _auto_resize=False, output_type="pt_raw" if vae is not None else "latent").images
+        if from_host:
+            if vae is not None:
+                out = ((out.float() / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
+            return out.to("cpu", non_blocking=False)
+        return out
+
+    dev_in = dict(pe=pe_h.to(dev), pp=pp_h.to(dev), noise=noise_h.to(dev),
+                  image=(src if vae is not None else ctx_lat_h).to(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, from_host):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s.record()
+        for _ in range(n):
+            one_edit(from_host)
+        e.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = s.elapsed_time(e)
+        if from_host:
+            ms = max(ms, wall * 1e3)  # the D2H read ends on the host
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        one_edit(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.prof_enable(True)
+    n0 = _lib.launch_count()
+    ms_total = timed(args.steps, False)
+    launches = _lib.launch_count() - n0
+    prof = _lib.prof_collect()
+    _lib.prof_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    one_edit(True)
+    ms_e2e = timed(args.steps, True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_per_edit = ms_total / args.steps
+    value = world * B / (ms_per_edit / 1e3)
+    e2e = world * B / (ms_e2e / args.steps / 1e3)
+    f_fwd = flops_per_forward(S_img, S_TXT, nd, ns) * B
+    f_edit = f_fwd * args.num_inference_steps
+    gm = prof["gemm"]
+    dom = max(("gemm", "attention"), key=lambda k: prof[k]["ms"])
+    pd = prof[dom]
+    achieved = pd["flops"] / (pd["ms"] / 1e3) / 1e12 if pd["ms"] > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": {"gemm": "gemm_bf16_kernel (tcgen05)", "attention": "attn_fwd_kernel (tcgen05)"}[dom],
+            "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_sustained"],
+            "frac_of_burst_peak": achieved / pk["tensor_burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+            "avg_launch_ms": pd["ms"] / max(pd["launches"], 1), "launches": pd["launches"],
+            "algorithmic_tflop_per_launch": pd["flops"] / max(pd["launches"], 1) / 1e12, "traffic": None,
+            "share_of_step": pd["ms"] / ms_total,
+            "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                            "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
+                            "gbps": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["flops"] == 0 else None}
+                        for k, v in prof.items() if v["launches"]}}
+    line = {
+        "metric": "edited images/sec @1024px 28-step", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_edit, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": dict(workload_config(args, world), vae="hand-written (included)" if vae is not None else
+                       "EXCLUDED (context latents supplied, latent output)"),
+        "ms_per_denoise_step": ms_per_edit / args.num_inference_steps,
+        "model_tflops_per_gpu": f_edit / (ms_per_edit / 1e3) / 1e12,
+        "model_frac_of_sustained_peak": f_edit / (ms_per_edit / 1e3) / 1e12 / pk["tensor_sustained"],
+        "e2e": {"value": e2e, "unit": "images/s",
+                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in
+                                              (pe_h, pp_h, noise_h, src if vae is not None else ctx_lat_h))),
+                "d2h_bytes_per_step": int(B * 3 * H * W if vae is not None else noise_h.numel() * 2)},
+        "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_sample(H, W, args.num_inference_steps)
+        cb.pop("sec_per_image_extrapolated", None)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

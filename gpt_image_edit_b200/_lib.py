@@ -45,6 +45,8 @@ _SIGNATURES = {
     "b2f_version": (_i32, []),
     "b2f_device_info": (_i32, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_size_t)]),
     "b2f_launch_count": (C.c_uint64, []),
+    "b2f_prof_enable": (None, [_i32]),
+    "b2f_prof_collect": (_i32, [_i32, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b2f_gemm_bf16": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
     "b2f_ln_modulate": (_i32, [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, C.c_float, _vp]),
     "b2f_rmsnorm_rope": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, C.c_float, _vp]),
@@ -96,6 +98,23 @@ def stream_ptr(stream: "torch.cuda.Stream | None" = None) -> int:
 
 def ptr(t: "torch.Tensor | None") -> int | None:
     return None if t is None else int(t.data_ptr())
+
+
+KERNEL_CLASSES = ("gemm", "attention", "ln_modulate", "rmsnorm_rope", "conv", "other")
+
+
+def prof_enable(on: bool) -> None:
+    lib.b2f_prof_enable(int(on))
+
+
+def prof_collect() -> dict:
+    """{class: dict(ms, launches, flops, bytes)} since the last collect (synchronises the events)."""
+    out = {}
+    for i, name in enumerate(KERNEL_CLASSES):
+        ms, n, fl, by = C.c_double(), _i64(), C.c_double(), C.c_double()
+        check(lib.b2f_prof_collect(i, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)), "b2f_prof_collect")
+        out[name] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+    return out
 
 
 def launch_count() -> int:

@@ -356,7 +356,10 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
+  prof_begin(KC_ATTN, stream);
   attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  prof_end(KC_ATTN, stream, (causal ? 2.0 : 4.0) * B * H * (double)Sq * Skv * DH,
+           2.0 * DH * B * (2.0 * H * Sq + 2.0 * Hkv * Skv));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("attn_fwd_kernel");
   return B2F_OK;

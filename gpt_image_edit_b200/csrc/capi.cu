@@ -19,6 +19,8 @@ int rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void*
 int euler_step(void* x, int64_t ldx, const void* v, int64_t ldv, int64_t rows, int cols, float dt,
                cudaStream_t stream);
 int silu(const void* x, void* y, int64_t n, cudaStream_t stream);
+void prof_set(bool on);
+int prof_collect(int kc, double* ms, int64_t* launches, double* flops, double* bytes);
 int rope_tables(const float* ids, int S, const int* axes_dim, double theta, float* cos, float* sin,
                 cudaStream_t stream);
 int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -62,6 +64,11 @@ int b2f_device_info(int* num_sms, int* cc_major, int* cc_minor, size_t* smem_opt
 }
 
 uint64_t b2f_launch_count(void) { return b2f::g_launch_count.load(); }
+
+void b2f_prof_enable(int on) { b2f::prof_set(on != 0); }
+int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* flops, double* bytes) {
+  return b2f::prof_collect(kernel_class, ms, launches, flops, bytes);
+}
 
 int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
                   const void* bias, void* out, int64_t ldc, int64_t out_batch_stride, int batch,

@@ -325,6 +325,11 @@ int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* 
                 mod_ld, static_cast<__nv_bfloat16*>(out), ldo, out_batch_stride, batch, rows, D, eps};
   const long long total = (long long)batch * rows;
   const unsigned grid = (unsigned)((total + 3) / 4);
+  prof_begin(KC_LNMOD, stream);
+  struct ProfEnd {
+    cudaStream_t s; double b;
+    ~ProfEnd() { prof_end(KC_LNMOD, s, 0.0, b); }
+  } prof_end_guard{stream, 4.0 * (double)total * D};
   if (D <= 1024)
     ln_modulate_kernel<4><<<grid, 128, 0, stream>>>(p);
   else if (D <= 3072)
@@ -351,7 +356,9 @@ int rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void*
                    static_cast<const __nv_bfloat16*>(wq_b), static_cast<const __nv_bfloat16*>(wk_b),
                    cos, sin, batch, S, H, n_a, eps};
   const long long total = (long long)batch * S;
+  prof_begin(KC_NORMROPE, stream);
   rmsnorm_rope_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(p);
+  prof_end(KC_NORMROPE, stream, 0.0, 8.0 * (double)total * H * 128);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("rmsnorm_rope_kernel");
   return B2F_OK;

@@ -279,7 +279,10 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cu
   p.panel_n = BN == 256 ? 16 : 32;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = num_tiles < device_info().num_sms ? num_tiles : device_info().num_sms;
+  prof_begin(KC_GEMM, stream);
   gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * p.K,
+           2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("gemm_bf16_kernel");
   return B2F_OK;

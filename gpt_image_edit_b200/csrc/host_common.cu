@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace b2f {
 
@@ -26,6 +27,69 @@ const DeviceInfo& device_info() {
     info.ok = (major == 10) && info.num_sms > 0;
   });
   return info;
+}
+
+// ------------------------------------------------------------------ event profiler
+namespace {
+struct ProfState {
+  bool enabled = false;
+  std::mutex mu;
+  std::vector<cudaEvent_t> pool;
+  struct Rec { cudaEvent_t a, b; };
+  std::vector<Rec> recs[KC_COUNT];
+  double flops[KC_COUNT] = {0}, bytes[KC_COUNT] = {0};
+  cudaEvent_t pending[KC_COUNT] = {nullptr};
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+ProfState g_prof;
+}  // namespace
+
+bool prof_enabled() { return g_prof.enabled; }
+void prof_begin(int kc, cudaStream_t s) {
+  if (!g_prof.enabled) return;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  cudaEvent_t e = g_prof.get();
+  cudaEventRecord(e, s);
+  g_prof.pending[kc] = e;
+}
+void prof_end(int kc, cudaStream_t s, double flops, double bytes) {
+  if (!g_prof.enabled) return;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  cudaEvent_t e = g_prof.get();
+  cudaEventRecord(e, s);
+  g_prof.recs[kc].push_back({g_prof.pending[kc], e});
+  g_prof.flops[kc] += flops;
+  g_prof.bytes[kc] += bytes;
+}
+void prof_set(bool on) { g_prof.enabled = on; }
+int prof_collect(int kc, double* ms, int64_t* launches, double* flops, double* bytes) {
+  if (kc < 0 || kc >= KC_COUNT) return B2F_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  double total = 0;
+  for (auto& r : g_prof.recs[kc]) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return B2F_ERR_CUDA;
+    float t = 0;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    total += t;
+    g_prof.pool.push_back(r.a);
+    g_prof.pool.push_back(r.b);
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = (int64_t)g_prof.recs[kc].size();
+  if (flops) *flops = g_prof.flops[kc];
+  if (bytes) *bytes = g_prof.bytes[kc];
+  g_prof.recs[kc].clear();
+  g_prof.flops[kc] = g_prof.bytes[kc] = 0;
+  return B2F_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -88,13 +152,13 @@ int make_tmap_3d_rows(CUtensorMap* out, const void* gptr, uint64_t width, uint64
 }
 
 int make_tmap_4d_bf16(CUtensorMap* out, const void* gptr, uint64_t n, uint64_t h, uint64_t w,
-                      uint64_t c, uint32_t box_h, uint32_t box_w, uint32_t box_c) {
+                      uint64_t c, uint32_t box_h, uint32_t box_w, uint32_t box_c, uint32_t stride) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return B2F_ERR_CUDA;
   cuuint64_t dims[4] = {c, w, h, n};
   cuuint64_t strides[3] = {c * 2, w * c * 2, h * w * c * 2};
-  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {box_c, box_w * stride, box_h * stride, 1};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gptr), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -26,8 +26,16 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 int make_tmap_3d_rows(CUtensorMap* out, const void* gptr, uint64_t width, uint64_t rows,
                       uint64_t batch, uint64_t ld_elems, uint64_t batch_stride_elems);
 // 4-D bf16 tensor map for NHWC activations: global [n, h, w, c], box [1, box_h, box_w, box_c].
+// `stride` (1 or 2) is the traversal stride in h and w: the box still delivers box_h x box_w pixels.
 int make_tmap_4d_bf16(CUtensorMap* out, const void* gptr, uint64_t n, uint64_t h, uint64_t w,
-                      uint64_t c, uint32_t box_h, uint32_t box_w, uint32_t box_c);
+                      uint64_t c, uint32_t box_h, uint32_t box_w, uint32_t box_c, uint32_t stride);
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
+// figures).  Disabled by default: zero overhead on the normal path.
+enum KernelClass { KC_GEMM = 0, KC_ATTN = 1, KC_LNMOD = 2, KC_NORMROPE = 3, KC_CONV = 4, KC_OTHER = 5, KC_COUNT = 6 };
+bool prof_enabled();
+void prof_begin(int kc, cudaStream_t s);
+void prof_end(int kc, cudaStream_t s, double flops, double bytes);
 
 inline int cuda_err(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return B2F_OK;

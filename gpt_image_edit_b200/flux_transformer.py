@@ -163,6 +163,24 @@ class B200FluxTransformer2DModel(torch.nn.Module):
                     v.copy_(sd[k])
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
+    @torch.no_grad()
+    def randomize_(self, seed: int = 0, std: float = 0.02, bias_std: float = 0.02):
+        """Seeded synthetic weights drawn on the device (no checkpoints exist offline):
+        weights ~ N(0, std^2), biases ~ N(0, bias_std^2), RMSNorm weights = 1."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        for k, t in self._store.items():
+            if k.endswith("norm_q.weight") or k.endswith("norm_k.weight") or "norm_added" in k:
+                t.fill_(1.0)
+            else:
+                s_ = bias_std if k.endswith(".bias") else std
+                # draw in fp32 chunks to bound temporary memory for the multi-GB fused tensors
+                flat = t.view(-1)
+                step = 1 << 26
+                for o in range(0, flat.numel(), step):
+                    n = min(step, flat.numel() - o)
+                    flat[o:o + n] = (torch.randn(n, device=self.device, generator=g) * s_).to(torch.bfloat16)
+        return self
+
     def named_parameters_diffusers(self):
         yield from self._views.items()
 

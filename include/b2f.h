@@ -40,6 +40,14 @@ int b2f_device_info(int* num_sms, int* cc_major, int* cc_minor, size_t* smem_opt
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 uint64_t b2f_launch_count(void);
 
+/* Per-kernel-class device timing for bench.py's roofline: when enabled, every launch of that class
+ * is bracketed by CUDA events on the launching stream.  b2f_prof_collect synchronises those events,
+ * returns their summed duration (ms), the launch count and the algorithmic FLOPs / bytes the
+ * launches declared, and resets the class.  Classes: 0 gemm, 1 attention, 2 ln_modulate,
+ * 3 rmsnorm_rope, 4 conv, 5 other. */
+void b2f_prof_enable(int on);
+int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* flops, double* bytes);
+
 /* ------------------------------------------------------------------------------------------
  * Linear layer: out[M,N] = epilogue(A[M,K] · W[N,K]^T + bias[N]).  tcgen05.mma, TMA, TMEM.
  * Replaces torch.nn.functional.linear → cuBLASLt as reached by diffusers' nn.Linear modules

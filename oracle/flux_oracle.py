@@ -183,6 +183,10 @@ def attention(q, k, v, attn_mask=None):
     """`F.scaled_dot_product_attention(q, k, v, attn_mask, dropout_p=0, is_causal=False)`; q,k,v [B,H,S,dh]."""
     if q.dtype == torch.float64 or not q.is_cuda:
         # explicit math keeps the CPU oracle independent of SDPA backend selection
+        if q.shape[1] > 1 and q.shape[1] * q.shape[2] * k.shape[2] * 4 > (2 << 30):
+            # bound the score matrix to one head at a time (full-size CPU baseline runs)
+            return torch.cat([attention(q[:, h:h + 1], k[:, h:h + 1], v[:, h:h + 1], attn_mask)
+                              for h in range(q.shape[1])], dim=1)
         scale = 1.0 / math.sqrt(q.shape[-1])
         s = torch.matmul(q, k.transpose(-1, -2)) * scale
         if attn_mask is not None:
