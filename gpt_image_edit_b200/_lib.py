@@ -34,6 +34,11 @@ lib = _load()
 
 _vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int
 
+class VaeCfg(C.Structure):
+    _fields_ = [("block_out", C.c_int * 4), ("layers_per_block", C.c_int), ("latent_channels", C.c_int),
+                ("in_channels", C.c_int), ("out_channels", C.c_int)]
+
+
 class FluxCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "num_heads", "head_dim", "num_double", "num_single", "in_channels", "out_channels",
@@ -53,6 +58,18 @@ _SIGNATURES = {
     "b2f_euler_step": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, C.c_float, _vp]),
     "b2f_silu": (_i32, [_vp, _vp, _i64, _vp]),
     "b2f_rope_tables": (_i32, [_vp, _i32, C.POINTER(_i32), C.c_double, _vp, _vp, _vp]),
+    "b2f_conv3x3": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b2f_groupnorm_silu": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, C.c_float, _i32, _vp]),
+    "b2f_upsample2x": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "b2f_nchw_to_nhwc_pad": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b2f_softmax_rows": (_i32, [_vp, _i64, _i32, _i32, C.c_float, _vp]),
+    "b2f_transpose_bf16": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "b2f_vae_create": (_i32, [C.POINTER(_vp), _vp]),
+    "b2f_vae_destroy": (None, [_vp]),
+    "b2f_vae_bind_weight": (_i32, [_vp, C.c_char_p, _vp, _i64]),
+    "b2f_vae_workspace_bytes": (C.c_size_t, [_vp, _i32, _i32, _i32]),
+    "b2f_vae_encode": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, C.c_size_t, _vp]),
+    "b2f_vae_decode": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, C.c_size_t, _vp]),
     "b2f_flux_create": (_i32, [C.POINTER(_vp), _vp]),
     "b2f_flux_destroy": (None, [_vp]),
     "b2f_flux_bind_weight": (_i32, [_vp, C.c_char_p, _vp, _i64]),

@@ -20,6 +20,16 @@ int euler_step(void* x, int64_t ldx, const void* v, int64_t ldv, int64_t rows, i
                cudaStream_t stream);
 int silu(const void* x, void* y, int64_t n, cudaStream_t stream);
 void prof_set(bool on);
+int conv3x3(const void* in, const void* w, const void* bias, void* out, const void* resid, int N,
+            int Hin, int Win, int Cin, int Cout, int stride, int out_nchw, cudaStream_t stream);
+int groupnorm_silu(const void* x, const void* gamma, const void* beta, void* y, double* stats_ws,
+                   int N, long long P, int C, float eps, int silu, cudaStream_t stream);
+int upsample2x(const void* in, void* out, int N, int H, int W, int C, cudaStream_t stream);
+int nchw_to_nhwc_pad(const void* in, int in_is_f32, void* out, int N, int C, int H, int W, int Cpad,
+                     cudaStream_t stream);
+int softmax_rows(void* s, int64_t ld, int rows, int L, float scale, cudaStream_t stream);
+int transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int Cc,
+                   cudaStream_t stream);
 int prof_collect(int kc, double* ms, int64_t* launches, double* flops, double* bytes);
 int rope_tables(const float* ids, int S, const int* axes_dim, double theta, float* cos, float* sin,
                 cudaStream_t stream);
@@ -104,6 +114,31 @@ int b2f_euler_step(void* x, int64_t ldx, const void* v, int64_t ldv, int64_t row
 int b2f_rope_tables(const float* ids, int S, const int* axes_dim, double theta, float* cos,
                     float* sin, b2f_stream_t stream) {
   return b2f::rope_tables(ids, S, axes_dim, theta, cos, sin, static_cast<cudaStream_t>(stream));
+}
+
+int b2f_conv3x3(const void* in, const void* w, const void* bias, void* out, const void* resid, int N,
+                int Hin, int Win, int Cin, int Cout, int stride, int out_nchw, b2f_stream_t stream) {
+  return b2f::conv3x3(in, w, bias, out, resid, N, Hin, Win, Cin, Cout, stride, out_nchw,
+                      static_cast<cudaStream_t>(stream));
+}
+int b2f_groupnorm_silu(const void* x, const void* gamma, const void* beta, void* y, void* stats_ws,
+                       int N, int64_t P, int C, float eps, int silu, b2f_stream_t stream) {
+  return b2f::groupnorm_silu(x, gamma, beta, y, static_cast<double*>(stats_ws), N, P, C, eps, silu,
+                             static_cast<cudaStream_t>(stream));
+}
+int b2f_upsample2x(const void* in, void* out, int N, int H, int W, int C, b2f_stream_t stream) {
+  return b2f::upsample2x(in, out, N, H, W, C, static_cast<cudaStream_t>(stream));
+}
+int b2f_nchw_to_nhwc_pad(const void* in, int in_is_f32, void* out, int N, int C, int H, int W,
+                         int Cpad, b2f_stream_t stream) {
+  return b2f::nchw_to_nhwc_pad(in, in_is_f32, out, N, C, H, W, Cpad, static_cast<cudaStream_t>(stream));
+}
+int b2f_softmax_rows(void* s, int64_t ld, int rows, int L, float scale, b2f_stream_t stream) {
+  return b2f::softmax_rows(s, ld, rows, L, scale, static_cast<cudaStream_t>(stream));
+}
+int b2f_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int Cc,
+                       b2f_stream_t stream) {
+  return b2f::transpose_bf16(in, ld_in, out, ld_out, R, Cc, static_cast<cudaStream_t>(stream));
 }
 
 int b2f_silu(const void* x, void* y, int64_t n, b2f_stream_t stream) {

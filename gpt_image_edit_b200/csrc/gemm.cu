@@ -239,6 +239,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[2 * j + 1] = r2.y + bf16r(g2.y * bf16r(v[2 * j + 1]));
             }
           }
+          else if (p.epi == B2F_EPI_RESID) {
+            const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
+            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 r2 = unpack_bf16x2(rw[j]);
+              v[2 * j] = r2.x + bf16r(v[2 * j]);
+              v[2 * j + 1] = r2.y + bf16r(v[2 * j + 1]);
+            }
+          }
           uint4 o;
           o.x = pack_bf16x2(v[0], v[1]);
           o.y = pack_bf16x2(v[2], v[3]);
@@ -302,9 +312,12 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
        reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(gate)) & 15)
     return B2F_ERR_ALIGN;
-  if (epilogue < 0 || epilogue > B2F_EPI_GATE_RESID) return B2F_ERR_INVALID;
+  if (epilogue < 0 || epilogue > B2F_EPI_RESID) return B2F_ERR_INVALID;
   if (epilogue == B2F_EPI_GATE_RESID) {
     if (!resid || !gate || (ldr & 7) || (gate_ld & 7) || (resid_bs & 7)) return B2F_ERR_INVALID;
+  }
+  if (epilogue == B2F_EPI_RESID) {
+    if (!resid || (ldr & 7) || (resid_bs & 7)) return B2F_ERR_INVALID;
   }
   GemmParams p{};
   p.batch = batch;

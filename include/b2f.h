@@ -71,6 +71,7 @@ int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* fl
 #define B2F_EPI_GELU_TANH 1
 #define B2F_EPI_SILU 2
 #define B2F_EPI_GATE_RESID 3
+#define B2F_EPI_RESID 4 /* out = bf16(resid + bf16(acc + bias))  (VAE attention to_out + residual) */
 
 int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
                   const void* bias, void* out, int64_t ldc, int64_t out_batch_stride, int batch,
@@ -205,6 +206,63 @@ int b2f_flux_forward(b2f_flux* ctx, const void* hidden, const void* enc, const v
                      int64_t mod_ld, void* out, int B, int S_img, int S_txt, int n_out_rows,
                      void* ws, size_t ws_bytes, int first_block, int last_block,
                      b2f_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3x3 convolution, NHWC bf16, tcgen05 implicit GEMM (A tiles are shifted 4-D TMA boxes of the
+ * input; padding = TMA zero fill).  Replaces cuDNN conv as reached by diffusers AutoencoderKL
+ * (SURVEY.md A.4).  in [N,Hin,Win,Cin] (Cin % 64 == 0), w OHWI [Cout,3,3,Cin], bias [>=8] bf16 or
+ * NULL, out [N,Ho,Wo,Cout] (NHWC) or, with out_nchw, [N,Cout,Ho,Wo].  stride 1: padding 1.
+ * stride 2: diffusers Downsample2D (pad right/bottom by one, no other padding), Ho = Hin/2.
+ * resid (NHWC, same shape as out, may alias out): out = bf16(resid + bf16(conv + bias)).
+ */
+int b2f_conv3x3(const void* in, const void* w, const void* bias, void* out, const void* resid, int N,
+                int Hin, int Win, int Cin, int Cout, int stride, int out_nchw, b2f_stream_t stream);
+
+/* GroupNorm(32 groups, eps, affine) [+ SiLU] over x [N, P, C] (P = H*W, NHWC), HBM-bound two-pass.
+ * stats_ws: device scratch of 64*N doubles.  Replaces nn.GroupNorm + nn.SiLU in ResnetBlock2D /
+ * the mid-block Attention.group_norm / conv_norm_out. */
+int b2f_groupnorm_silu(const void* x, const void* gamma, const void* beta, void* y, void* stats_ws,
+                       int N, int64_t P, int C, float eps, int silu, b2f_stream_t stream);
+/* Nearest-neighbour 2x upsample, NHWC (Upsample2D's F.interpolate). */
+int b2f_upsample2x(const void* in, void* out, int N, int H, int W, int C, b2f_stream_t stream);
+/* NCHW (bf16, or fp32 when in_is_f32) -> NHWC bf16 with channels zero-padded to Cpad. */
+int b2f_nchw_to_nhwc_pad(const void* in, int in_is_f32, void* out, int N, int C, int H, int W,
+                         int Cpad, b2f_stream_t stream);
+/* In-place row softmax p = softmax(scale * s) over rows of length L (bf16, fp32 math). */
+int b2f_softmax_rows(void* s, int64_t ld, int rows, int L, float scale, b2f_stream_t stream);
+/* out[c, r] = in[r, c] for an [R, Cc] bf16 matrix. */
+int b2f_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int Cc,
+                       b2f_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FLUX VAE (diffusers AutoencoderKL) as one object.  Replaces `pipe.vae.encode(x)` /
+ * `pipe.vae.decode(z)` — reference univa/utils/flux_pipeline.py:609, :1129; train_denoiser.py:887.
+ * Weights are borrowed bf16 device pointers bound under their diffusers names with
+ * these layout conventions (the Python side converts at load and converts back in state_dict()):
+ *   3x3 conv weights   OHWI [Cout,3,3,Cin]; conv_in weights have Cin zero-padded to 64
+ *   1x1 conv_shortcut  [Cout,Cin]
+ *   biases             zero-padded to a multiple of 8 elements
+ *   mid attention      to_q/to_k/to_v bound fused as `<...>.attentions.0.qkv.{weight,bias}` [3C,C]
+ */
+typedef struct b2f_vae b2f_vae;
+typedef struct {
+  int block_out[4];     /* 128,256,512,512 */
+  int layers_per_block; /* 2 */
+  int latent_channels;  /* 16 */
+  int in_channels;      /* 3 */
+  int out_channels;     /* 3 */
+} b2f_vae_cfg;
+int b2f_vae_create(b2f_vae** out, const b2f_vae_cfg* cfg);
+void b2f_vae_destroy(b2f_vae* ctx);
+int b2f_vae_bind_weight(b2f_vae* ctx, const char* key, const void* dptr, int64_t numel);
+size_t b2f_vae_workspace_bytes(const b2f_vae* ctx, int N, int H, int W);
+/* image [N,3,H,W] (bf16, or fp32 when image_is_f32) -> moments [N, 2*latent, H/8, W/8] bf16
+ * (mean | logvar, un-clamped; `latent_dist.mode()` is the first half). */
+int b2f_vae_encode(b2f_vae* ctx, const void* image_nchw, int image_is_f32, int N, int H, int W,
+                   void* moments_nchw, void* ws, size_t ws_bytes, b2f_stream_t stream);
+/* z [N,latent,h,w] bf16 -> image [N,3,8h,8w] bf16. */
+int b2f_vae_decode(b2f_vae* ctx, const void* z_nchw, int N, int h_lat, int w_lat, void* image_nchw,
+                   void* ws, size_t ws_bytes, b2f_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -103,3 +103,16 @@ def test_size_rule_rescales_to_max_area():
     assert target_size(256, 256, 1024 ** 2) == (1024, 1024)     # reference quirk: 256 request -> 1 MP
     assert target_size(256, 256, 256 * 256) == (256, 256)
     assert target_size(720, 1280, 1024 ** 2) == (768, 1360)
+
+
+def test_anyres_dynamic_resize_matches_reference_semantics():
+    """Expected values produced by the reference's own univa/utils/anyres_util.py (pure Python, importable in
+    the build container; the two implementations were also compared on a 10x9x6 grid of sizes/bucket lists)."""
+    from univa.utils.anyres_util import compute_size, dynamic_resize, pick_ratio
+
+    assert dynamic_resize(1024, 1024) == (1024, 1024)
+    assert dynamic_resize(720, 1280) == (1504, 2784)
+    assert dynamic_resize(1280, 720) == (2784, 1504)
+    assert dynamic_resize(512, 768) == (832, 1248)
+    assert pick_ratio(600, 800, "any_11ratio") == (4, 3)
+    assert compute_size(4, 3, 32, anchor_pixels=448 * 448) == (384, 512)
