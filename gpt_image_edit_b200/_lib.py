@@ -58,6 +58,10 @@ _SIGNATURES = {
     "b2f_euler_step": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, C.c_float, _vp]),
     "b2f_silu": (_i32, [_vp, _vp, _i64, _vp]),
     "b2f_rope_tables": (_i32, [_vp, _i32, C.POINTER(_i32), C.c_double, _vp, _vp, _vp]),
+    "b2f_rmsnorm": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, C.c_float, _vp]),
+    "b2f_rope_half": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _i64, _i32, _vp]),
+    "b2f_swiglu": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "b2f_move_rows": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
     "b2f_conv3x3": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b2f_groupnorm_silu": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, C.c_float, _i32, _vp]),
     "b2f_upsample2x": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -1,0 +1,105 @@
+"""safetensors -> device loaders with diffusers / HF key names (SURVEY.md §8f-4, §5 "Checkpoint").
+
+Directory layouts read (those the reference's `from_pretrained` calls consume, cli.py:37-41, 64-68):
+  flux_path/transformer/*.safetensors        diffusers FluxTransformer2DModel keys
+  flux_path/vae/*.safetensors                diffusers AutoencoderKL keys
+  flux_path/scheduler/scheduler_config.json  FlowMatchEulerDiscreteScheduler config
+  model_path/*.safetensors                   Univa checkpoint: visual.*, model.*, denoise_tower.denoiser.*,
+                                             denoise_tower.denoise_projector.{0,2}.*  (train_denoiser.py:112-115)
+  model_path/task_head_final.pt              cli.py:49
+No real checkpoint exists offline; tests round-trip synthetic ones written with `save_state_dict`.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import torch
+from safetensors import safe_open
+from safetensors.torch import save_file
+
+from .scheduler import FlowMatchEulerDiscreteScheduler
+
+
+def iter_safetensors(directory, prefix: str = ""):
+    """Yields (key-without-prefix, tensor) over every *.safetensors shard in `directory`."""
+    d = Path(directory)
+    files = sorted(d.glob("*.safetensors"))
+    if not files:
+        raise FileNotFoundError(f"no *.safetensors under {d}")
+    for f in files:
+        with safe_open(str(f), framework="pt", device="cpu") as sf:
+            for k in sf.keys():
+                if k.startswith(prefix):
+                    yield k[len(prefix):], sf.get_tensor(k)
+
+
+def load_state_dict_from_dir(directory, prefix: str = "") -> dict:
+    return dict(iter_safetensors(directory, prefix))
+
+
+def save_state_dict(sd: dict, directory, filename: str = "diffusion_pytorch_model.safetensors", prefix: str = ""):
+    Path(directory).mkdir(parents=True, exist_ok=True)
+    save_file({prefix + k: v.detach().cpu().contiguous() for k, v in sd.items()}, str(Path(directory) / filename))
+
+
+def load_pipeline_components(flux_path, device="cuda"):
+    """-> (vae, scheduler) for FluxKontextPipeline.from_pretrained."""
+    from .vae import B200AutoencoderKL, VaeConfig
+
+    root = Path(flux_path)
+    cfg = {}
+    if (root / "vae" / "config.json").exists():
+        raw = json.loads((root / "vae" / "config.json").read_text())
+        cfg = {k: raw[k] for k in ("block_out_channels", "layers_per_block", "latent_channels", "scaling_factor",
+                                   "shift_factor", "in_channels", "out_channels") if k in raw}
+        if "block_out_channels" in cfg:
+            cfg["block_out_channels"] = tuple(cfg["block_out_channels"])
+    vae = B200AutoencoderKL(VaeConfig(**cfg), device=device)
+    vae.load_state_dict(load_state_dict_from_dir(root / "vae"))
+    scfg = {}
+    if (root / "scheduler" / "scheduler_config.json").exists():
+        raw = json.loads((root / "scheduler" / "scheduler_config.json").read_text())
+        scfg = {k: raw[k] for k in ("num_train_timesteps", "shift", "use_dynamic_shifting", "base_shift", "max_shift",
+                                    "base_image_seq_len", "max_image_seq_len") if k in raw}
+    return vae, FlowMatchEulerDiscreteScheduler(**scfg)
+
+
+def load_flux_transformer(directory, device="cuda", prefix: str = ""):
+    from .flux_transformer import B200FluxTransformer2DModel, FluxTransformerConfig
+
+    d = Path(directory)
+    cfg = {}
+    if (d / "config.json").exists():
+        raw = json.loads((d / "config.json").read_text())
+        cfg = {k: raw[k] for k in ("in_channels", "num_layers", "num_single_layers", "attention_head_dim",
+                                   "num_attention_heads", "joint_attention_dim", "pooled_projection_dim",
+                                   "guidance_embeds", "axes_dims_rope") if k in raw}
+    m = B200FluxTransformer2DModel(FluxTransformerConfig(**cfg), device=device)
+    m.load_state_dict(load_state_dict_from_dir(d, prefix))
+    return m
+
+
+def load_univa_checkpoint(model_path, device="cuda"):
+    """-> (UnivaQwen2p5VLForConditionalGeneration, task_head, None) from a Univa checkpoint directory."""
+    from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig, UnivaQwen2p5VLForConditionalGeneration
+    from univa.serve.cli import TaskHead
+
+    root = Path(model_path)
+    raw = json.loads((root / "config.json").read_text()) if (root / "config.json").exists() else {}
+    cfg = UnivaQwen2p5VLConfig(denoise_tower=raw.get("denoise_tower"), text_config=raw.get("text_config"),
+                               vision_config=raw.get("vision_config"))
+    model = UnivaQwen2p5VLForConditionalGeneration(cfg, device=device)
+    sd = load_state_dict_from_dir(root)
+    model.lvlm.load_state_dict({k: v for k, v in sd.items() if k.startswith(("visual.", "model."))})
+    model.denoise_tower.denoiser.load_state_dict({k[len("denoise_tower.denoiser."):]: v for k, v in sd.items()
+                                                  if k.startswith("denoise_tower.denoiser.")})
+    model.denoise_tower.denoise_projector.load_state_dict({k[len("denoise_tower.denoise_projector."):]: v for k, v in sd.items()
+                                                           if k.startswith("denoise_tower.denoise_projector.")})
+    head = TaskHead(cfg.hidden_size, device=device)
+    th = root / "task_head_final.pt"
+    if th.exists():
+        t = torch.load(th, map_location="cpu")
+        head.w0.copy_(t["0.weight"]); head.b0.copy_(t["0.bias"])
+        head.w3[:2].copy_(t["3.weight"]); head.b3[:2].copy_(t["3.bias"])
+    return model, head, None

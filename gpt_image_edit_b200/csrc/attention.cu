@@ -17,6 +17,11 @@
 // through transformers' attn_implementation="flash_attention_2" (univa/serve/cli.py:40).
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
+
+#ifndef B2F_ATTN_DEFAULT_VARIANT
+#define B2F_ATTN_DEFAULT_VARIANT 0
+#endif
 
 #include "host_common.h"
 #include "ptx.cuh"
@@ -49,6 +54,23 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3
+// minimax polynomial for 2^f (max rel. error 1.0e-4, far below the bf16 rounding of P), exponent
+// add through the integer pipe.  Used for a fraction of the exponentials so the SFU (16 ex2/clk/SM)
+// stops being co-critical with the tensor pipe.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;            // 1.5 * 2^23: low mantissa bits of t hold n
+  const float f = x - (t - 12582912.0f);
+  float r = fmaf(0.05592203512787819f, f, 0.24264007806777954f);
+  r = fmaf(r, f, 0.6931210160255432f);
+  r = fmaf(r, f, 0.9999244809150696f);
+  return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
+}
+
+// POLY: every POLY-th exponential goes to the polynomial (0 = never).
+// TURNS: the two softmax warpgroups take turns on the exp section (forces anti-phase).
+template <int POLY, bool TURNS>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -223,6 +245,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t s_tmem = tmem_base + lane_addr + uint32_t(t * 128);
     const uint32_t o_tmem = tmem_base + lane_addr + 256 + uint32_t(t * 128);
     float m = -INFINITY, l = 0.f;
+    if (TURNS) {
+    // named barriers 1/2 = "tile 0 / tile 1 may run its exp section"; tile 0 goes first
+    if (t == 1) named_bar_arrive(1, 256);
+    }
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -240,30 +266,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int c = 0; c < 128; ++c)
           if (kv0 + c >= limit) sr[c] = 0xff800000u;  // -inf
       }
-      float mx = -INFINITY;
+      // 8 independent max chains (a single dependent chain of 128 FMNMX costs ~4 clk per link and
+      // nothing else in this warp can hide it: only two softmax warps share an SM sub-partition)
+      float mx8[8];
 #pragma unroll
-      for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
+#pragma unroll
+      for (int c = 8; c < 128; c += 8)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       const float m_new = fmaxf(m, mx * p.scale_log2);
       // lazy rescale: keep the stale max unless it grew by more than 2^8 (P stays < 256)
       const bool grow = (m_new - m) > 8.0f;
       const float m_use = grow ? m_new : m;
       const float alpha = grow ? ex2(m - m_use) : 1.0f;
       const float neg_m = (m_use == -INFINITY) ? 0.f : -m_use;  // fully masked row (causal tail)
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (TURNS) named_bar_sync(1 + t, 256);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float p0 = ex2(fmaf(__uint_as_float(sr[half * 64 + 2 * c]), p.scale_log2, neg_m));
-          const float p1 =
-              ex2(fmaf(__uint_as_float(sr[half * 64 + 2 * c + 1]), p.scale_log2, neg_m));
-          sum += p0 + p1;
+          const float x0 = fmaf(__uint_as_float(sr[half * 64 + 2 * c]), p.scale_log2, neg_m);
+          const float x1 = fmaf(__uint_as_float(sr[half * 64 + 2 * c + 1]), p.scale_log2, neg_m);
+          const float p0 = ex2(x0);
+          constexpr int PH = POLY / 2 ? POLY / 2 : 1;
+          const float p1 = (POLY && (c % PH) == PH - 1) ? ex2_poly(x1) : ex2(x1);
+          sum4[c & 3] += p0 + p1;
           pk[c] = pack_bf16x2(p0, p1);
         }
         B2F_TMEM_ST_X32(s_tmem + half * 32, pk);
       }
-      l = l * alpha + sum;
+      if (TURNS) named_bar_arrive(1 + (t ^ 1), 256);
+      l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       m = m_use;
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
         // S_t(j) being ready proves P_t·V_{j-1} completed, so O_t is stable here
@@ -331,12 +369,22 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15)
     return B2F_ERR_ALIGN;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+  // kernel variant: compile-time (POLY, TURNS); B2F_ATTN_VARIANT selects at run time for tuning
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
+  static KernelFn kernel = nullptr;
+  if (!kernel) {
+    const char* v = getenv("B2F_ATTN_VARIANT");
+    const int variant = v ? atoi(v) : B2F_ATTN_DEFAULT_VARIANT;
+    switch (variant) {
+      case 1: kernel = attn_fwd_kernel<4, false>; break;
+      case 2: kernel = attn_fwd_kernel<2, false>; break;
+      case 3: kernel = attn_fwd_kernel<0, true>; break;
+      case 4: kernel = attn_fwd_kernel<4, true>; break;
+      case 5: kernel = attn_fwd_kernel<2, true>; break;
+      default: kernel = attn_fwd_kernel<0, false>; break;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
     if (e != cudaSuccess) return cuda_err(e, "attention smem attribute");
-    attr_set = true;
   }
   CUtensorMap tmQ, tmK, tmV;
   int rc = make_tmap_3d_rows(&tmQ, q, (uint64_t)H * DH, Sq, B, ldq, (uint64_t)Sq * ldq);
@@ -357,7 +405,7 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   p.ldo = ldo;
   dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
   prof_begin(KC_ATTN, stream);
-  attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(tmQ, tmK, tmV, p);
   prof_end(KC_ATTN, stream, (causal ? 2.0 : 4.0) * B * H * (double)Sq * Skv * DH,
            2.0 * DH * B * (2.0 * H * Sq + 2.0 * Hkv * Skv));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

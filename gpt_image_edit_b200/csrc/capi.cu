@@ -20,6 +20,14 @@ int euler_step(void* x, int64_t ldx, const void* v, int64_t ldv, int64_t rows, i
                cudaStream_t stream);
 int silu(const void* x, void* y, int64_t n, cudaStream_t stream);
 void prof_set(bool on);
+int rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int64_t rows, int D,
+            float eps, cudaStream_t stream);
+int rope_half(void* x, int64_t ld, int heads, int head_pitch, const float* cos, const float* sin,
+              int rot, int64_t tokens, int fp32_math, cudaStream_t stream);
+int swiglu(const void* gu, int64_t ld, void* out, int64_t ldo, int64_t rows, int I,
+           cudaStream_t stream);
+int move_rows(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, const int64_t* idx, int64_t n,
+              int D, int scatter, cudaStream_t stream);
 int conv3x3(const void* in, const void* w, const void* bias, void* out, const void* resid, int N,
             int Hin, int Win, int Cin, int Cout, int stride, int out_nchw, cudaStream_t stream);
 int groupnorm_silu(const void* x, const void* gamma, const void* beta, void* y, double* stats_ws,
@@ -139,6 +147,24 @@ int b2f_softmax_rows(void* s, int64_t ld, int rows, int L, float scale, b2f_stre
 int b2f_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int Cc,
                        b2f_stream_t stream) {
   return b2f::transpose_bf16(in, ld_in, out, ld_out, R, Cc, static_cast<cudaStream_t>(stream));
+}
+
+int b2f_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int64_t rows, int D,
+                float eps, b2f_stream_t stream) {
+  return b2f::rmsnorm(x, ldx, w, y, ldy, rows, D, eps, static_cast<cudaStream_t>(stream));
+}
+int b2f_rope_half(void* x, int64_t ld, int heads, int head_pitch, const float* cos, const float* sin,
+                  int rot, int64_t tokens, int fp32_math, b2f_stream_t stream) {
+  return b2f::rope_half(x, ld, heads, head_pitch, cos, sin, rot, tokens, fp32_math,
+                        static_cast<cudaStream_t>(stream));
+}
+int b2f_swiglu(const void* gu, int64_t ld, void* out, int64_t ldo, int64_t rows, int I,
+               b2f_stream_t stream) {
+  return b2f::swiglu(gu, ld, out, ldo, rows, I, static_cast<cudaStream_t>(stream));
+}
+int b2f_move_rows(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, const int64_t* idx,
+                  int64_t n, int D, int scatter, b2f_stream_t stream) {
+  return b2f::move_rows(src, ld_src, dst, ld_dst, idx, n, D, scatter, static_cast<cudaStream_t>(stream));
 }
 
 int b2f_silu(const void* x, void* y, int64_t n, b2f_stream_t stream) {

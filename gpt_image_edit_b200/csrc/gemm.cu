@@ -11,6 +11,11 @@
 // Replaces: torch.nn.functional.linear → cuBLASLt (diffusers FluxTransformer2DModel linears,
 // reference call site univa/utils/flux_pipeline.py:1067).
 #include <atomic>
+#include <cstdlib>
+
+#ifndef B2F_GEMM_2CTA_DEFAULT
+#define B2F_GEMM_2CTA_DEFAULT 0
+#endif
 
 #include "host_common.h"
 #include "ptx.cuh"
@@ -68,6 +73,72 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return 0.5f * x * (1.0f + tanhf(inner));
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// Epilogue for 32 accumulator columns of one output row: bias / activation / gate / residual with the
+// bf16 rounding points of the torch-eager chain, then 16-byte stores.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int n0,
+                                               __nv_bfloat16* out_row, const __nv_bfloat16* res_row,
+                                               const __nv_bfloat16* gate_row) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = n0 + g * 8;
+    if (n >= p.N) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+    if (p.bias) {
+      const uint4 bq = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+      const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 b2 = unpack_bf16x2(bw[j]);
+        v[2 * j] += b2.x;
+        v[2 * j + 1] += b2.y;
+      }
+    }
+    if (p.epi == B2F_EPI_GELU_TANH) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(bf16r(v[j]));
+    } else if (p.epi == B2F_EPI_GELU_ERF) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = bf16r(v[j]);
+        v[j] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+      }
+    } else if (p.epi == B2F_EPI_SILU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_f(bf16r(v[j]));
+    } else if (p.epi == B2F_EPI_GATE_RESID) {
+      const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
+      const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
+      const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+      const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 g2 = unpack_bf16x2(gw[j]);
+        const float2 r2 = unpack_bf16x2(rw[j]);
+        v[2 * j] = r2.x + bf16r(g2.x * bf16r(v[2 * j]));
+        v[2 * j + 1] = r2.y + bf16r(g2.y * bf16r(v[2 * j + 1]));
+      }
+    }
+    else if (p.epi == B2F_EPI_RESID) {
+      const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
+      const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 r2 = unpack_bf16x2(rw[j]);
+        v[2 * j] = r2.x + bf16r(v[2 * j]);
+        v[2 * j + 1] = r2.y + bf16r(v[2 * j + 1]);
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out_row + n) = o;
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -203,59 +274,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int n0 = n_blk * BN + c0;
         if (!row_ok || n0 >= p.N) continue;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + g * 8;
-          if (n >= p.N) break;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-          if (p.bias) {
-            const uint4 bq = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
-            const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 b2 = unpack_bf16x2(bw[j]);
-              v[2 * j] += b2.x;
-              v[2 * j + 1] += b2.y;
-            }
-          }
-          if (p.epi == B2F_EPI_GELU_TANH) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(bf16r(v[j]));
-          } else if (p.epi == B2F_EPI_SILU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = silu_f(bf16r(v[j]));
-          } else if (p.epi == B2F_EPI_GATE_RESID) {
-            const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
-            const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
-            const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
-            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 g2 = unpack_bf16x2(gw[j]);
-              const float2 r2 = unpack_bf16x2(rw[j]);
-              v[2 * j] = r2.x + bf16r(g2.x * bf16r(v[2 * j]));
-              v[2 * j + 1] = r2.y + bf16r(g2.y * bf16r(v[2 * j + 1]));
-            }
-          }
-          else if (p.epi == B2F_EPI_RESID) {
-            const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
-            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 r2 = unpack_bf16x2(rw[j]);
-              v[2 * j] = r2.x + bf16r(v[2 * j]);
-              v[2 * j + 1] = r2.y + bf16r(v[2 * j + 1]);
-            }
-          }
-          uint4 o;
-          o.x = pack_bf16x2(v[0], v[1]);
-          o.y = pack_bf16x2(v[2], v[3]);
-          o.z = pack_bf16x2(v[4], v[5]);
-          o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(out_row + n) = o;
-        }
+        epilogue_chunk(p, acc, n0, out_row, res_row, gate_row);
       }
       if (++as == 2) {
         as = 0;
@@ -298,6 +317,209 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cu
   return B2F_OK;
 }
 
+
+// ================================================================================================
+// CTA-pair variant (cta_group::2): one 256 x 256 output tile per pair of SMs.
+//   CTA r of the pair loads A rows [m0 + 128 r, +128) and W rows [n0 + 128 r, +128) into ITS smem;
+//   CTA 0's MMA lane issues tcgen05.mma.cta_group::2 (M = 256, N = 256): each SM's tensor core
+//   multiplies its own 128 A rows with BOTH halves of W (its own + the peer's smem) into its own
+//   TMEM (128 lanes x 256 columns).  Per SM and k-step that is 32 KB of TMA traffic instead of the
+//   48 KB of the 1-CTA 128x256 tile — a third less L2->SM bandwidth and energy per FLOP.
+//   Barriers: TMA bytes of both CTAs are counted on CTA 0's `full` barrier; tcgen05.commit
+//   multicasts "stage free" / "accumulator ready" to both CTAs; both CTAs' epilogue warps arrive on
+//   CTA 0's `tmem_empty`.
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;       // 128 rows of A per CTA
+  static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;      // 128 rows of W per CTA
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 32 KB
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);   // one arrive per CTA's producer (+ both CTAs' TMA bytes)
+      mbar_init(&empty_bar[i], 1);  // one multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // p.m_blocks_per_batch / num_m_blocks are in units of 256-row pair tiles here
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        int m_blk, n_blk;
+        tile_coords(p, t, m_blk, n_blk);
+        const int bb = m_blk / p.m_blocks_per_batch;
+        const int mb = m_blk - bb * p.m_blocks_per_batch;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (leader)
+            mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          else
+            mbar_arrive_cta0(&full_bar[stage]);
+          tma_load_3d_2cta(sa, &tmA, &full_bar[stage], kb * BLOCK_K, mb * 256 + int(rank) * BLOCK_M, bb);
+          tma_load_2d_2cta(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN + int(rank) * (BN / 2));
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_sdesc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+            const uint64_t db = make_sdesc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+            umma_ss_2cta(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[as]);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row_in_tile = int(rank) * BLOCK_M + q * 32 + lane;  // row inside the 256-row pair tile
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      int m_blk, n_blk;
+      tile_coords(p, t, m_blk, n_blk);
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int bidx = m_blk / p.m_blocks_per_batch;
+      const long long row = (long long)(m_blk - bidx * p.m_blocks_per_batch) * 256 + row_in_tile;
+      const bool row_ok = row < p.M;
+      const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
+      __nv_bfloat16* out_row = p.out + bidx * p.out_bs + row * p.ldc;
+      const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[32];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
+        __syncwarp();
+        B2F_TMEM_LD_X32(taddr, acc);
+        tmem_wait_ld();
+        if (c0 + 32 == BN) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta0(&tmem_empty[as]);
+        }
+        const int n0 = n_blk * BN + c0;
+        if (!row_ok || n0 >= p.N) continue;
+        epilogue_chunk(p, acc, n0, out_row, res_row, gate_row);
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs are done with each other's smem / barriers / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_err(e, "gemm 2cta smem attribute");
+    attr_set = true;
+  }
+  p.m_blocks_per_batch = (p.M + 255) / 256;
+  p.num_m_blocks = p.batch * p.m_blocks_per_batch;
+  p.num_n_blocks = (p.N + Cfg::BN - 1) / Cfg::BN;
+  p.panel_n = 16;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int max_pairs = device_info().num_sms / 2;
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  prof_begin(KC_GEMM, stream);
+  gemm_bf16_2cta_kernel<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * p.K,
+           2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("gemm_bf16_2cta_kernel");
+  return B2F_OK;
+}
+
 }  // namespace
 
 int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
@@ -312,7 +534,7 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
        reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(gate)) & 15)
     return B2F_ERR_ALIGN;
-  if (epilogue < 0 || epilogue > B2F_EPI_RESID) return B2F_ERR_INVALID;
+  if (epilogue < 0 || epilogue > B2F_EPI_GELU_ERF) return B2F_ERR_INVALID;
   if (epilogue == B2F_EPI_GATE_RESID) {
     if (!resid || !gate || (ldr & 7) || (gate_ld & 7) || (resid_bs & 7)) return B2F_ERR_INVALID;
   }
@@ -338,6 +560,17 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
   const long long num_m = (long long)batch * ((M + BLOCK_M - 1) / BLOCK_M);
   const bool use256 = num_m * ((N + 255) / 256) >= device_info().num_sms && N >= 256;
   CUtensorMap tmA, tmB;
+  // CTA-pair kernel for the large projections (>= one full wave of 256x256 pair tiles)
+  static const int mode_2cta = [] { const char* v = getenv("B2F_GEMM_2CTA"); return v ? atoi(v) : B2F_GEMM_2CTA_DEFAULT; }();
+  const long long pair_tiles = (long long)batch * ((M + 255) / 256) * ((N + 255) / 256);
+  if (mode_2cta && N >= 256 && pair_tiles >= device_info().num_sms / 2) {
+    int rc2 = make_tmap_3d_rows(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)lda,
+                                batch > 1 ? (uint64_t)a_bs : (uint64_t)M * lda);
+    if (rc2 != B2F_OK) return rc2;
+    rc2 = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, BLOCK_K);
+    if (rc2 != B2F_OK) return rc2;
+    return launch_gemm_2cta(tmA, tmB, p, stream);
+  }
   int rc = make_tmap_3d_rows(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)lda,
                              batch > 1 ? (uint64_t)a_bs : (uint64_t)M * lda);
   if (rc != B2F_OK) return rc;

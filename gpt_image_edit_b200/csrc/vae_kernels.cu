@@ -98,14 +98,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* x, c
   unpack8v(*reinterpret_cast<const uint4*>(x + off), f);
   unpack8v(__ldg(reinterpret_cast<const uint4*>(gamma + oct * 8)), ga);
   unpack8v(__ldg(reinterpret_cast<const uint4*>(beta + oct * 8)), be);
+  // an octet of channels touches at most 8/cpg groups (one for the real widths, cpg >= 8, two for
+  // cpg = 4): derive mean / rstd once per distinct group, in double, then stay in fp32
+  int g_prev = -1;
+  float mean = 0.f, rstd = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int g = (oct * 8 + j) / cpg;
-    const double sm = stats[((long long)n * 32 + g) * 2], sq = stats[((long long)n * 32 + g) * 2 + 1];
-    const double mean = sm / cnt;
-    const double var = fmax(sq / cnt - mean * mean, 0.0);
-    const float rstd = rsqrtf((float)var + eps);
-    float v = bf16r((f[j] - (float)mean) * rstd * ga[j] + be[j]);
+    if (g != g_prev) {
+      const double sm = stats[((long long)n * 32 + g) * 2], sq = stats[((long long)n * 32 + g) * 2 + 1];
+      const double md = sm / cnt;
+      mean = (float)md;
+      rstd = rsqrtf((float)fmax(sq / cnt - md * md, 0.0) + eps);
+      g_prev = g;
+    }
+    float v = bf16r((f[j] - mean) * rstd * ga[j] + be[j]);
     if (silu) v = v / (1.0f + __expf(-v));
     o[j] = v;
   }

@@ -134,7 +134,7 @@ class B200FluxTransformer2DModel(torch.nn.Module):
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None and getattr(_lib, "lib", None) is not None:  # not during interpreter teardown
             _lib.lib.b2f_flux_destroy(h)
             self._h = None
 

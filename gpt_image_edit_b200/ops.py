@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
-EPI_BIAS, EPI_GELU_TANH, EPI_SILU, EPI_GATE_RESID = 0, 1, 2, 3
+EPI_BIAS, EPI_GELU_TANH, EPI_SILU, EPI_GATE_RESID, EPI_RESID, EPI_GELU_ERF = 0, 1, 2, 3, 4, 5
 
 
 def _req(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> None:
@@ -44,12 +44,13 @@ def linear(x, weight, bias=None, *, epilogue: int = EPI_BIAS, out=None, resid=No
     _req(out, "out")
     o3 = _as3(out)
     ldr = rbs = gld = 0
-    if epilogue == EPI_GATE_RESID:
+    if epilogue in (EPI_GATE_RESID, EPI_RESID):
         _req(resid, "resid")
-        _req(gate, "gate")
         r3 = _as3(resid)
         ldr, rbs = r3.stride(1), r3.stride(0)
-        gld = gate.stride(0) if gate.dim() == 2 else 0
+        if epilogue == EPI_GATE_RESID:
+            _req(gate, "gate")
+            gld = gate.stride(0) if gate.dim() == 2 else 0
     check(
         _lib.lib.b2f_gemm_bf16(
             ptr(x3), x3.stride(1), x3.stride(0), ptr(weight), weight.stride(0), ptr(bias),
@@ -149,3 +150,55 @@ def rope_tables(ids: torch.Tensor, axes_dim=(16, 56, 56), theta: float = 10000.0
     axes = (C.c_int * 3)(*axes_dim)
     check(_lib.lib.b2f_rope_tables(ptr(ids), S, axes, float(theta), ptr(cos), ptr(sin), stream_ptr()), "b2f_rope_tables")
     return cos, sin
+
+
+def rmsnorm(x, weight, *, out=None, eps: float = 1e-6) -> torch.Tensor:
+    """Qwen2RMSNorm over the last dim of x [..., D] (rows must be uniformly pitched)."""
+    _req(x, "x")
+    _req(weight, "weight")
+    x2 = x.reshape(-1, x.shape[-1])
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    o2 = out.reshape(-1, out.shape[-1])
+    check(_lib.lib.b2f_rmsnorm(ptr(x2), x2.stride(0), ptr(weight), ptr(o2), o2.stride(0), x2.shape[0], x2.shape[1], eps,
+                               stream_ptr()), "b2f_rmsnorm")
+    return out
+
+
+def rope_half_(x, heads: int, head_pitch: int, cos, sin, *, fp32_math: bool):
+    """In-place rotate-half RoPE on x [tokens, >= heads*head_pitch] (row view)."""
+    _req(x, "x")
+    _req(cos, "cos", torch.float32)
+    _req(sin, "sin", torch.float32)
+    check(_lib.lib.b2f_rope_half(ptr(x), x.stride(0), heads, head_pitch, ptr(cos), ptr(sin), cos.shape[-1], x.shape[0],
+                                 int(fp32_math), stream_ptr()), "b2f_rope_half")
+    return x
+
+
+def swiglu(gu, inter: int, *, out=None) -> torch.Tensor:
+    _req(gu, "gu")
+    rows = gu.shape[0]
+    if out is None:
+        out = torch.empty((rows, inter), device=gu.device, dtype=torch.bfloat16)
+    check(_lib.lib.b2f_swiglu(ptr(gu), gu.stride(0), ptr(out), out.stride(0), rows, inter, stream_ptr()), "b2f_swiglu")
+    return out
+
+
+def gather_rows(table, idx, *, out=None) -> torch.Tensor:
+    _req(table, "table")
+    _req(idx, "idx", torch.int64)
+    n, D = idx.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((n, D), device=table.device, dtype=torch.bfloat16)
+    check(_lib.lib.b2f_move_rows(ptr(table), table.stride(0), ptr(out), out.stride(0), ptr(idx), n, D, 0, stream_ptr()),
+          "b2f_move_rows(gather)")
+    return out
+
+
+def scatter_rows_(dst, idx, src):
+    _req(dst, "dst")
+    _req(src, "src")
+    _req(idx, "idx", torch.int64)
+    check(_lib.lib.b2f_move_rows(ptr(src), src.stride(0), ptr(dst), dst.stride(0), ptr(idx), idx.numel(), dst.shape[1], 1,
+                                 stream_ptr()), "b2f_move_rows(scatter)")
+    return dst

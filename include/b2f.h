@@ -72,6 +72,7 @@ int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* fl
 #define B2F_EPI_SILU 2
 #define B2F_EPI_GATE_RESID 3
 #define B2F_EPI_RESID 4 /* out = bf16(resid + bf16(acc + bias))  (VAE attention to_out + residual) */
+#define B2F_EPI_GELU_ERF 5 /* out = bf16(gelu_erf(bf16(acc + bias)))  (Qwen2.5-VL patch merger, nn.GELU()) */
 
 int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
                   const void* bias, void* out, int64_t ldc, int64_t out_batch_stride, int batch,
@@ -206,6 +207,26 @@ int b2f_flux_forward(b2f_flux* ctx, const void* hidden, const void* enc, const v
                      int64_t mod_ld, void* out, int B, int S_img, int S_txt, int n_out_rows,
                      void* ws, size_t ws_bytes, int first_block, int last_block,
                      b2f_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernels of the Qwen2.5-VL conditioning prefill (transformers Qwen2_5_VL*, SURVEY.md Appendix B;
+ * reference univa/models/qwen2p5vl/modeling_univa_qwen2p5vl.py:373-399, 481-492, 521-523).
+ */
+/* Qwen2RMSNorm: y = w * bf16(float(x) * rsqrt(mean(x^2) + eps)); D % 256 == 0, D <= 5120. */
+int b2f_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int64_t rows, int D,
+                float eps, b2f_stream_t stream);
+/* rotate-half RoPE in place on `heads` head vectors per token (slot pitch head_pitch, first `rot`
+ * elements rotated; cos/sin fp32 [tokens, rot]).  fp32_math=1: vision tower (one rounding);
+ * fp32_math=0: text M-RoPE evaluated in bf16 as transformers' eager code does. */
+int b2f_rope_half(void* x, int64_t ld, int heads, int head_pitch, const float* cos, const float* sin,
+                  int rot, int64_t tokens, int fp32_math, b2f_stream_t stream);
+/* SwiGLU combine: out = bf16(bf16(silu(gu[:, :I])) * gu[:, I:2I]). */
+int b2f_swiglu(const void* gu, int64_t ld, void* out, int64_t ldo, int64_t rows, int I,
+               b2f_stream_t stream);
+/* Row gather (scatter=0: dst[i] = src[idx[i]], embed_tokens) / scatter (scatter=1: dst[idx[i]] =
+ * src[i], masked_scatter of the image embeddings); idx: int64 device array, D % 8 == 0. */
+int b2f_move_rows(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, const int64_t* idx,
+                  int64_t n, int D, int scatter, b2f_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 3x3 convolution, NHWC bf16, tcgen05 implicit GEMM (A tiles are shifted 4-D TMA boxes of the

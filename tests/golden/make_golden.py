@@ -177,6 +177,7 @@ def vae_golden():
 
 def main():
     vae_golden()
+    rope_index_golden()
     cfg = fo.FluxConfig(**TOY, guidance_embeds=False)
     sd = fo.make_synthetic_state_dict(cfg, seed=11, dtype=torch.float64)
     inp = toy_inputs(cfg)
@@ -197,6 +198,39 @@ def main():
                                inp2["timestep"], inp2["img_ids"], inp2["txt_ids"], guidance=inp2["guidance"].float())
     torch.save(dict(cfg=TOY, seed=12, inputs=inp2, output=out2), HERE / "flux_toy_oracle.pt")
     print("oracle output", out2.shape, out2.abs().mean().item())
+
+
+
+def rope_index_golden():
+    """Runs the REFERENCE's own get_rope_index (source text of
+    univa/models/qwen2p5vl/modeling_univa_qwen2p5vl.py:139-318, extracted with ast because the module
+    itself needs diffusers/transformers-4.50 to import) on a few token layouts -> rope_index_ref.pt."""
+    import ast
+    import textwrap
+    from types import SimpleNamespace
+    from typing import Optional, Tuple  # noqa: F401  (names used by the extracted source)
+
+    src = Path("/root/reference/univa/models/qwen2p5vl/modeling_univa_qwen2p5vl.py").read_text()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "get_rope_index")
+    code = textwrap.dedent(ast.get_source_segment(src, fn))
+    ns = {"torch": torch, "Optional": Optional, "Tuple": Tuple}
+    exec(code, ns)
+    fake = SimpleNamespace(config=SimpleNamespace(vision_config=SimpleNamespace(spatial_merge_size=2, tokens_per_second=2),
+                                                   image_token_id=900, video_token_id=901, vision_start_token_id=902))
+    img32, img4, img256 = [900] * 32, [900] * 4, [900] * 256
+    cases = [
+        (torch.tensor([[1, 2, 3, 902] + img32 + [903, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14],
+                       [1, 902] + img4 + [903, 4, 902] + img32 + [903, 5, 6, 7, 8, 9]]),
+         torch.tensor([[1, 16, 8], [1, 4, 4], [1, 16, 8]])),
+        (torch.tensor([[1, 2, 3, 902] + img256 + [903] + list(range(10, 37))]), torch.tensor([[1, 32, 32]])),
+        (torch.tensor([[7, 8, 902] + img4 + [903, 9, 902]]), torch.tensor([[1, 4, 4]])),   # trailing vision_start
+    ]
+    out = []
+    for ids, grid in cases:
+        pos, delta = ns["get_rope_index"](fake, ids, grid)
+        out.append(dict(input_ids=ids, image_grid_thw=grid, position_ids=pos, deltas=delta))
+    torch.save(out, HERE / "rope_index_ref.pt")
+    print("rope_index golden:", [tuple(o["position_ids"].shape) for o in out])
 
 
 if __name__ == "__main__":

@@ -1,0 +1,54 @@
+"""GPU smoke of the reference-facing entry point: one non-interactive `univa.serve.cli` turn with
+synthetic weights (few layers at the real widths), 256x256 / 2 steps — BASELINE.json configs[0]'s
+plumbing case, run on the GPU because this engine has no CPU path — plus the checkpoint round trip."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cli_single_turn_writes_png(tmp_path):
+    from PIL import Image
+
+    from univa.serve import cli
+
+    rng = np.random.default_rng(0)
+    src = tmp_path / "src.png"
+    Image.fromarray(rng.integers(0, 256, size=(300, 420, 3), dtype=np.uint8)).save(src)
+    out = tmp_path / "out.png"
+    args = cli.build_parser().parse_args([
+        "--synthetic", "--small", "--prompt", "make the sky purple", "--image", str(src), "--output", str(out),
+        "--height", "256", "--width", "256", "--num_inference_steps", "2", "--max_area", str(256 * 256)])
+    cli.main(args)
+    img = Image.open(out)
+    # update_size(any_11ratio, anchor 256*256) of a 420x300 image, then the pipeline's /16 floor
+    assert img.size[0] % 16 == 0 and img.size[1] % 16 == 0 and img.size[0] > img.size[1]
+    assert np.asarray(img).std() > 0
+
+
+def test_checkpoint_roundtrip_through_safetensors(tmp_path):
+    from gpt_image_edit_b200 import checkpoint as ck
+    from gpt_image_edit_b200.flux_transformer import B200FluxTransformer2DModel, FluxTransformerConfig
+    from gpt_image_edit_b200.vae import B200AutoencoderKL, VaeConfig
+
+    cfg = dict(num_layers=1, num_single_layers=1, attention_head_dim=128, num_attention_heads=2, joint_attention_dim=256,
+               pooled_projection_dim=64)
+    m = B200FluxTransformer2DModel(FluxTransformerConfig(**cfg)).randomize_(3)
+    ck.save_state_dict(m.state_dict(), tmp_path / "transformer")
+    (tmp_path / "transformer" / "config.json").write_text(__import__("json").dumps(cfg))
+    m2 = ck.load_flux_transformer(tmp_path / "transformer")
+    a, b = m.state_dict(), m2.state_dict()
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    assert "transformer_blocks.0.attn.to_q.weight" in a and "single_transformer_blocks.0.proj_mlp.bias" in a
+
+    v = B200AutoencoderKL(VaeConfig(block_out_channels=(64, 128, 256, 256))).randomize_(4)
+    ck.save_state_dict({k: t.contiguous() for k, t in v.state_dict().items()}, tmp_path / "vae")
+    (tmp_path / "vae" / "config.json").write_text('{"block_out_channels": [64, 128, 256, 256]}')
+    (tmp_path / "scheduler").mkdir()
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text('{"base_shift": 0.5, "max_shift": 1.15}')
+    v2, sched = ck.load_pipeline_components(tmp_path)
+    sa, sb = v.state_dict(), v2.state_dict()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert sa["encoder.conv_in.weight"].shape == (64, 3, 3, 3)          # diffusers OIHW layout at the boundary
+    assert sched.config.max_shift == 1.15

@@ -1,0 +1,113 @@
+"""`UnivaQwen2p5VLForConditionalGeneration` — the conditioning model surface of the reference
+(univa/models/qwen2p5vl/modeling_univa_qwen2p5vl.py:32-47, 325-536, 604-621) over libb2f:
+
+    model(input_ids, pixel_values=, attention_mask=, image_grid_thw=, output_type="denoise_embeds")
+        -> [B, L, 4096]     Qwen2.5-VL prefill (ViT + decoder + final norm) -> denoise_projector (MLP2)
+    model.denoise_tower.denoiser            the FLUX module handed to the pipeline (cli.py:126-128)
+    model.denoise_tower.denoise_projector   MLP2
+    model.forward_denoiser_context()        pass-through mode used by FSDP / log_validation (:352-355)
+
+`output_type="lvlm"` (text generation with lm_head / KV-cache decode) is outside the hot path
+ and raises.  One prefill serves both of cli.py's forward calls: the hidden state
+`hidden_states[-1]` the task head reads (cli.py:199-206) is exactly the pre-MLP2 tensor returned by
+`prefill_hidden()`.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+
+import torch
+
+from gpt_image_edit_b200._lib import B2FError
+from gpt_image_edit_b200.qwen2p5vl import B200Qwen2p5VL, QwenTextConfig, QwenVisionConfig, get_rope_index
+
+from ..configuration_univa_denoise_tower import UnivaDenoiseTowerConfig
+from ..modeling_univa_denoise_tower import UnivaDenoiseTower
+
+
+class UnivaQwen2p5VLConfig:
+    model_type = "univa_qwen2p5vl"
+
+    def __init__(self, denoise_tower: dict | UnivaDenoiseTowerConfig | None = None, text_config: dict | None = None,
+                 vision_config: dict | None = None, image_token_id: int = 151655, video_token_id: int = 151656,
+                 vision_start_token_id: int = 151652, shortcut_projector_type=None, shortcut_image_embeds=False, **kw):
+        self.text_config = QwenTextConfig(image_token_id=image_token_id, video_token_id=video_token_id,
+                                          vision_start_token_id=vision_start_token_id, **(text_config or {}))
+        self.vision_config = QwenVisionConfig(**(vision_config or {}))
+        if not isinstance(denoise_tower, UnivaDenoiseTowerConfig):
+            dt = dict(denoise_tower or {})
+            dt.setdefault("input_hidden_size", self.text_config.hidden_size)
+            denoise_tower = UnivaDenoiseTowerConfig(**dt)
+        self.denoise_tower = denoise_tower
+        self.image_token_id, self.video_token_id = image_token_id, video_token_id
+        self.vision_start_token_id = vision_start_token_id
+        self.hidden_size = self.text_config.hidden_size
+        self.shortcut_projector_type, self.shortcut_image_embeds = shortcut_projector_type, shortcut_image_embeds
+
+
+class UnivaQwen2p5VLForConditionalGeneration(torch.nn.Module):
+    config_class = UnivaQwen2p5VLConfig
+
+    def __init__(self, config: UnivaQwen2p5VLConfig, device="cuda"):
+        super().__init__()
+        self.config = config
+        self.lvlm = B200Qwen2p5VL(config.text_config, config.vision_config, device=device)
+        self.denoise_tower = UnivaDenoiseTower(config.denoise_tower, device=device)
+        self.forward_denoiser = False
+        self.rope_deltas = None
+
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    @property
+    def device(self):
+        return self.lvlm.device
+
+    def get_rope_index(self, input_ids, image_grid_thw=None, video_grid_thw=None, second_per_grid_ts=None,
+                       attention_mask=None):
+        if video_grid_thw is not None:
+            raise B2FError("video inputs are outside the image-editing hot path")
+        c = self.config
+        return get_rope_index(input_ids, image_grid_thw, attention_mask, spatial_merge_size=c.vision_config.spatial_merge_size,
+                              image_token_id=c.image_token_id, vision_start_token_id=c.vision_start_token_id)
+
+    def forward_visual(self, pixel_values, grid_thw):
+        return self.lvlm.forward_visual(pixel_values, grid_thw)
+
+    @torch.no_grad()
+    def prefill_hidden(self, input_ids, pixel_values=None, attention_mask=None, image_grid_thw=None):
+        """Last hidden state after the final norm, [B, L, hidden]."""
+        return self.lvlm(input_ids, pixel_values=pixel_values, attention_mask=attention_mask, image_grid_thw=image_grid_thw)
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, pixel_values=None, image_grid_thw=None,
+                output_type: str = "lvlm", denoiser_kwargs=None, only_use_t5: bool = False,
+                vlm_residual_image_factor: float = 0.0, **kwargs):
+        if not only_use_t5 and self.forward_denoiser:           # reference :352-355
+            return self.denoise_tower.denoiser(**kwargs)
+        if not output_type.startswith("denoise"):
+            raise B2FError('output_type="lvlm" (lm_head / generate) is outside the denoising hot path')
+        outputs = None
+        if not only_use_t5:
+            if vlm_residual_image_factor > 0.0:
+                raise B2FError("vlm_residual_image_factor > 0 is not implemented (default 0.0 in the reference)")
+            hidden = self.prefill_hidden(input_ids, pixel_values, attention_mask, image_grid_thw)
+            outputs = self.denoise_tower.denoise_projector(hidden)
+        if output_type == "denoise_embeds":
+            return outputs
+        if output_type == "denoise_model_pred":
+            kw = dict(denoiser_kwargs or {})
+            assert len(kw) > 0, "denoiser_kwargs should not be empty when output_type is denoise_model_pred"
+            kw["enc_attention_mask"] = attention_mask
+            return self.denoise_tower(encoder_hidden_states=outputs, **kw)
+        raise ValueError(f"Unknown output_type: {output_type}.")
+
+    @contextmanager
+    def forward_denoiser_context(self):                          # reference :604-621
+        prev = self.forward_denoiser
+        self.forward_denoiser = True
+        try:
+            yield
+        finally:
+            self.forward_denoiser = prev

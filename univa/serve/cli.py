@@ -1,0 +1,192 @@
+"""`python -m univa.serve.cli` — the reference's serving entry point (univa/serve/cli.py:118-286)
+over the libb2f engine: same flags (`--model_path --flux_path --height --width --num_inference_steps
+--guidance_scale --no_joint_with_t5 --ocr_enhancer --no_auto_hw`), same turn structure
+(VLM prefill -> task head -> MLP2 -> [T5 ‖ CLIP] -> FluxKontextPipeline -> PNG).
+
+Differences, all forced by this environment and all explicit:
+  * `--synthetic` builds every model with seeded random weights at the real architecture sizes (no
+    checkpoints or tokenizer files exist offline); token ids then follow SURVEY.md §8d's canonical
+    layout instead of the chat template.  Without `--synthetic` the loaders in
+    gpt_image_edit_b200.checkpoint read the reference's checkpoint directories (safetensors).
+  * one VLM prefill per turn instead of the reference's two identical ones (cli.py:200 and :211):
+    `hidden_states[-1]` of the first equals the pre-MLP2 tensor of the second.
+  * T5-XXL / CLIP-L prompt encoders are SURVEY.md §8f "next": with `--synthetic` their outputs are
+    seeded stand-ins of the right shape; the text-reply branch (`model.generate`) is not built.
+  * `--prompt/--image/--output` run one non-interactive turn (the reference is REPL-only).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import numpy as np
+import torch
+
+from gpt_image_edit_b200 import ops
+from gpt_image_edit_b200.image_io import image_to_condition_tensor, qwen_pixel_values, resize_u8
+from gpt_image_edit_b200.pipeline import FluxKontextPipeline
+from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
+from gpt_image_edit_b200.vae import B200AutoencoderKL
+from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig, UnivaQwen2p5VLForConditionalGeneration
+from univa.utils.anyres_util import dynamic_resize
+
+seed = 42
+ASSISTANT_TOKEN_ID = 77091          # reference cli.py:202
+IM_START, IM_END, VISION_START, VISION_END, IMAGE_PAD = 151644, 151645, 151652, 151653, 151655
+
+
+class TaskHead(torch.nn.Module):
+    """Linear(3584,10240)·SiLU·Dropout·Linear(10240,2) (reference cli.py:42-49) as two libb2f GEMMs."""
+
+    def __init__(self, hidden=3584, inner=10240, device="cuda"):
+        super().__init__()
+        z = lambda *s: torch.zeros(s, device=device, dtype=torch.bfloat16)
+        self.w0, self.b0, self.w3, self.b3 = z(inner, hidden), z(inner), z(8, inner), z(8)   # 2 logits, rows padded to 8
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.linear(ops.linear(x.to(torch.bfloat16), self.w0, self.b0, epilogue=ops.EPI_SILU), self.w3, self.b3)[:, :2]
+
+
+def load_main_model_and_processor(model_path, device, synthetic=False, small=False):
+    if not synthetic:
+        from gpt_image_edit_b200.checkpoint import load_univa_checkpoint
+        return load_univa_checkpoint(model_path, device)
+    kw = {}
+    if small:  # plumbing runs: a few layers at full width
+        kw = dict(text_config=dict(num_hidden_layers=2), vision_config=dict(depth=2, fullatt_block_indexes=(1,)),
+                  denoise_tower=dict(denoiser_config=dict(num_layers=1, num_single_layers=1)))
+    cfg = UnivaQwen2p5VLConfig(**kw)
+    model = UnivaQwen2p5VLForConditionalGeneration(cfg, device=device)
+    model.lvlm.randomize_(seed=10)
+    model.denoise_tower.denoiser.randomize_(seed=0)
+    g = torch.Generator(device=device).manual_seed(11)
+    for t in model.denoise_tower.denoise_projector.state_dict().values():
+        t.copy_((torch.randn(t.shape, device=device, generator=g) * 0.02).to(torch.bfloat16))
+    head = TaskHead(cfg.hidden_size, device=device)
+    head.w0.copy_((torch.randn(head.w0.shape, device=device, generator=g) * 0.02).to(torch.bfloat16))
+    head.w3[:2].copy_((torch.randn(2, head.w3.shape[1], device=device, generator=g) * 0.02).to(torch.bfloat16))
+    head.b3[1] = 1.0   # synthetic head always routes to "generate"
+    return model, head, None
+
+
+def load_pipe(denoiser, flux_path, device, synthetic=False):
+    if not synthetic:
+        pipe = FluxKontextPipeline.from_pretrained(flux_path, transformer=denoiser, torch_dtype=torch.bfloat16)
+        return pipe, None, None
+    vae = B200AutoencoderKL(device=device).randomize_(seed=1)
+    return FluxKontextPipeline(transformer=denoiser, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler()), None, None
+
+
+def update_size(shapes, anyres="any_11ratio", anchor_pixels=1024 * 1024):
+    """(h, w) of the generation from the input image sizes (reference cli.py:82-97)."""
+    if not shapes:
+        return int(anchor_pixels ** 0.5), int(anchor_pixels ** 0.5)
+    w = sum(s[0] for s in shapes) / len(shapes)
+    h = sum(s[1] for s in shapes) / len(shapes)
+    return dynamic_resize(int(h), int(w), anyres, anchor_pixels=anchor_pixels)
+
+
+def synthetic_chat_tokens(n_image_tokens: int, n_text: int = 24, vocab: int = 152064, seed_: int = 2):
+    """<|im_start|> user \\n <|vision_start|> [image_pad]*n <|vision_end|> text... <|im_end|> \\n <|im_start|> assistant \\n
+    with seeded text ids (the chat template needs tokenizer files that are not available offline)."""
+    g = torch.Generator().manual_seed(seed_)
+    text = torch.randint(1000, 100000, (n_text,), generator=g).tolist()
+    ids = [IM_START, 872, 198, VISION_START] + [IMAGE_PAD] * n_image_tokens + [VISION_END] + text + \
+          [IM_END, 198, IM_START, ASSISTANT_TOKEN_ID, 198]
+    return torch.tensor([ids])
+
+
+@torch.no_grad()
+def run_turn(args, model, task_head, pipe, image_u8: np.ndarray | None, text: str, device):
+    shapes = [(image_u8.shape[1], image_u8.shape[0])] if image_u8 is not None else []
+    new_h, new_w = (args.height, args.width) if args.no_auto_hw or not shapes else \
+        update_size(shapes, "any_11ratio", anchor_pixels=args.height * args.width)
+    pixel_values = grid = None
+    n_img_tok = 0
+    if image_u8 is not None:
+        pixel_values, grid = qwen_pixel_values(resize_u8(image_u8, 448, 448))          # min_pixels = max_pixels = 448^2
+        n_img_tok = pixel_values.shape[0] // 4
+    input_ids = synthetic_chat_tokens(n_img_tok).to(device)
+    hidden = model.prefill_hidden(input_ids, pixel_values=None if pixel_values is None else pixel_values.to(device),
+                                  attention_mask=torch.ones_like(input_ids), image_grid_thw=grid)
+    assistant_vec = hidden[input_ids == ASSISTANT_TOKEN_ID][-1:]
+    task = task_head(assistant_vec)[0].float()
+    if not (task[0] < task[1]):
+        raise NotImplementedError("the text-reply branch (model.generate, reference cli.py:256-267) is outside the hot path")
+    lvlm_embeds = model.denoise_tower.denoise_projector(hidden)                          # MLP2 -> [1, L, 4096]
+    g = torch.Generator(device=device).manual_seed(seed + 1)
+    pooled = torch.randn(1, 768, device=device, generator=g).bfloat16()                 # CLIP-L stand-in (§8f)
+    if not args.no_joint_with_t5:
+        t5 = torch.randn(1, 256, 4096, device=device, generator=g).bfloat16()           # T5-XXL stand-in (§8f)
+        prompt_embeds = torch.cat([lvlm_embeds, t5], dim=1)
+    else:
+        prompt_embeds = lvlm_embeds
+    cond = None if image_u8 is None else image_to_condition_tensor(image_u8).to(device)
+    return pipe(image=cond, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled, height=new_h, width=new_w,
+                num_inference_steps=args.num_inference_steps, guidance_scale=args.guidance_scale,
+                generator=torch.Generator(device=device).manual_seed(seed),
+                **({"max_area": args.max_area, "_auto_resize": False} if args.max_area else {})).images[0]
+
+
+def main(args):
+    if not torch.cuda.is_available():
+        raise SystemExit("univa.serve.cli runs on a B200 through libb2f; there is no CPU path")
+    device = torch.device("cuda")
+    model, task_head, _ = load_main_model_and_processor(args.model_path, device, args.synthetic, args.small)
+    pipe, _, _ = load_pipe(model.denoise_tower.denoiser, args.flux_path, device, args.synthetic)
+    from PIL import Image
+
+    def load(path):
+        return None if not path else np.asarray(Image.open(path).convert("RGB"))
+
+    if args.prompt is not None or args.image is not None:
+        img = run_turn(args, model, task_head, pipe, load(args.image), args.prompt or "", device)
+        img.save(args.output)
+        print(f"Assistant: generate image at {args.output}")
+        return
+    print("Interactive UniWorld-V1 Chat (Exit if input is empty)")
+    k = 0
+    while True:
+        txt = input("Text prompt (or press Enter to skip): ").strip()
+        img_input = input("Image URLs (comma-separated, or press Enter to skip): ").strip()
+        if not img_input and not txt:
+            print("Exit.")
+            break
+        urls = [u.strip() for u in img_input.split(",") if u.strip()]
+        if len(urls) > 1:
+            print("only one context image per edit is supported (as in the reference pipeline, SURVEY.md §3.1)")
+        out = run_turn(args, model, task_head, pipe, load(urls[0]) if urls else None, txt, device)
+        path = os.path.join(os.getcwd(), f"output_{k}.png")
+        out.save(path)
+        k += 1
+        print(f"Assistant: generate image at {path}\n")
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description="Model and component paths")
+    p.add_argument("--model_path", type=str, default="")
+    p.add_argument("--flux_path", type=str, default="")
+    p.add_argument("--no_auto_hw", action="store_true")
+    p.add_argument("--height", type=int, default=1024)
+    p.add_argument("--width", type=int, default=1024)
+    p.add_argument("--num_inference_steps", type=int, default=28)
+    p.add_argument("--guidance_scale", type=float, default=3.5)
+    p.add_argument("--ocr_enhancer", action="store_true")
+    p.add_argument("--no_joint_with_t5", action="store_true")
+    # additions
+    p.add_argument("--synthetic", action="store_true", help="seeded random weights (no checkpoints offline)")
+    p.add_argument("--small", action="store_true", help="with --synthetic: a few layers only (plumbing runs)")
+    p.add_argument("--max_area", type=int, default=0, help="pass max_area to the pipeline and disable _auto_resize "
+                   "(the reference always rescales to ~1 MP, SURVEY.md §0 item 8)")
+    p.add_argument("--prompt", type=str, default=None)
+    p.add_argument("--image", type=str, default=None)
+    p.add_argument("--output", type=str, default="output.png")
+    return p
+
+
+if __name__ == "__main__":
+    a = build_parser().parse_args()
+    if not a.synthetic and not (a.model_path and a.flux_path):
+        raise SystemExit("--model_path and --flux_path are required (or pass --synthetic)")
+    main(a)
