@@ -266,36 +266,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int c = 0; c < 128; ++c)
           if (kv0 + c >= limit) sr[c] = 0xff800000u;  // -inf
       }
-      // 8 independent max chains (a single dependent chain of 128 FMNMX costs ~4 clk per link and
-      // nothing else in this warp can hide it: only two softmax warps share an SM sub-partition)
-      float mx8[8];
+      // row max with 3-input FMNMX3 in 4 independent chains (a single dependent chain costs ~4 clk per
+      // link and only two softmax warps share an SM sub-partition, so nothing would hide it)
+      float mx4[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
+      for (int i = 0; i < 4; ++i)
+        mx4[i] = fmaxf(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1]));
 #pragma unroll
       for (int c = 8; c < 128; c += 8)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
-      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        for (int i = 0; i < 4; ++i)
+          mx4[i] = fmax3(mx4[i], __uint_as_float(sr[c + 2 * i]), __uint_as_float(sr[c + 2 * i + 1]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m, mx * p.scale_log2);
       // lazy rescale: keep the stale max unless it grew by more than 2^8 (P stays < 256)
       const bool grow = (m_new - m) > 8.0f;
       const float m_use = grow ? m_new : m;
       const float alpha = grow ? ex2(m - m_use) : 1.0f;
       const float neg_m = (m_use == -INFINITY) ? 0.f : -m_use;  // fully masked row (causal tail)
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};   // two packed (FADD2) accumulator pairs
       if (TURNS) named_bar_sync(1 + t, 256);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float x0 = fmaf(__uint_as_float(sr[half * 64 + 2 * c]), p.scale_log2, neg_m);
-          const float x1 = fmaf(__uint_as_float(sr[half * 64 + 2 * c + 1]), p.scale_log2, neg_m);
-          const float p0 = ex2(x0);
+          float x0, x1;
+          ffma2(x0, x1, __uint_as_float(sr[half * 64 + 2 * c]), __uint_as_float(sr[half * 64 + 2 * c + 1]),
+                p.scale_log2, p.scale_log2, neg_m, neg_m);
           constexpr int PH = POLY / 2 ? POLY / 2 : 1;
+          const float p0 = ex2(x0);
           const float p1 = (POLY && (c % PH) == PH - 1) ? ex2_poly(x1) : ex2(x1);
-          sum4[c & 3] += p0 + p1;
+          const int a = (c & 1) * 2;
+          fadd2(sum4[a], sum4[a + 1], sum4[a], sum4[a + 1], p0, p1);
           pk[c] = pack_bf16x2(p0, p1);
         }
         B2F_TMEM_ST_X32(s_tmem + half * 32, pk);
@@ -354,6 +357,278 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+
+// ================================================================================================
+// v2: the same CTA layout (two 128-row Q tiles, 4-slot K/V ring of 128-row tiles), but S is produced
+// and consumed in 64-column SUB-BLOCKS with TWO S buffers per tile, so the tensor core computes
+// S(u+1) (and S(u+2)) while the softmax warpgroup is still working on S(u):
+//   TMEM per tile t:  S buffers at t*128 + {0, 64} (P bf16 aliased over the first 32 columns of each),
+//                     O at 256 + t*128.
+//   MMA lane:   QK(t,0) QK(t,1) | for u: wait P(t,u) -> PV(t,u) -> QK(t,u+2) into the buffer PV(t,u)
+//               just released.  The softmax warpgroup never waits for the tensor pipe in steady state.
+//   o_done[t] completes once per PV(t,u); the warpgroup only looks at it before the (rare, lazy) O
+//   rescale and before the epilogue — completions can never run ahead by more than one phase because
+//   PV(t,u) needs P(t,u) from the same warpgroup.
+constexpr int SUB = 64;
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + 2 * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + KV_SLOTS) * TILE_BYTES);
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* kv_full = bars + 1;              // KV_SLOTS
+  uint64_t* kv_empty = kv_full + KV_SLOTS;   // KV_SLOTS
+  uint64_t* s_full = kv_empty + KV_SLOTS;    // [tile][buf] = 4
+  uint64_t* p_full = s_full + 4;             // [tile][buf] = 4
+  uint64_t* o_done = p_full + 4;             // [tile] = 2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qpair = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.H / p.Hkv);
+  const int q0 = qpair * 2 * BQ;
+  int kv_len = p.Skv;
+  if (p.causal) kv_len = min(p.Skv, q0 + 2 * BQ);
+  const int n_kv = (kv_len + BKV - 1) / BKV;
+  const int n_sub = (kv_len + SUB - 1) / SUB;   // 64-column sub-blocks actually needed
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KV_SLOTS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      for (int t = 0; t < 2; ++t)
+        for (int half = 0; half < 2; ++half)
+          tma_load_3d(q_smem + t * TILE_BYTES + half * (TILE_BYTES / 2), &tmQ, q_full,
+                      h * DH + half * 64, q0 + t * BQ, b);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        for (int kv = 0; kv < 2; ++kv) {
+          mbar_wait(&kv_empty[slot], phase ^ 1);
+          mbar_expect_tx(&kv_full[slot], TILE_BYTES);
+          uint8_t* dst = kv_smem + slot * TILE_BYTES;
+          const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
+          tma_load_3d(dst, tm, &kv_full[slot], hk * DH, j * BKV, b);
+          tma_load_3d(dst + TILE_BYTES / 2, tm, &kv_full[slot], hk * DH + 64, j * BKV, b);
+          if (++slot == KV_SLOTS) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, SUB, 0);  // S sub-block: 128 x 64
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 1);   // O: 128 x 128, V MN-major
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t kv_addr = smem_u32(kv_smem);
+      // K rows [64 hh, 64 hh + 64) of a 128-row tile start 8 KB into each dh-half sub-tile
+      auto issue_qk = [&](int t, int buf, uint32_t k_tile, int hh) {
+        const uint32_t d = tmem_base + uint32_t(t * 128 + buf * SUB);
+        const uint32_t qa = q_addr + t * TILE_BYTES;
+        const uint32_t ka = k_tile + hh * (SUB * 128);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          const uint32_t off = (k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32;
+          umma_ss(d, make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024), idesc_qk,
+                  k != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int buf, uint32_t v_tile, int hh, bool first) {
+        const uint32_t d = tmem_base + 256 + uint32_t(t * 128);
+        const uint32_t pa = tmem_base + uint32_t(t * 128 + buf * SUB);
+        const uint32_t va = v_tile + hh * (SUB * 128);
+#pragma unroll
+        for (int k = 0; k < SUB / 16; ++k)
+          umma_ts(d, pa + k * 8, make_sdesc_sw128(va + k * 2048, TILE_BYTES / 2, 1024), idesc_pv,
+                  (first && k == 0) ? 0u : 1u);
+      };
+      // ring bookkeeping: tile index i (0 = K_0, 1 = V_0, 2 = K_1, ...) lives in slot i % 4, phase (i / 4) & 1
+      auto slot_of = [](int i) { return i % KV_SLOTS; };
+      auto phase_of = [](int i) { return uint32_t((i / KV_SLOTS) & 1); };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      for (int u0 = 0; u0 < 2 && u0 < n_sub; ++u0)
+        for (int t = 0; t < 2; ++t) {
+          issue_qk(t, u0, kv_addr, u0);
+          umma_commit(&s_full[t * 2 + u0]);
+        }
+      if (n_sub <= 2) umma_commit(&kv_empty[0]);   // K_0 fully consumed (otherwise released below)
+      for (int u = 0; u < n_sub; ++u) {
+        const int j = u >> 1, hh = u & 1, buf = u & 1;
+        const int vi = 2 * j + 1;              // ring index of V_j
+        if (hh == 0 || u == 0) {
+          mbar_wait(&kv_full[slot_of(vi)], phase_of(vi));
+          tc_fence_after();
+        }
+        const uint32_t v_tile = kv_addr + slot_of(vi) * TILE_BYTES;
+        const int u2 = u + 2;                  // the QK that reuses this S buffer
+        const int ki2 = 2 * (u2 >> 1);         // ring index of K_{u2/2}
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t * 2 + buf], uint32_t(u >> 1) & 1);
+          tc_fence_after();
+          issue_pv(t, buf, v_tile, hh, u == 0);
+          umma_commit(&o_done[t]);
+          if (u2 < n_sub) {
+            if (t == 0 && hh == 0) {
+              mbar_wait(&kv_full[slot_of(ki2)], phase_of(ki2));
+              tc_fence_after();
+            }
+            issue_qk(t, buf, kv_addr + slot_of(ki2) * TILE_BYTES, hh);
+            umma_commit(&s_full[t * 2 + buf]);
+          }
+        }
+        // releases: V_j after its second half (or the last sub-block); K tiles after their last QK
+        const bool last_of_v = (hh == 1) || (u == n_sub - 1);
+        if (last_of_v) umma_commit(&kv_empty[slot_of(vi)]);
+        if (u2 < n_sub && ((u2 & 1) == 1 || u2 == n_sub - 1)) umma_commit(&kv_empty[slot_of(ki2)]);
+        if (u == 0 && n_sub > 2) {
+          // K_0 was consumed by the prologue QKs (u = 0, 1): everything issued so far covers them
+          umma_commit(&kv_empty[0]);
+        }
+      }
+    }
+  } else {
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + t * BQ + row_in_tile;
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const uint32_t s_base = tmem_base + lane_addr + uint32_t(t * 128);
+    const uint32_t o_tmem = tmem_base + lane_addr + 256 + uint32_t(t * 128);
+    float m = -INFINITY, l = 0.f;
+    for (int u = 0; u < n_sub; ++u) {
+      const int buf = u & 1;
+      const uint32_t s_tmem = s_base + uint32_t(buf * SUB);
+      mbar_wait(&s_full[t * 2 + buf], uint32_t(u >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr[64];
+      B2F_TMEM_LD_X32(s_tmem + 0, (sr + 0));
+      B2F_TMEM_LD_X32(s_tmem + 32, (sr + 32));
+      tmem_wait_ld();
+      const int kv0 = u * SUB;
+      const bool need_mask = (kv0 + SUB > p.Skv) || (p.causal && kv0 + SUB > q0 + t * BQ);
+      if (need_mask) {
+        const int limit = p.causal ? min(p.Skv, q_row + 1) : p.Skv;
+#pragma unroll
+        for (int c = 0; c < SUB; ++c)
+          if (kv0 + c >= limit) sr[c] = 0xff800000u;
+      }
+      float mx4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx4[i] = fmaxf(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1]));
+#pragma unroll
+      for (int c = 8; c < SUB; c += 8)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          mx4[i] = fmax3(mx4[i], __uint_as_float(sr[c + 2 * i]), __uint_as_float(sr[c + 2 * i + 1]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      const bool grow = (m_new - m) > 8.0f;
+      const float m_use = grow ? m_new : m;
+      const float alpha = grow ? ex2(m - m_use) : 1.0f;
+      const float neg_m = (m_use == -INFINITY) ? 0.f : -m_use;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float x0, x1;
+        ffma2(x0, x1, __uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]), p.scale_log2, p.scale_log2,
+              neg_m, neg_m);
+        const float p0 = ex2(x0), p1 = ex2(x1);
+        const int a = (c & 1) * 2;
+        fadd2(sum4[a], sum4[a + 1], sum4[a], sum4[a + 1], p0, p1);
+        pk[c] = pack_bf16x2(p0, p1);
+      }
+      B2F_TMEM_ST_X32(s_tmem, pk);
+      l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+      m = m_use;
+      if (u > 0 && __any_sync(0xffffffffu, grow)) {
+        // O must be quiescent: PV(t, u-1) is the last one issued (PV(t,u) waits for the arrive below)
+        mbar_wait(&o_done[t], uint32_t(u - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t o[32];
+          B2F_TMEM_LD_X32(o_tmem + c0, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          B2F_TMEM_ST_X32(o_tmem + c0, o);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t * 2 + buf]);
+    }
+    mbar_wait(&o_done[t], uint32_t(n_sub - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const bool row_ok = q_row < p.Sq;
+    __nv_bfloat16* out_row = p.out + ((long long)b * p.Sq + q_row) * p.ldo + (long long)h * DH;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t o[32];
+      __syncwarp();
+      B2F_TMEM_LD_X32(o_tmem + c0, o);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(out_row + c0 + g * 8) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -381,6 +656,7 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
       case 3: kernel = attn_fwd_kernel<0, true>; break;
       case 4: kernel = attn_fwd_kernel<4, true>; break;
       case 5: kernel = attn_fwd_kernel<2, true>; break;
+      case 10: kernel = attn_fwd_kernel_v2; break;
       default: kernel = attn_fwd_kernel<0, false>; break;
     }
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);

@@ -9,6 +9,10 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
               const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M, int N,
               int K, int epilogue, const void* resid, int64_t ldr, int64_t resid_bs, const void* gate,
               int64_t gate_ld, cudaStream_t stream);
+int gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
+                       const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M,
+                       int d_model, int K, const void* nw_q, const void* nw_k, const float* cos,
+                       const float* sin, int rope_row0, float eps, cudaStream_t stream);
 int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
                 const void* shift, int64_t mod_ld, void* out, int64_t ldo, int64_t out_batch_stride,
                 int batch, int rows, int D, float eps, cudaStream_t stream);
@@ -96,6 +100,16 @@ int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void
   return b2f::gemm_bf16(A, lda, a_batch_stride, W, ldw, bias, out, ldc, out_batch_stride, batch, M,
                         N, K, epilogue, resid, ldr, resid_batch_stride, gate, gate_ld,
                         static_cast<cudaStream_t>(stream));
+}
+
+int b2f_gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_batch_stride, const void* W,
+                           int64_t ldw, const void* bias, void* out, int64_t ldc,
+                           int64_t out_batch_stride, int batch, int M, int d_model, int K,
+                           const void* nw_q, const void* nw_k, const float* cos, const float* sin,
+                           int rope_row0, float eps, b2f_stream_t stream) {
+  return b2f::gemm_qkv_norm_rope(A, lda, a_batch_stride, W, ldw, bias, out, ldc, out_batch_stride, batch,
+                                 M, d_model, K, nw_q, nw_k, cos, sin, rope_row0, eps,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int b2f_ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,

@@ -14,7 +14,7 @@
 #include <cstdlib>
 
 #ifndef B2F_GEMM_2CTA_DEFAULT
-#define B2F_GEMM_2CTA_DEFAULT 0
+#define B2F_GEMM_2CTA_DEFAULT 1
 #endif
 
 #include "host_common.h"
@@ -43,6 +43,13 @@ struct GemmParams {
   long long gate_ld;
   int m_blocks_per_batch;
   int num_m_blocks, num_n_blocks, panel_n;
+  // B2F_EPI_QKV_NORM_ROPE: N = 3*d_model laid out [Q | K | V], heads of 128 columns
+  const __nv_bfloat16* nw_q;
+  const __nv_bfloat16* nw_k;
+  const float* rope_cos;  // [S, 128] fp32, row = rope_row0 + row-in-batch
+  const float* rope_sin;
+  int rope_row0, d_model;
+  float norm_eps;
 };
 
 template <int BN>
@@ -137,6 +144,120 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     o.z = pack_bf16x2(v[4], v[5]);
     o.w = pack_bf16x2(v[6], v[7]);
     *reinterpret_cast<uint4*>(out_row + n) = o;
+  }
+}
+
+
+// One 128-column head of a fused QKV projection for one token, straight from the accumulators:
+//   x = bf16(acc + bias);  y = bf16(x * rsqrt(mean(x^2) + eps));  z = bf16(y * w);
+//   out = bf16(z * cos + rot(z) * sin)        (diffusers RMSNorm + apply_rotary_emb)
+// — the same rounding chain as rmsnorm_rope_kernel, but without the extra HBM round trip.
+__device__ __forceinline__ void epilogue_head_norm_rope(const GemmParams& p, uint32_t (&a)[128], int n_head0,
+                                                        long long row, __nv_bfloat16* out_row, bool is_k) {
+  const __nv_bfloat16* w = is_k ? p.nw_k : p.nw_q;
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < 128; c += 8) {
+    const uint4 bq = p.bias ? __ldg(reinterpret_cast<const uint4*>(p.bias + n_head0 + c)) : make_uint4(0, 0, 0, 0);
+    const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 b2 = unpack_bf16x2(bw[j]);
+      const float x0 = bf16r(__uint_as_float(a[c + 2 * j]) + b2.x);
+      const float x1 = bf16r(__uint_as_float(a[c + 2 * j + 1]) + b2.y);
+      ss = fmaf(x0, x0, ss);
+      ss = fmaf(x1, x1, ss);
+      a[c + 2 * j] = __float_as_uint(x0);
+      a[c + 2 * j + 1] = __float_as_uint(x1);
+    }
+  }
+  const float r = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
+  const float* cs = p.rope_cos + ((long long)p.rope_row0 + row) * 128;
+  const float* sn = p.rope_sin + ((long long)p.rope_row0 + row) * 128;
+#pragma unroll
+  for (int c = 0; c < 128; c += 8) {
+    const uint4 wq = __ldg(reinterpret_cast<const uint4*>(w + c));
+    const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cs + c)), c1 = __ldg(reinterpret_cast<const float4*>(cs + c + 4));
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sn + c)), s1 = __ldg(reinterpret_cast<const float4*>(sn + c + 4));
+    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 w2 = unpack_bf16x2(ww[j]);
+      const float z0 = bf16r(bf16r(__uint_as_float(a[c + 2 * j]) * r) * w2.x);
+      const float z1 = bf16r(bf16r(__uint_as_float(a[c + 2 * j + 1]) * r) * w2.y);
+      o[2 * j] = z0 * cc[2 * j] - z1 * sc[2 * j];
+      o[2 * j + 1] = z1 * cc[2 * j + 1] + z0 * sc[2 * j + 1];
+    }
+    uint4 ov;
+    ov.x = pack_bf16x2(o[0], o[1]);
+    ov.y = pack_bf16x2(o[2], o[3]);
+    ov.z = pack_bf16x2(o[4], o[5]);
+    ov.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(out_row + n_head0 + c) = ov;
+  }
+}
+
+// Epilogue of one output tile for the calling warp's 32 rows: TMEM -> registers -> fused math -> global.
+// `arrive_cta0`: the CTA-pair kernel hands the accumulator stage back on CTA 0's barrier.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int as, int q, int lane,
+                                              int n_blk, bool row_ok, long long row, __nv_bfloat16* out_row,
+                                              const __nv_bfloat16* res_row, const __nv_bfloat16* gate_row,
+                                              uint64_t* tmem_empty_bar, bool arrive_cta0) {
+  auto release = [&]() {
+    // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (arrive_cta0)
+        mbar_arrive_cta0(tmem_empty_bar);
+      else
+        mbar_arrive(tmem_empty_bar);
+    }
+  };
+  if (p.epi == B2F_EPI_QKV_NORM_ROPE) {
+#pragma unroll 1
+    for (int h0 = 0; h0 < BN; h0 += 128) {
+      uint32_t a[128];
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + h0);
+      __syncwarp();
+      B2F_TMEM_LD_X32(taddr + 0, (a + 0));
+      B2F_TMEM_LD_X32(taddr + 32, (a + 32));
+      B2F_TMEM_LD_X32(taddr + 64, (a + 64));
+      B2F_TMEM_LD_X32(taddr + 96, (a + 96));
+      tmem_wait_ld();
+      if (h0 + 128 == BN) release();
+      const int n_head0 = n_blk * BN + h0;
+      if (!row_ok || n_head0 >= p.N) continue;
+      const int which = n_head0 / p.d_model;  // 0 = Q, 1 = K, 2 = V
+      if (which < 2) {
+        epilogue_head_norm_rope(p, a, n_head0, row, out_row, which == 1);
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = a[cc * 32 + j];
+          epilogue_chunk(p, acc, n_head0 + cc * 32, out_row, res_row, gate_row);
+        }
+      }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t acc[32];
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
+    __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+    B2F_TMEM_LD_X32(taddr, acc);
+    tmem_wait_ld();
+    if (c0 + 32 == BN) release();
+    const int n0 = n_blk * BN + c0;
+    if (!row_ok || n0 >= p.N) continue;
+    epilogue_chunk(p, acc, n0, out_row, res_row, gate_row);
   }
 }
 
@@ -259,23 +380,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
       __nv_bfloat16* out_row = p.out + bidx * p.out_bs + row * p.ldc;
       const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t acc[32];
-        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
-        B2F_TMEM_LD_X32(taddr, acc);
-        tmem_wait_ld();
-        if (c0 + 32 == BN) {
-          // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        }
-        const int n0 = n_blk * BN + c0;
-        if (!row_ok || n0 >= p.N) continue;
-        epilogue_chunk(p, acc, n0, out_row, res_row, gate_row);
-      }
+      epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], false);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -464,22 +569,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
       __nv_bfloat16* out_row = p.out + bidx * p.out_bs + row * p.ldc;
       const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t acc[32];
-        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
-        __syncwarp();
-        B2F_TMEM_LD_X32(taddr, acc);
-        tmem_wait_ld();
-        if (c0 + 32 == BN) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cta0(&tmem_empty[as]);
-        }
-        const int n0 = n_blk * BN + c0;
-        if (!row_ok || n0 >= p.N) continue;
-        epilogue_chunk(p, acc, n0, out_row, res_row, gate_row);
-      }
+      epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], true);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -522,10 +612,17 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams 
 
 }  // namespace
 
-int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
+struct QkvExtra {
+  const void *nw_q, *nw_k;
+  const float *cos, *sin;
+  int rope_row0, d_model;
+  float eps;
+};
+
+static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
               const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M, int N,
               int K, int epilogue, const void* resid, int64_t ldr, int64_t resid_bs, const void* gate,
-              int64_t gate_ld, cudaStream_t stream) {
+              int64_t gate_ld, const QkvExtra* qx, cudaStream_t stream) {
   if (!device_info().ok) return B2F_ERR_NODEVICE;
   if (batch <= 0 || M <= 0 || N <= 0 || K <= 0 || !A || !W || !out) return B2F_ERR_INVALID;
   if ((K & 7) || (N & 7) || (lda & 7) || (ldw & 7) || (ldc & 7) || (a_bs & 7) || (out_bs & 7))
@@ -534,7 +631,14 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
        reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(gate)) & 15)
     return B2F_ERR_ALIGN;
-  if (epilogue < 0 || epilogue > B2F_EPI_GELU_ERF) return B2F_ERR_INVALID;
+  if (epilogue < 0 || epilogue > B2F_EPI_QKV_NORM_ROPE) return B2F_ERR_INVALID;
+  if (epilogue == B2F_EPI_QKV_NORM_ROPE) {
+    if (!qx || !qx->nw_q || !qx->nw_k || !qx->cos || !qx->sin || qx->d_model <= 0) return B2F_ERR_INVALID;
+    if (N != 3 * qx->d_model || (qx->d_model % 128)) return B2F_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(qx->nw_q) | reinterpret_cast<uintptr_t>(qx->nw_k) |
+         reinterpret_cast<uintptr_t>(qx->cos) | reinterpret_cast<uintptr_t>(qx->sin)) & 15)
+      return B2F_ERR_ALIGN;
+  }
   if (epilogue == B2F_EPI_GATE_RESID) {
     if (!resid || !gate || (ldr & 7) || (gate_ld & 7) || (resid_bs & 7)) return B2F_ERR_INVALID;
   }
@@ -556,6 +660,15 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
   p.resid_bs = resid_bs;
   p.gate = static_cast<const __nv_bfloat16*>(gate);
   p.gate_ld = gate_ld;
+  if (qx) {
+    p.nw_q = static_cast<const __nv_bfloat16*>(qx->nw_q);
+    p.nw_k = static_cast<const __nv_bfloat16*>(qx->nw_k);
+    p.rope_cos = qx->cos;
+    p.rope_sin = qx->sin;
+    p.rope_row0 = qx->rope_row0;
+    p.d_model = qx->d_model;
+    p.norm_eps = qx->eps;
+  }
 
   const long long num_m = (long long)batch * ((M + BLOCK_M - 1) / BLOCK_M);
   const bool use256 = num_m * ((N + 255) / 256) >= device_info().num_sms && N >= 256;
@@ -578,6 +691,24 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
                          BLOCK_K);
   if (rc != B2F_OK) return rc;
   return use256 ? launch_gemm<256>(tmA, tmB, p, stream) : launch_gemm<128>(tmA, tmB, p, stream);
+}
+
+int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
+              const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M, int N,
+              int K, int epilogue, const void* resid, int64_t ldr, int64_t resid_bs, const void* gate,
+              int64_t gate_ld, cudaStream_t stream) {
+  if (epilogue == B2F_EPI_QKV_NORM_ROPE) return B2F_ERR_INVALID;  // needs the extended entry point
+  return gemm_bf16_impl(A, lda, a_bs, W, ldw, bias, out, ldc, out_bs, batch, M, N, K, epilogue, resid, ldr,
+                        resid_bs, gate, gate_ld, nullptr, stream);
+}
+
+int gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
+                       const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M,
+                       int d_model, int K, const void* nw_q, const void* nw_k, const float* cos,
+                       const float* sin, int rope_row0, float eps, cudaStream_t stream) {
+  QkvExtra qx{nw_q, nw_k, cos, sin, rope_row0, d_model, eps};
+  return gemm_bf16_impl(A, lda, a_bs, W, ldw, bias, out, ldc, out_bs, batch, M, 3 * d_model, K,
+                        B2F_EPI_QKV_NORM_ROPE, nullptr, 0, 0, nullptr, 0, &qx, stream);
 }
 
 }  // namespace b2f

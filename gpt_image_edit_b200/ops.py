@@ -202,3 +202,21 @@ def scatter_rows_(dst, idx, src):
     check(_lib.lib.b2f_move_rows(ptr(src), src.stride(0), ptr(dst), dst.stride(0), ptr(idx), idx.numel(), dst.shape[1], 1,
                                  stream_ptr()), "b2f_move_rows(scatter)")
     return dst
+
+
+def linear_qkv_norm_rope(x, weight, bias, wq, wk, cos, sin, *, rope_row0: int = 0, out=None, eps: float = 1e-6):
+    """[Q|K|V] = x @ weight^T + bias with per-head RMSNorm + RoPE on Q, K fused in the GEMM epilogue."""
+    _req(x, "x")
+    _req(weight, "weight")
+    _req(cos, "cos", torch.float32)
+    _req(sin, "sin", torch.float32)
+    x3 = _as3(x)
+    B, M, K = x3.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty((*x.shape[:-1], N), device=x.device, dtype=torch.bfloat16)
+    o3 = _as3(out)
+    check(_lib.lib.b2f_gemm_qkv_norm_rope(ptr(x3), x3.stride(1), x3.stride(0), ptr(weight), weight.stride(0), ptr(bias),
+                                          ptr(o3), o3.stride(1), o3.stride(0), B, M, N // 3, K, ptr(wq), ptr(wk),
+                                          ptr(cos), ptr(sin), rope_row0, eps, stream_ptr()), "b2f_gemm_qkv_norm_rope")
+    return out

@@ -72,6 +72,7 @@ int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* fl
 #define B2F_EPI_SILU 2
 #define B2F_EPI_GATE_RESID 3
 #define B2F_EPI_RESID 4 /* out = bf16(resid + bf16(acc + bias))  (VAE attention to_out + residual) */
+#define B2F_EPI_QKV_NORM_ROPE 6 /* only through b2f_gemm_qkv_norm_rope */
 #define B2F_EPI_GELU_ERF 5 /* out = bf16(gelu_erf(bf16(acc + bias)))  (Qwen2.5-VL patch merger, nn.GELU()) */
 
 int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
@@ -79,6 +80,18 @@ int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void
                   int M, int N, int K, int epilogue, const void* resid, int64_t ldr,
                   int64_t resid_batch_stride, const void* gate, int64_t gate_ld,
                   b2f_stream_t stream);
+
+/* Fused QKV projection of an MMDiT attention block: out[.., 3*d] = A · Wqkv^T + b with per-head
+ * RMSNorm(eps, weight nw_q / nw_k) and interleaved-pair RoPE applied to the Q and K heads in the GEMM
+ * epilogue (V passes through) — diffusers to_q/to_k/to_v + norm_q/norm_k + apply_rotary_emb in one
+ * kernel.  cos/sin: fp32 [S,128]; token `row` of every batch item uses table row
+ * rope_row0 + row (the image stream of a double block starts at S_txt).  Same rounding chain as
+ * b2f_rmsnorm_rope. */
+int b2f_gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_batch_stride, const void* W,
+                           int64_t ldw, const void* bias, void* out, int64_t ldc,
+                           int64_t out_batch_stride, int batch, int M, int d_model, int K,
+                           const void* nw_q, const void* nw_k, const float* cos, const float* sin,
+                           int rope_row0, float eps, b2f_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * AdaLN modulate (HBM-bound): out = LayerNorm(x; eps, no affine) * (1 + scale[b]) + shift[b].

@@ -95,3 +95,27 @@ def test_gemm_gate_resid_batched_views():
     assert _rel_l2(h, ref) < 6e-3
     # rows outside the slice untouched
     assert torch.equal(ha[:, :S0], h_before[:, :S0]) and torch.equal(ha[:, S0 + S:], h_before[:, S0 + S:])
+
+
+@pytest.mark.parametrize("B,M,H,K,row0", [(1, 200, 2, 256, 0), (2, 300, 3, 384, 40), (1, 8736, 24, 3072, 0)])
+def test_gemm_qkv_norm_rope_equals_unfused_path(B, M, H, K, row0):
+    """Fused epilogue == GEMM(bias) followed by the standalone rmsnorm_rope kernel (same rounding chain)."""
+    from gpt_image_edit_b200 import ops
+
+    d = H * 128
+    g = torch.Generator(device="cuda").manual_seed(H)
+    x = torch.randn(B, M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(3 * d, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(3 * d, device="cuda", generator=g).bfloat16()
+    wq, wk = ((1 + 0.1 * torch.randn(128, device="cuda", generator=g)).bfloat16() for _ in range(2))
+    S = row0 + M
+    ids = torch.zeros(S, 3, device="cuda")
+    ids[:, 1] = torch.arange(S, device="cuda") % 97
+    ids[:, 2] = torch.arange(S, device="cuda") % 53
+    cos, sin = ops.rope_tables(ids)
+    fused = ops.linear_qkv_norm_rope(x, w, b, wq, wk, cos, sin, rope_row0=row0)
+    ref = ops.linear(x, w, b)
+    ops.rmsnorm_rope_(ref, H, wq, wk, cos[row0:].contiguous(), sin[row0:].contiguous())
+    mism = (fused != ref).float().mean().item()
+    assert mism < 1e-3, f"{mism:.4%} elements differ"
+    assert torch.equal(fused[..., 2 * d:], ref[..., 2 * d:])      # V untouched by norm/rope
