@@ -68,9 +68,24 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
 }
 
-// POLY: every POLY-th exponential goes to the polynomial (0 = never).
+// Packed pair version (FFMA2 / FADD2): 2^x0, 2^x1 without MUFU in 11 issue slots.
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& r0, float& r1) {
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  float t0, t1, n0, n1, f0, f1;
+  fadd2(t0, t1, x0, x1, 12582912.0f, 12582912.0f);
+  fadd2(n0, n1, t0, t1, -12582912.0f, -12582912.0f);
+  fadd2(f0, f1, x0, x1, -n0, -n1);
+  ffma2(r0, r1, f0, f1, 0.05592203512787819f, 0.05592203512787819f, 0.24264007806777954f, 0.24264007806777954f);
+  ffma2(r0, r1, r0, r1, f0, f1, 0.6931210160255432f, 0.6931210160255432f);
+  ffma2(r0, r1, r0, r1, f0, f1, 0.9999244809150696f, 0.9999244809150696f);
+  r0 = __int_as_float(__float_as_int(r0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(r1) + (__float_as_int(t1) << 23));
+}
+
+// POLY: one pair of exponentials in every POLY pairs goes to the polynomial (0 = never).
 // TURNS: the two softmax warpgroups take turns on the exp section (forces anti-phase).
-template <int POLY, bool TURNS>
+template <int POLY, bool TURNS, int ABL = 0>   // ABL: timing ablations (wrong results), see attention_fwd
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -152,89 +167,98 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0);  // B = K tile, K-major
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 1);   // B = V tile, MN-major
-      const uint32_t q_addr = smem_u32(q_smem);
-      const uint32_t kv_addr = smem_u32(kv_smem);
-      int slot = 0;
-      uint32_t phase = 0;
-      auto issue_qk = [&](int t, uint32_t k_addr) {
-        const uint32_t d = tmem_base + uint32_t(t * 128);
-        const uint32_t qa = q_addr + t * TILE_BYTES;
+    // ---------------------------------------------------------------- MMA issuer
+    // The WHOLE warp runs this loop (waits, descriptor arithmetic) so that the address math stays on
+    // the uniform datapath; only the tcgen05.mma / tcgen05.commit instructions are predicated to one
+    // lane.  (With the loop nested under `if (lane == 0)` every descriptor went through R2UR moves and
+    // the issue thread, not the tensor pipe, paced the kernel: ncu showed it busy ~75 % of the time.)
+    constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0);  // B = K tile, K-major
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 1);   // B = V tile, MN-major
+    const uint32_t q_addr = smem_u32(q_smem);
+    const uint32_t kv_addr = smem_u32(kv_smem);
+    // descriptor of byte offset 0 of each buffer; every MMA operand is "base + constant" (one uniform
+    // 64-bit add on the 14-bit address field, which cannot carry out for addresses < 256 KB)
+    const uint64_t dq_base = make_sdesc_sw128(q_addr, 16, 1024);
+    const uint64_t dk_base = make_sdesc_sw128(kv_addr, 16, 1024);
+    const uint64_t dv_base = make_sdesc_sw128(kv_addr, TILE_BYTES / 2, 1024);
+    int slot = 0;
+    uint32_t phase = 0;
+    auto issue_qk = [&](int t, int k_slot) {
+      const uint32_t d = tmem_base + uint32_t(t * 128);
+      const uint64_t qd = dq_base + uint64_t((t * TILE_BYTES) >> 4);
+      const uint64_t kd = dk_base + uint64_t((k_slot * TILE_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
-          // dh 0..63 live in the first 16 KB sub-tile, 64..127 in the second
-          const uint32_t off = (k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32;
-          umma_ss(d, make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(k_addr + off, 16, 1024),
-                  idesc_qk, k != 0 ? 1u : 0u);
+          const uint64_t off = uint64_t(((k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32) >> 4);
+          umma_ss(d, qd + off, kd + off, idesc_qk, k != 0 ? 1u : 0u);
         }
-      };
-      auto issue_pv = [&](int t, uint32_t v_addr, bool first) {
-        const uint32_t d = tmem_base + 256 + uint32_t(t * 128);
-        const uint32_t pa = tmem_base + uint32_t(t * 128);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int t, int v_slot, bool first) {
+      const uint32_t d = tmem_base + 256 + uint32_t(t * 128);
+      const uint32_t pa = tmem_base + uint32_t(t * 128);
+      const uint64_t vd = dv_base + uint64_t((v_slot * TILE_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // 16 kv rows per step = 2 KB; N (dh) halves are 16 KB apart (LBO), 8-row groups 1 KB (SBO)
-          umma_ts(d, pa + k * 8, make_sdesc_sw128(v_addr + k * 2048, TILE_BYTES / 2, 1024),
-                  idesc_pv, (first && k == 0) ? 0u : 1u);
-        }
-      };
-      auto advance = [&]() {
-        if (++slot == KV_SLOTS) {
-          slot = 0;
-          phase ^= 1;
-        }
-      };
-      mbar_wait(q_full, 0);
-      // prologue: S_t = Q_t K_0^T for both tiles
-      mbar_wait(&kv_full[slot], phase);
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_ts(d, pa + k * 8, vd + uint64_t((k * 2048) >> 4), idesc_pv, (first && k == 0) ? 0u : 1u);
+      }
+      __syncwarp();
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+    };
+    auto advance = [&]() {
+      if (++slot == KV_SLOTS) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    mbar_wait(q_full, 0);
+    // prologue: S_t = Q_t K_0^T for both tiles
+    mbar_wait(&kv_full[slot], phase);
+    tc_fence_after();
+    issue_qk(0, slot);
+    commit(&s_full[0]);
+    issue_qk(1, slot);
+    commit(&s_full[1]);
+    commit(&kv_empty[slot]);
+    advance();
+    for (int j = 0; j < n_kv; ++j) {
+      const int v_slot = slot;
+      const uint32_t v_phase = phase;
+      advance();
+      const int k_slot = slot;  // K_{j+1} (if any)
+      const uint32_t k_phase = phase;
+      const bool more = (j + 1 < n_kv);
+      if (more) advance();
+      mbar_wait(&kv_full[v_slot], v_phase);
+      // tile 0
+      mbar_wait(&p_full[0], j & 1);
       tc_fence_after();
-      {
-        const uint32_t k_addr = kv_addr + slot * TILE_BYTES;
-        issue_qk(0, k_addr);
-        umma_commit(&s_full[0]);
-        issue_qk(1, k_addr);
-        umma_commit(&s_full[1]);
-        umma_commit(&kv_empty[slot]);
-        advance();
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const int v_slot = slot;
-        const uint32_t v_phase = phase;
-        advance();
-        const int k_slot = slot;  // K_{j+1} (if any)
-        const uint32_t k_phase = phase;
-        const bool more = (j + 1 < n_kv);
-        if (more) advance();
-        mbar_wait(&kv_full[v_slot], v_phase);
-        const uint32_t v_addr = kv_addr + v_slot * TILE_BYTES;
-        const uint32_t k_addr = kv_addr + k_slot * TILE_BYTES;
-        // tile 0
-        mbar_wait(&p_full[0], j & 1);
+      issue_pv(0, v_slot, j == 0);
+      if (more) {
+        mbar_wait(&kv_full[k_slot], k_phase);
         tc_fence_after();
-        issue_pv(0, v_addr, j == 0);
-        if (more) {
-          mbar_wait(&kv_full[k_slot], k_phase);
-          tc_fence_after();
-          issue_qk(0, k_addr);
-          umma_commit(&s_full[0]);
-        }
-        // tile 1
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, v_addr, j == 0);
-        umma_commit(&kv_empty[v_slot]);
-        if (more) {
-          issue_qk(1, k_addr);
-          umma_commit(&s_full[1]);
-          umma_commit(&kv_empty[k_slot]);
-        }
+        issue_qk(0, k_slot);
+        commit(&s_full[0]);
       }
-      umma_commit(&o_done[0]);
-      umma_commit(&o_done[1]);
+      // tile 1
+      mbar_wait(&p_full[1], j & 1);
+      tc_fence_after();
+      issue_pv(1, v_slot, j == 0);
+      commit(&kv_empty[v_slot]);
+      if (more) {
+        issue_qk(1, k_slot);
+        commit(&s_full[1]);
+        commit(&kv_empty[k_slot]);
+      }
     }
+    commit(&o_done[0]);
+    commit(&o_done[1]);
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
     const int t = (warp - 2) >> 2;
@@ -277,7 +301,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           mx4[i] = fmax3(mx4[i], __uint_as_float(sr[c + 2 * i]), __uint_as_float(sr[c + 2 * i + 1]));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if (ABL & 2) mx = __uint_as_float(sr[lane & 127]) * 0.f + 20.f;   // ablation: no row-max pass
       const float m_new = fmaxf(m, mx * p.scale_log2);
       // lazy rescale: keep the stale max unless it grew by more than 2^8 (P stays < 256)
       const bool grow = (m_new - m) > 8.0f;
@@ -294,14 +319,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           float x0, x1;
           ffma2(x0, x1, __uint_as_float(sr[half * 64 + 2 * c]), __uint_as_float(sr[half * 64 + 2 * c + 1]),
                 p.scale_log2, p.scale_log2, neg_m, neg_m);
-          constexpr int PH = POLY / 2 ? POLY / 2 : 1;
-          const float p0 = ex2(x0);
-          const float p1 = (POLY && (c % PH) == PH - 1) ? ex2_poly(x1) : ex2(x1);
+          float p0, p1;
+          if (POLY && (c % (POLY ? POLY : 1)) == (POLY ? POLY : 1) - 1) {
+            ex2_poly2(x0, x1, p0, p1);
+          } else if (ABL & 1) {
+            p0 = x0 * 1e-3f;   // ablation: no MUFU
+            p1 = x1 * 1e-3f;
+          } else {
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+          }
           const int a = (c & 1) * 2;
           fadd2(sum4[a], sum4[a + 1], sum4[a], sum4[a + 1], p0, p1);
           pk[c] = pack_bf16x2(p0, p1);
         }
-        B2F_TMEM_ST_X32(s_tmem + half * 32, pk);
+        if (!(ABL & 4)) B2F_TMEM_ST_X32(s_tmem + half * 32, pk);
       }
       if (TURNS) named_bar_arrive(1 + (t ^ 1), 256);
       l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
@@ -651,11 +683,17 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
     const char* v = getenv("B2F_ATTN_VARIANT");
     const int variant = v ? atoi(v) : B2F_ATTN_DEFAULT_VARIANT;
     switch (variant) {
-      case 1: kernel = attn_fwd_kernel<4, false>; break;
-      case 2: kernel = attn_fwd_kernel<2, false>; break;
+      case 1: kernel = attn_fwd_kernel<4, false>; break;   // 25 % of the exponentials on the FMA pipe
+      case 2: kernel = attn_fwd_kernel<2, false>; break;   // 50 %
       case 3: kernel = attn_fwd_kernel<0, true>; break;
       case 4: kernel = attn_fwd_kernel<4, true>; break;
-      case 5: kernel = attn_fwd_kernel<2, true>; break;
+      case 5: kernel = attn_fwd_kernel<3, false>; break;   // 33 %
+      case 6: kernel = attn_fwd_kernel<8, false>; break;   // 12.5 %
+      case 21: kernel = attn_fwd_kernel<0, false, 1>; break;  // ablations for timing analysis only
+      case 22: kernel = attn_fwd_kernel<0, false, 2>; break;
+      case 23: kernel = attn_fwd_kernel<0, false, 3>; break;
+      case 24: kernel = attn_fwd_kernel<0, false, 7>; break;
+      case 25: kernel = attn_fwd_kernel<0, true, 3>; break;
       case 10: kernel = attn_fwd_kernel_v2; break;
       default: kernel = attn_fwd_kernel<0, false>; break;
     }

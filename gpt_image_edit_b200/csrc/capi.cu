@@ -12,7 +12,8 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
 int gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
                        const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M,
                        int d_model, int K, const void* nw_q, const void* nw_k, const float* cos,
-                       const float* sin, int rope_row0, float eps, cudaStream_t stream);
+                       const float* sin, int rope_row0, float eps, int n_extra, void* out_extra,
+                       int64_t ld_extra, int64_t bs_extra, int epi_extra, cudaStream_t stream);
 int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
                 const void* shift, int64_t mod_ld, void* out, int64_t ldo, int64_t out_batch_stride,
                 int batch, int rows, int D, float eps, cudaStream_t stream);
@@ -106,10 +107,11 @@ int b2f_gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_batch_stride, c
                            int64_t ldw, const void* bias, void* out, int64_t ldc,
                            int64_t out_batch_stride, int batch, int M, int d_model, int K,
                            const void* nw_q, const void* nw_k, const float* cos, const float* sin,
-                           int rope_row0, float eps, b2f_stream_t stream) {
+                           int rope_row0, float eps, int n_extra, void* out_extra, int64_t ld_extra,
+                           int64_t extra_batch_stride, int epi_extra, b2f_stream_t stream) {
   return b2f::gemm_qkv_norm_rope(A, lda, a_batch_stride, W, ldw, bias, out, ldc, out_batch_stride, batch,
-                                 M, d_model, K, nw_q, nw_k, cos, sin, rope_row0, eps,
-                                 static_cast<cudaStream_t>(stream));
+                                 M, d_model, K, nw_q, nw_k, cos, sin, rope_row0, eps, n_extra, out_extra,
+                                 ld_extra, extra_batch_stride, epi_extra, static_cast<cudaStream_t>(stream));
 }
 
 int b2f_ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,

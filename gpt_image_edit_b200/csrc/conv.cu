@@ -132,38 +132,38 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0);
+    const uint64_t d_base = make_sdesc_sw128(smem_u32(smem), 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        const uint64_t da = d_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
+        const uint64_t db = da + uint64_t(Cfg::A_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_sdesc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-            const uint64_t db = make_sdesc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_ss(d_tmem, da + uint64_t((k * UMMA_K * 2) >> 4), db + uint64_t((k * UMMA_K * 2) >> 4), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
-          if (++stage == Cfg::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
+        __syncwarp();
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
       }
     }
   } else {

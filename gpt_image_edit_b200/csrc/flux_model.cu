@@ -28,7 +28,8 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
 int gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
                        const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M,
                        int d_model, int K, const void* nw_q, const void* nw_k, const float* cos,
-                       const float* sin, int rope_row0, float eps, cudaStream_t stream);
+                       const float* sin, int rope_row0, float eps, int n_extra, void* out_extra,
+                       int64_t ld_extra, int64_t bs_extra, int epi_extra, cudaStream_t stream);
 int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                   int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
                   int head_dim, float scale, int causal, cudaStream_t stream);
@@ -334,9 +335,10 @@ int b2f_flux_forward(b2f_flux* h, const void* hidden, const void* enc, const voi
       // QKV projections with per-head RMSNorm + RoPE fused into the GEMM epilogue; both streams write
       // straight into the joint [txt; img] qkv buffer
       RUN(gemm_qkv_norm_rope(xn_img, d, h_bs, w.qkv.w, d, w.qkv.b, qkv_img, 3 * d, qkv_bs, B, S_img, (int)d,
-                             (int)d, w.norm_q, w.norm_k, c->rope_cos, c->rope_sin, S_txt, eps, st));
+                             (int)d, w.norm_q, w.norm_k, c->rope_cos, c->rope_sin, S_txt, eps, 0, nullptr, 0, 0, 0, st));
       RUN(gemm_qkv_norm_rope(xn_txt, d, h_bs, w.add_qkv.w, d, w.add_qkv.b, qkv_txt, 3 * d, qkv_bs, B, S_txt,
-                             (int)d, (int)d, w.norm_added_q, w.norm_added_k, c->rope_cos, c->rope_sin, 0, eps, st));
+                             (int)d, (int)d, w.norm_added_q, w.norm_added_k, c->rope_cos, c->rope_sin, 0, eps, 0,
+                             nullptr, 0, 0, 0, st));
       RUN(attention_fwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, cat, 5 * d, B, H, H, S, S,
                         g.head_dim, scale, 0, st));
       RUN(gemm_bf16(cat_img, 5 * d, cat_bs, w.to_out.w, d, w.to_out.b, h_img, d, h_bs, B, S_img,
@@ -361,11 +363,11 @@ int b2f_flux_forward(b2f_flux* h, const void* hidden, const void* enc, const voi
       // mod columns: [shift, scale, gate]
       const bf16_t* ms = modp + (int64_t)g.num_double * 12 * d + (int64_t)si * 3 * d;
       RUN(ln_modulate(hb, d, h_bs, ms + d, ms, mod_ld, xn, d, h_bs, B, S, (int)d, eps, st));
+      // ONE launch for [to_q;to_k;to_v;proj_mlp] (N = 7d): Q/K get RMSNorm+RoPE, V passes through into
+      // qkv, the MLP columns are GELU'd straight into cat[:, :, d:5d]
       RUN(gemm_qkv_norm_rope(xn, d, h_bs, w.qkv_mlp.w, d, w.qkv_mlp.b, qkv, 3 * d, qkv_bs, B, S, (int)d, (int)d,
-                             w.norm_q, w.norm_k, c->rope_cos, c->rope_sin, 0, eps, st));
-      RUN(gemm_bf16(xn, d, h_bs, w.qkv_mlp.w + 3 * d * d, d, w.qkv_mlp.b + 3 * d, cat + d, 5 * d,
-                    cat_bs, B, S, (int)(4 * d), (int)d, B2F_EPI_GELU_TANH, nullptr, 0, 0, nullptr, 0,
-                    st));
+                             w.norm_q, w.norm_k, c->rope_cos, c->rope_sin, 0, eps, (int)(4 * d), cat + d, 5 * d,
+                             cat_bs, B2F_EPI_GELU_TANH, st));
       RUN(attention_fwd(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, cat, 5 * d, B, H, H, S, S,
                         g.head_dim, scale, 0, st));
       RUN(gemm_bf16(cat, 5 * d, cat_bs, w.proj_out.w, 5 * d, w.proj_out.b, hb, d, h_bs, B, S, (int)d,

@@ -50,6 +50,11 @@ struct GemmParams {
   const float* rope_sin;
   int rope_row0, d_model;
   float norm_eps;
+  // optional second output block: columns [split_n, N) go to out2 (own pitch) with epilogue epi2
+  // (single-stream block: [Q|K|V | proj_mlp] in one launch, the MLP part GELU'd into the cat buffer)
+  int split_n, epi2;
+  __nv_bfloat16* out2;
+  long long ldc2, out2_bs;
 };
 
 template <int BN>
@@ -83,7 +88,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 
 // Epilogue for 32 accumulator columns of one output row: bias / activation / gate / residual with the
 // bf16 rounding points of the torch-eager chain, then 16-byte stores.
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int n0,
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int epi, const uint32_t (&acc)[32], int n0,
                                                __nv_bfloat16* out_row, const __nv_bfloat16* res_row,
                                                const __nv_bfloat16* gate_row) {
 #pragma unroll
@@ -103,19 +108,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         v[2 * j + 1] += b2.y;
       }
     }
-    if (p.epi == B2F_EPI_GELU_TANH) {
+    if (epi == B2F_EPI_GELU_TANH) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(bf16r(v[j]));
-    } else if (p.epi == B2F_EPI_GELU_ERF) {
+    } else if (epi == B2F_EPI_GELU_ERF) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float x = bf16r(v[j]);
         v[j] = 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
       }
-    } else if (p.epi == B2F_EPI_SILU) {
+    } else if (epi == B2F_EPI_SILU) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = silu_f(bf16r(v[j]));
-    } else if (p.epi == B2F_EPI_GATE_RESID) {
+    } else if (epi == B2F_EPI_GATE_RESID) {
       const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
       const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
       const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
@@ -128,7 +133,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         v[2 * j + 1] = r2.y + bf16r(g2.y * bf16r(v[2 * j + 1]));
       }
     }
-    else if (p.epi == B2F_EPI_RESID) {
+    else if (epi == B2F_EPI_RESID) {
       const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
       const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
 #pragma unroll
@@ -206,7 +211,8 @@ template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int as, int q, int lane,
                                               int n_blk, bool row_ok, long long row, __nv_bfloat16* out_row,
                                               const __nv_bfloat16* res_row, const __nv_bfloat16* gate_row,
-                                              uint64_t* tmem_empty_bar, bool arrive_cta0) {
+                                              uint64_t* tmem_empty_bar, bool arrive_cta0,
+                                              __nv_bfloat16* out_row2 = nullptr) {
   auto release = [&]() {
     // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
     tc_fence_before();
@@ -232,16 +238,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       if (h0 + 128 == BN) release();
       const int n_head0 = n_blk * BN + h0;
       if (!row_ok || n_head0 >= p.N) continue;
-      const int which = n_head0 / p.d_model;  // 0 = Q, 1 = K, 2 = V
+      const int which = n_head0 / p.d_model;  // 0 = Q, 1 = K, 2 = V, >= 3: second output block
       if (which < 2) {
         epilogue_head_norm_rope(p, a, n_head0, row, out_row, which == 1);
       } else {
+        const bool second = p.split_n > 0 && n_head0 >= p.split_n;
+        __nv_bfloat16* orow = second ? out_row2 : out_row;
+        const int epi = second ? p.epi2 : B2F_EPI_BIAS;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t acc[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = a[cc * 32 + j];
-          epilogue_chunk(p, acc, n_head0 + cc * 32, out_row, res_row, gate_row);
+          epilogue_chunk(p, epi, acc, n_head0 + cc * 32, orow, res_row, gate_row);
         }
       }
     }
@@ -257,7 +266,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     if (c0 + 32 == BN) release();
     const int n0 = n_blk * BN + c0;
     if (!row_ok || n0 >= p.N) continue;
-    epilogue_chunk(p, acc, n0, out_row, res_row, gate_row);
+    epilogue_chunk(p, p.epi, acc, n0, out_row, res_row, gate_row);
   }
 }
 
@@ -329,38 +338,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
+    // whole warp runs the loop (uniform-datapath address math); one elected lane issues the MMAs
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0);
+    const uint64_t d_base = make_sdesc_sw128(smem_u32(smem), 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+        const uint64_t da = d_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
+        const uint64_t db = da + uint64_t(Cfg::A_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_sdesc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-            const uint64_t db = make_sdesc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_ss(d_tmem, da + uint64_t((k * UMMA_K * 2) >> 4), db + uint64_t((k * UMMA_K * 2) >> 4), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
-          if (++stage == Cfg::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
+        __syncwarp();
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
       }
     }
   } else {
@@ -380,7 +390,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
       __nv_bfloat16* out_row = p.out + bidx * p.out_bs + row * p.ldc;
       const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
-      epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], false);
+      __nv_bfloat16* out_row2 = p.out2 ? p.out2 + bidx * p.out2_bs + row * p.ldc2 - p.split_n : nullptr;
+      epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], false,
+                        out_row2);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -519,8 +531,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0);
+      const uint64_t d_base = make_sdesc_sw128(smem_u32(smem), 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -532,16 +545,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint64_t da = d_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t db = da + uint64_t(Cfg::A_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_sdesc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-            const uint64_t db = make_sdesc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-            umma_ss_2cta(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_ss_2cta(d_tmem, da + uint64_t((k * UMMA_K * 2) >> 4), db + uint64_t((k * UMMA_K * 2) >> 4),
+                           idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[as]);
           }
-          umma_commit_2cta(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[as]);
+          __syncwarp();
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -569,7 +583,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
       __nv_bfloat16* out_row = p.out + bidx * p.out_bs + row * p.ldc;
       const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
-      epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], true);
+      __nv_bfloat16* out_row2 = p.out2 ? p.out2 + bidx * p.out2_bs + row * p.ldc2 - p.split_n : nullptr;
+      epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], true,
+                        out_row2);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -617,6 +633,9 @@ struct QkvExtra {
   const float *cos, *sin;
   int rope_row0, d_model;
   float eps;
+  int n_extra, epi_extra;   // optional second output block of n_extra columns
+  void* out_extra;
+  int64_t ld_extra, bs_extra;
 };
 
 static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
@@ -634,7 +653,10 @@ static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* 
   if (epilogue < 0 || epilogue > B2F_EPI_QKV_NORM_ROPE) return B2F_ERR_INVALID;
   if (epilogue == B2F_EPI_QKV_NORM_ROPE) {
     if (!qx || !qx->nw_q || !qx->nw_k || !qx->cos || !qx->sin || qx->d_model <= 0) return B2F_ERR_INVALID;
-    if (N != 3 * qx->d_model || (qx->d_model % 128)) return B2F_ERR_UNSUPPORTED;
+    if (N != 3 * qx->d_model + qx->n_extra || (qx->d_model % 128) || (qx->n_extra & 7)) return B2F_ERR_UNSUPPORTED;
+    if (qx->n_extra && (!qx->out_extra || (qx->ld_extra & 7) || (qx->bs_extra & 7) ||
+                        (reinterpret_cast<uintptr_t>(qx->out_extra) & 15)))
+      return B2F_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(qx->nw_q) | reinterpret_cast<uintptr_t>(qx->nw_k) |
          reinterpret_cast<uintptr_t>(qx->cos) | reinterpret_cast<uintptr_t>(qx->sin)) & 15)
       return B2F_ERR_ALIGN;
@@ -668,6 +690,13 @@ static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* 
     p.rope_row0 = qx->rope_row0;
     p.d_model = qx->d_model;
     p.norm_eps = qx->eps;
+    if (qx->n_extra) {
+      p.split_n = 3 * qx->d_model;
+      p.epi2 = qx->epi_extra;
+      p.out2 = static_cast<__nv_bfloat16*>(qx->out_extra);
+      p.ldc2 = qx->ld_extra;
+      p.out2_bs = qx->bs_extra;
+    }
   }
 
   const long long num_m = (long long)batch * ((M + BLOCK_M - 1) / BLOCK_M);
@@ -705,9 +734,10 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
 int gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,
                        const void* bias, void* out, int64_t ldc, int64_t out_bs, int batch, int M,
                        int d_model, int K, const void* nw_q, const void* nw_k, const float* cos,
-                       const float* sin, int rope_row0, float eps, cudaStream_t stream) {
-  QkvExtra qx{nw_q, nw_k, cos, sin, rope_row0, d_model, eps};
-  return gemm_bf16_impl(A, lda, a_bs, W, ldw, bias, out, ldc, out_bs, batch, M, 3 * d_model, K,
+                       const float* sin, int rope_row0, float eps, int n_extra, void* out_extra,
+                       int64_t ld_extra, int64_t bs_extra, int epi_extra, cudaStream_t stream) {
+  QkvExtra qx{nw_q, nw_k, cos, sin, rope_row0, d_model, eps, n_extra, epi_extra, out_extra, ld_extra, bs_extra};
+  return gemm_bf16_impl(A, lda, a_bs, W, ldw, bias, out, ldc, out_bs, batch, M, 3 * d_model + n_extra, K,
                         B2F_EPI_QKV_NORM_ROPE, nullptr, 0, 0, nullptr, 0, &qx, stream);
 }
 

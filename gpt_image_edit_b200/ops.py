@@ -204,19 +204,25 @@ def scatter_rows_(dst, idx, src):
     return dst
 
 
-def linear_qkv_norm_rope(x, weight, bias, wq, wk, cos, sin, *, rope_row0: int = 0, out=None, eps: float = 1e-6):
-    """[Q|K|V] = x @ weight^T + bias with per-head RMSNorm + RoPE on Q, K fused in the GEMM epilogue."""
+def linear_qkv_norm_rope(x, weight, bias, wq, wk, cos, sin, *, rope_row0: int = 0, out=None, eps: float = 1e-6,
+                         out_extra=None, epi_extra: int = EPI_BIAS):
+    """[Q|K|V] = x @ weight^T + bias with per-head RMSNorm + RoPE on Q, K fused in the GEMM epilogue.
+    With `out_extra` [.., n_extra]: weight has 3d + n_extra rows, the extra columns go there via epi_extra."""
     _req(x, "x")
     _req(weight, "weight")
     _req(cos, "cos", torch.float32)
     _req(sin, "sin", torch.float32)
     x3 = _as3(x)
     B, M, K = x3.shape
-    N = weight.shape[0]
+    n_extra = 0 if out_extra is None else out_extra.shape[-1]
+    N = weight.shape[0] - n_extra
     if out is None:
         out = torch.empty((*x.shape[:-1], N), device=x.device, dtype=torch.bfloat16)
     o3 = _as3(out)
+    e3 = None if out_extra is None else _as3(out_extra)
     check(_lib.lib.b2f_gemm_qkv_norm_rope(ptr(x3), x3.stride(1), x3.stride(0), ptr(weight), weight.stride(0), ptr(bias),
                                           ptr(o3), o3.stride(1), o3.stride(0), B, M, N // 3, K, ptr(wq), ptr(wk),
-                                          ptr(cos), ptr(sin), rope_row0, eps, stream_ptr()), "b2f_gemm_qkv_norm_rope")
+                                          ptr(cos), ptr(sin), rope_row0, eps, n_extra, ptr(e3),
+                                          0 if e3 is None else e3.stride(1), 0 if e3 is None else e3.stride(0),
+                                          epi_extra, stream_ptr()), "b2f_gemm_qkv_norm_rope")
     return out

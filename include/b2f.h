@@ -86,12 +86,16 @@ int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void
  * epilogue (V passes through) — diffusers to_q/to_k/to_v + norm_q/norm_k + apply_rotary_emb in one
  * kernel.  cos/sin: fp32 [S,128]; token `row` of every batch item uses table row
  * rope_row0 + row (the image stream of a double block starts at S_txt).  Same rounding chain as
- * b2f_rmsnorm_rope. */
+ * b2f_rmsnorm_rope.  Optional second output block: when n_extra > 0, W has 3*d_model + n_extra rows and
+ * the extra columns are written to out_extra (pitch ld_extra) through epilogue epi_extra — the
+ * single-stream block's [to_q;to_k;to_v;proj_mlp] runs as ONE launch, its GELU'd MLP part landing in
+ * the [attn|mlp] buffer. */
 int b2f_gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_batch_stride, const void* W,
                            int64_t ldw, const void* bias, void* out, int64_t ldc,
                            int64_t out_batch_stride, int batch, int M, int d_model, int K,
                            const void* nw_q, const void* nw_k, const float* cos, const float* sin,
-                           int rope_row0, float eps, b2f_stream_t stream);
+                           int rope_row0, float eps, int n_extra, void* out_extra, int64_t ld_extra,
+                           int64_t extra_batch_stride, int epi_extra, b2f_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * AdaLN modulate (HBM-bound): out = LayerNorm(x; eps, no affine) * (1 + scale[b]) + shift[b].
