@@ -43,6 +43,29 @@ def flops_per_forward(S_img: int, S_txt: int, n_double=N_DOUBLE, n_single=N_SING
     return lin + attn + emb + ada
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the dominant-kernel launch captured with `ncu --set full`
+    (profiles/r01_ncu_gemm_summary.json, produced by scripts/ncu_summary.py); None if absent."""
+    f = ROOT / "profiles" / "r01_ncu_gemm_summary.json"
+    if not f.exists():
+        return None
+    best = None
+    for rec in json.loads(f.read_text()):
+        try:
+            rd, wr = rec["dram__bytes_read.sum"].split(), rec["dram__bytes_write.sum"].split()
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]]
+            dur = float(rec["gpu__time_duration.sum"].split()[0])
+        except Exception:
+            continue
+        if best is None or dur > best[1]:
+            best = (tot, dur, rec.get("kernel", ""))
+    if best is None:
+        return None
+    return {"dram_bytes_per_launch": best[0], "launch_us_under_ncu": best[1], "kernel": best[2],
+            "note": "largest captured launch: QKV projection 8192x9216x3072 (algorithmic 258 MB)"}
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -293,7 +316,7 @@ def main():
             "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_sustained"],
             "frac_of_burst_peak": achieved / pk["tensor_burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
             "avg_launch_ms": pd["ms"] / max(pd["launches"], 1), "launches": pd["launches"],
-            "algorithmic_tflop_per_launch": pd["flops"] / max(pd["launches"], 1) / 1e12, "traffic": None,
+            "algorithmic_tflop_per_launch": pd["flops"] / max(pd["launches"], 1) / 1e12, "traffic": ncu_traffic(),
             "share_of_step": pd["ms"] / ms_total,
             "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                             "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,

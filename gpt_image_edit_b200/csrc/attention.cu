@@ -20,7 +20,7 @@
 #include <cstdlib>
 
 #ifndef B2F_ATTN_DEFAULT_VARIANT
-#define B2F_ATTN_DEFAULT_VARIANT 0
+#define B2F_ATTN_DEFAULT_VARIANT 1
 #endif
 
 #include "host_common.h"
@@ -99,8 +99,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* kv_full = bars + 1;       // KV_SLOTS
   uint64_t* kv_empty = kv_full + KV_SLOTS;
   uint64_t* s_full = kv_empty + KV_SLOTS;  // 2
-  uint64_t* p_full = s_full + 2;           // 2
-  uint64_t* o_done = p_full + 2;           // 2
+  uint64_t* p_full = s_full + 2;           // [tile][half] = 4: P columns [0,64) and [64,128) handed over separately
+  uint64_t* o_done = p_full + 4;           // 2
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -127,9 +127,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
       mbar_init(&o_done[i], 1);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);  // one elected arrive per softmax warp
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -196,13 +196,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       __syncwarp();
     };
-    auto issue_pv = [&](int t, int v_slot, bool first) {
+    // O_t += P_t[:, 64*hf : 64*hf+64] · V[64*hf : 64*hf+64, :]  (4 k-steps of 16 kv rows)
+    auto issue_pv = [&](int t, int v_slot, int hf, bool first) {
       const uint32_t d = tmem_base + 256 + uint32_t(t * 128);
-      const uint32_t pa = tmem_base + uint32_t(t * 128);
-      const uint64_t vd = dv_base + uint64_t((v_slot * TILE_BYTES) >> 4);
+      const uint32_t pa = tmem_base + uint32_t(t * 128 + hf * 32);
+      const uint64_t vd = dv_base + uint64_t((v_slot * TILE_BYTES + hf * 8192) >> 4);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
+        for (int k = 0; k < 4; ++k)
           umma_ts(d, pa + k * 8, vd + uint64_t((k * 2048) >> 4), idesc_pv, (first && k == 0) ? 0u : 1u);
       }
       __syncwarp();
@@ -236,10 +237,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool more = (j + 1 < n_kv);
       if (more) advance();
       mbar_wait(&kv_full[v_slot], v_phase);
-      // tile 0
+      // tile 0: the first half of P·V starts while the warpgroup still exponentiates the second half
       mbar_wait(&p_full[0], j & 1);
       tc_fence_after();
-      issue_pv(0, v_slot, j == 0);
+      issue_pv(0, v_slot, 0, j == 0);
+      mbar_wait(&p_full[1], j & 1);
+      tc_fence_after();
+      issue_pv(0, v_slot, 1, false);
       if (more) {
         mbar_wait(&kv_full[k_slot], k_phase);
         tc_fence_after();
@@ -247,9 +251,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         commit(&s_full[0]);
       }
       // tile 1
-      mbar_wait(&p_full[1], j & 1);
+      mbar_wait(&p_full[2], j & 1);
       tc_fence_after();
-      issue_pv(1, v_slot, j == 0);
+      issue_pv(1, v_slot, 0, j == 0);
+      mbar_wait(&p_full[3], j & 1);
+      tc_fence_after();
+      issue_pv(1, v_slot, 1, false);
       commit(&kv_empty[v_slot]);
       if (more) {
         issue_qk(1, k_slot);
@@ -301,14 +308,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           mx4[i] = fmax3(mx4[i], __uint_as_float(sr[c + 2 * i]), __uint_as_float(sr[c + 2 * i + 1]));
-      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      if (ABL & 2) mx = __uint_as_float(sr[lane & 127]) * 0.f + 20.f;   // ablation: no row-max pass
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m, mx * p.scale_log2);
       // lazy rescale: keep the stale max unless it grew by more than 2^8 (P stays < 256)
       const bool grow = (m_new - m) > 8.0f;
       const float m_use = grow ? m_new : m;
       const float alpha = grow ? ex2(m - m_use) : 1.0f;
       const float neg_m = (m_use == -INFINITY) ? 0.f : -m_use;  // fully masked row (causal tail)
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        // Rare path, BEFORE any P of this block is published: S_t(j) being ready proves P_t·V_{j-1}
+        // completed and P_t·V_j cannot start before the arrives below, so O_t is quiescent here.
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t o[32];
+          B2F_TMEM_LD_X32(o_tmem + c0, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          B2F_TMEM_ST_X32(o_tmem + c0, o);
+        }
+      }
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};   // two packed (FADD2) accumulator pairs
       if (TURNS) named_bar_sync(1 + t, 256);
 #pragma unroll
@@ -333,26 +352,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           fadd2(sum4[a], sum4[a + 1], sum4[a], sum4[a + 1], p0, p1);
           pk[c] = pack_bf16x2(p0, p1);
         }
-        if (!(ABL & 4)) B2F_TMEM_ST_X32(s_tmem + half * 32, pk);
+        B2F_TMEM_ST_X32(s_tmem + half * 32, pk);
+        // publish this half of P (and, with the first half, the rescaled O): one arrive per warp
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t * 2 + half]);
       }
       if (TURNS) named_bar_arrive(1 + (t ^ 1), 256);
       l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       m = m_use;
-      if (j > 0 && __any_sync(0xffffffffu, grow)) {
-        // S_t(j) being ready proves P_t·V_{j-1} completed, so O_t is stable here
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t o[32];
-          B2F_TMEM_LD_X32(o_tmem + c0, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-          B2F_TMEM_ST_X32(o_tmem + c0, o);
-        }
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
     }
     // ---------------------------------------------------------------- epilogue: O / l -> bf16
     mbar_wait(&o_done[t], 0);
@@ -690,10 +699,7 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
       case 5: kernel = attn_fwd_kernel<3, false>; break;   // 33 %
       case 6: kernel = attn_fwd_kernel<8, false>; break;   // 12.5 %
       case 21: kernel = attn_fwd_kernel<0, false, 1>; break;  // ablations for timing analysis only
-      case 22: kernel = attn_fwd_kernel<0, false, 2>; break;
-      case 23: kernel = attn_fwd_kernel<0, false, 3>; break;
-      case 24: kernel = attn_fwd_kernel<0, false, 7>; break;
-      case 25: kernel = attn_fwd_kernel<0, true, 3>; break;
+
       case 10: kernel = attn_fwd_kernel_v2; break;
       default: kernel = attn_fwd_kernel<0, false>; break;
     }
