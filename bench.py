@@ -176,7 +176,9 @@ def workload_config(args, world):
             "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world,
             "parallelism": f"batch-sharded replicas x{world} (weights broadcast once over NCCL)",
             "l2": "inputs larger than L2 (23.8 GB of weights stream every forward)",
-            "conditioning": "prompt_embeds/pooled are synthetic inputs (Qwen2.5-VL/T5/CLIP encoders not in the timed region)"}
+            "conditioning": ("synthetic prompt_embeds (no encoders in the timed region)" if getattr(args, "no_conditioning", False) else
+                             "Qwen2.5-VL-7B prefill (ViT 448x448 + 28-layer decoder, L=290) + MLP2 run inside the timed region on "
+                             "libb2f kernels; T5-XXL/CLIP-L outputs are synthetic stand-ins (SURVEY.md §8f)")}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -192,6 +194,8 @@ def main():
     ap.add_argument("--num-inference-steps", type=int, default=28)
     ap.add_argument("--layers", type=str, default=None, help="debug: 'D,S' block counts (invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-conditioning", action="store_true", help="feed synthetic prompt_embeds instead of running the "
+                    "Qwen2.5-VL prefill + MLP2 inside the timed region")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -208,6 +212,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version banner there)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     D.init_from_env("nccl", dev)
@@ -228,13 +234,35 @@ def main():
         vae = None
     pipe = FluxKontextPipeline(transformer=model, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler())
 
+    # conditioning model (Qwen2.5-VL-7B prefill + MLP2) with synthetic weights: inside the timed region
+    cond = None
+    if not args.no_conditioning:
+        from gpt_image_edit_b200.qwen2p5vl import B200Qwen2p5VL
+        from univa.models.modeling_univa_denoise_tower import DenoiseProjector
+        from univa.serve.cli import synthetic_chat_tokens
+
+        qwen = B200Qwen2p5VL(device=dev)
+        mlp2 = DenoiseProjector(3584, 4096, device=dev)
+        if rank == 0:
+            qwen.randomize_(seed=10)
+            gq = torch.Generator(device=dev).manual_seed(11)
+            for t in mlp2.state_dict().values():
+                t.copy_((torch.randn(t.shape, device=dev, generator=gq) * 0.02).to(torch.bfloat16))
+        D.broadcast_weights(qwen.storage(), src=0)
+        D.broadcast_weights(list(mlp2.state_dict().values()), src=0)
+        cond = (qwen, mlp2, synthetic_chat_tokens(256))      # L = 4 + 256 + 1 + 24 + 5 = 290 tokens (~288)
+
     B, H, W = args.batch_per_gpu, args.height, args.width
     S_img = 2 * (H // 16) * (W // 16)
     g = torch.Generator().manual_seed(1 + rank)
     src_u8 = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
     src = (src_u8.float() / 127.5 - 1.0).pin_memory()                       # [-1,1] fp32 NCHW, as cli.py:99-116
     g2 = torch.Generator().manual_seed(2 + rank)
-    pe_h = torch.randn(B, S_TXT, 4096, generator=g2).bfloat16().pin_memory()
+    L_qwen = cond[2].shape[1] if cond is not None else S_TXT - 256
+    n_t5 = S_TXT - L_qwen if cond is not None else 256
+    pe_h = torch.randn(B, S_TXT if cond is None else n_t5, 4096, generator=g2).bfloat16().pin_memory()   # T5 stand-in (§8f)
+    pix_h = torch.randn(B * 1024, 1176, generator=g2).bfloat16().pin_memory()      # 448x448 -> 1024 patches per image
+    ids_h = (cond[2].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
     pp_h = torch.randn(B, 768, generator=g2).bfloat16().pin_memory()
     noise_h = torch.stack([torch.randn(S_img // 2, 64, generator=torch.Generator().manual_seed(42 + rank * B + i))
                            for i in range(B)]).bfloat16().pin_memory()
@@ -245,9 +273,15 @@ def main():
         if from_host:
             pe, pp, noise = nb(pe_h), nb(pp_h), nb(noise_h)
             image = nb(src) if vae is not None else nb(ctx_lat_h)
+            pix, ids = (nb(pix_h), nb(ids_h)) if cond is not None else (None, None)
         else:
             pe, pp, noise = dev_in["pe"], dev_in["pp"], dev_in["noise"].clone()
             image = dev_in["image"]
+            pix, ids = dev_in["pix"], dev_in["ids"]
+        if cond is not None:
+            # VLM prefill (ViT + 28-layer decoder) -> MLP2 -> [B, L, 4096]; joined with the T5 embeddings (cli.py:210-234)
+            hidden = cond[0](ids, pixel_values=pix, image_grid_thw=[(1, 32, 32)] * B)
+            pe = torch.cat([cond[1](hidden), pe], dim=1)
         out = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pp, height=H, width=W,
                    num_inference_steps=args.num_inference_steps, guidance_scale=3.5, latents=noise,
                    max_area=H * W, _auto_resize=False, output_type="pt_raw" if vae is not None else "latent").images
@@ -258,7 +292,7 @@ def main():
         return out
 
     dev_in = dict(pe=pe_h.to(dev), pp=pp_h.to(dev), noise=noise_h.to(dev),
-                  image=(src if vae is not None else ctx_lat_h).to(dev))
+                  image=(src if vae is not None else ctx_lat_h).to(dev), pix=pix_h.to(dev), ids=ids_h.to(dev))
 
     def barrier():
         if world > 1:
@@ -333,7 +367,8 @@ def main():
         "model_frac_of_sustained_peak": f_edit / (ms_per_edit / 1e3) / 1e12 / pk["tensor_sustained"],
         "e2e": {"value": e2e, "unit": "images/s",
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in
-                                              (pe_h, pp_h, noise_h, src if vae is not None else ctx_lat_h))),
+                                              (pe_h, pp_h, noise_h, src if vae is not None else ctx_lat_h) +
+                                              ((pix_h, ids_h) if cond is not None else ()))),
                 "d2h_bytes_per_step": int(B * 3 * H * W if vae is not None else noise_h.numel() * 2)},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
     }

@@ -113,6 +113,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   int kv_len = p.Skv;
   if (p.causal) kv_len = min(p.Skv, q0 + 2 * BQ);
   const int n_kv = (kv_len + BKV - 1) / BKV;
+  // the second Q tile of the last pair may lie entirely beyond Sq (S = 8736 = 34*256 + 32): skip all of
+  // its MMAs and its softmax warpgroup instead of multiplying zero rows
+  const bool t1_active = TURNS || (q0 + BQ < p.Sq);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -224,8 +227,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     issue_qk(0, slot);
     commit(&s_full[0]);
-    issue_qk(1, slot);
-    commit(&s_full[1]);
+    if (t1_active) {
+      issue_qk(1, slot);
+      commit(&s_full[1]);
+    }
     commit(&kv_empty[slot]);
     advance();
     for (int j = 0; j < n_kv; ++j) {
@@ -251,16 +256,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         commit(&s_full[0]);
       }
       // tile 1
-      mbar_wait(&p_full[2], j & 1);
-      tc_fence_after();
-      issue_pv(1, v_slot, 0, j == 0);
-      mbar_wait(&p_full[3], j & 1);
-      tc_fence_after();
-      issue_pv(1, v_slot, 1, false);
+      if (t1_active) {
+        mbar_wait(&p_full[2], j & 1);
+        tc_fence_after();
+        issue_pv(1, v_slot, 0, j == 0);
+        mbar_wait(&p_full[3], j & 1);
+        tc_fence_after();
+        issue_pv(1, v_slot, 1, false);
+      }
       commit(&kv_empty[v_slot]);
       if (more) {
-        issue_qk(1, k_slot);
-        commit(&s_full[1]);
+        if (t1_active) {
+          issue_qk(1, k_slot);
+          commit(&s_full[1]);
+        }
         commit(&kv_empty[k_slot]);
       }
     }
@@ -276,6 +285,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t s_tmem = tmem_base + lane_addr + uint32_t(t * 128);
     const uint32_t o_tmem = tmem_base + lane_addr + 256 + uint32_t(t * 128);
     float m = -INFINITY, l = 0.f;
+    if (t == 0 || t1_active) {
     if (TURNS) {
     // named barriers 1/2 = "tile 0 / tile 1 may run its exp section"; tile 0 goes first
     if (t == 1) named_bar_arrive(1, 256);
@@ -388,6 +398,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+    }  // t == 0 || t1_active
   }
 
   tc_fence_before();

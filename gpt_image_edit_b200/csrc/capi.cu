@@ -16,7 +16,8 @@ int gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_bs, const void* W, 
                        int64_t ld_extra, int64_t bs_extra, int epi_extra, cudaStream_t stream);
 int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
                 const void* shift, int64_t mod_ld, void* out, int64_t ldo, int64_t out_batch_stride,
-                int batch, int rows, int D, float eps, cudaStream_t stream);
+                int batch, int rows, int D, float eps, int split_row, const void* scale_b,
+                const void* shift_b, cudaStream_t stream);
 int rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void* wq_a,
                  const void* wk_a, const void* wq_b, const void* wk_b, const float* cos,
                  const float* sin, int batch, int S, int H, int head_dim, int n_a, float eps,
@@ -116,10 +117,10 @@ int b2f_gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_batch_stride, c
 
 int b2f_ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
                     const void* shift, int64_t mod_ld, void* out, int64_t ldo,
-                    int64_t out_batch_stride, int batch, int rows, int D, float eps,
-                    b2f_stream_t stream) {
+                    int64_t out_batch_stride, int batch, int rows, int D, float eps, int split_row,
+                    const void* scale_b, const void* shift_b, b2f_stream_t stream) {
   return b2f::ln_modulate(x, ldx, x_batch_stride, scale, shift, mod_ld, out, ldo, out_batch_stride,
-                          batch, rows, D, eps, static_cast<cudaStream_t>(stream));
+                          batch, rows, D, eps, split_row, scale_b, shift_b, static_cast<cudaStream_t>(stream));
 }
 
 int b2f_rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void* wq_a,

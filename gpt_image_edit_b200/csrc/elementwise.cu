@@ -52,6 +52,11 @@ struct LnModParams {
   long long ldo, out_batch_stride;
   int batch, rows, D;
   float eps;
+  // rows [0, split_row) of every batch item use (scale, shift); rows >= split_row use (scale_b, shift_b)
+  // — the text and image streams of a double block in one launch.  split_row = 0: single stream.
+  int split_row;
+  const __nv_bfloat16* scale_b;
+  const __nv_bfloat16* shift_b;
 };
 
 template <int MAXC>
@@ -88,8 +93,9 @@ __global__ void __launch_bounds__(128) ln_modulate_kernel(const LnModParams p) {
     }
   }
   const float rstd = rsqrtf(warp_sum(ss) / float(p.D) + p.eps);
-  const __nv_bfloat16* sc = p.scale + (long long)b * p.mod_ld;
-  const __nv_bfloat16* sh = p.shift + (long long)b * p.mod_ld;
+  const bool second = p.split_row > 0 && r >= p.split_row;
+  const __nv_bfloat16* sc = (second ? p.scale_b : p.scale) + (long long)b * p.mod_ld;
+  const __nv_bfloat16* sh = (second ? p.shift_b : p.shift) + (long long)b * p.mod_ld;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     if (c < nchunk) {
@@ -314,7 +320,8 @@ int temb_combine(const void* t, const void* g, const void* txt, void* temb, void
 
 int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
                 const void* shift, int64_t mod_ld, void* out, int64_t ldo, int64_t out_batch_stride,
-                int batch, int rows, int D, float eps, cudaStream_t stream) {
+                int batch, int rows, int D, float eps, int split_row, const void* scale_b,
+                const void* shift_b, cudaStream_t stream) {
   if (!device_info().ok) return B2F_ERR_NODEVICE;
   if (!x || !scale || !shift || !out || batch <= 0 || rows <= 0) return B2F_ERR_INVALID;
   if (D <= 0 || (D & 255) || D > 256 * LN_MAXC) return B2F_ERR_UNSUPPORTED;
@@ -322,7 +329,9 @@ int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* 
     return B2F_ERR_ALIGN;
   LnModParams p{static_cast<const __nv_bfloat16*>(x), ldx, x_batch_stride,
                 static_cast<const __nv_bfloat16*>(scale), static_cast<const __nv_bfloat16*>(shift),
-                mod_ld, static_cast<__nv_bfloat16*>(out), ldo, out_batch_stride, batch, rows, D, eps};
+                mod_ld, static_cast<__nv_bfloat16*>(out), ldo, out_batch_stride, batch, rows, D, eps,
+                split_row, static_cast<const __nv_bfloat16*>(scale_b), static_cast<const __nv_bfloat16*>(shift_b)};
+  if (split_row > 0 && (!scale_b || !shift_b)) return B2F_ERR_INVALID;
   const long long total = (long long)batch * rows;
   const unsigned grid = (unsigned)((total + 3) / 4);
   prof_begin(KC_LNMOD, stream);

@@ -35,7 +35,8 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
                   int head_dim, float scale, int causal, cudaStream_t stream);
 int ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
                 const void* shift, int64_t mod_ld, void* out, int64_t ldo, int64_t out_batch_stride,
-                int batch, int rows, int D, float eps, cudaStream_t stream);
+                int batch, int rows, int D, float eps, int split_row, const void* scale_b,
+                const void* shift_b, cudaStream_t stream);
 int rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void* wq_a,
                  const void* wk_a, const void* wq_b, const void* wk_b, const float* cos,
                  const float* sin, int batch, int S, int H, int head_dim, int n_a, float eps,
@@ -330,8 +331,8 @@ int b2f_flux_forward(b2f_flux* h, const void* hidden, const void* enc, const voi
       // mod columns: [img: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp | txt: same]
       const bf16_t* mi = modp + (int64_t)blk * 12 * d;
       const bf16_t* mt = mi + 6 * d;
-      RUN(ln_modulate(h_img, d, h_bs, mi + d, mi, mod_ld, xn_img, d, h_bs, B, S_img, (int)d, eps, st));
-      RUN(ln_modulate(h_txt, d, h_bs, mt + d, mt, mod_ld, xn_txt, d, h_bs, B, S_txt, (int)d, eps, st));
+      // both streams in one launch over the joint buffer: text rows use the context modulation
+      RUN(ln_modulate(hb, d, h_bs, mt + d, mt, mod_ld, xn, d, h_bs, B, S, (int)d, eps, S_txt, mi + d, mi, st));
       // QKV projections with per-head RMSNorm + RoPE fused into the GEMM epilogue; both streams write
       // straight into the joint [txt; img] qkv buffer
       RUN(gemm_qkv_norm_rope(xn_img, d, h_bs, w.qkv.w, d, w.qkv.b, qkv_img, 3 * d, qkv_bs, B, S_img, (int)d,
@@ -345,10 +346,8 @@ int b2f_flux_forward(b2f_flux* h, const void* hidden, const void* enc, const voi
                     (int)d, (int)d, B2F_EPI_GATE_RESID, h_img, d, h_bs, mi + 2 * d, mod_ld, st));
       RUN(gemm_bf16(cat_txt, 5 * d, cat_bs, w.to_add_out.w, d, w.to_add_out.b, h_txt, d, h_bs, B,
                     S_txt, (int)d, (int)d, B2F_EPI_GATE_RESID, h_txt, d, h_bs, mt + 2 * d, mod_ld, st));
-      RUN(ln_modulate(h_img, d, h_bs, mi + 4 * d, mi + 3 * d, mod_ld, xn_img, d, h_bs, B, S_img,
-                      (int)d, eps, st));
-      RUN(ln_modulate(h_txt, d, h_bs, mt + 4 * d, mt + 3 * d, mod_ld, xn_txt, d, h_bs, B, S_txt,
-                      (int)d, eps, st));
+      RUN(ln_modulate(hb, d, h_bs, mt + 4 * d, mt + 3 * d, mod_ld, xn, d, h_bs, B, S, (int)d, eps, S_txt,
+                      mi + 4 * d, mi + 3 * d, st));
       RUN(gemm_bf16(xn_img, d, h_bs, w.ff1.w, d, w.ff1.b, cat_img + d, 5 * d, cat_bs, B, S_img,
                     (int)(4 * d), (int)d, B2F_EPI_GELU_TANH, nullptr, 0, 0, nullptr, 0, st));
       RUN(gemm_bf16(xn_txt, d, h_bs, w.ffc1.w, d, w.ffc1.b, cat_txt + d, 5 * d, cat_bs, B, S_txt,
@@ -362,7 +361,7 @@ int b2f_flux_forward(b2f_flux* h, const void* hidden, const void* enc, const voi
       const SingleW& w = c->sgl[si];
       // mod columns: [shift, scale, gate]
       const bf16_t* ms = modp + (int64_t)g.num_double * 12 * d + (int64_t)si * 3 * d;
-      RUN(ln_modulate(hb, d, h_bs, ms + d, ms, mod_ld, xn, d, h_bs, B, S, (int)d, eps, st));
+      RUN(ln_modulate(hb, d, h_bs, ms + d, ms, mod_ld, xn, d, h_bs, B, S, (int)d, eps, 0, nullptr, nullptr, st));
       // ONE launch for [to_q;to_k;to_v;proj_mlp] (N = 7d): Q/K get RMSNorm+RoPE, V passes through into
       // qkv, the MLP columns are GELU'd straight into cat[:, :, d:5d]
       RUN(gemm_qkv_norm_rope(xn, d, h_bs, w.qkv_mlp.w, d, w.qkv_mlp.b, qkv, 3 * d, qkv_bs, B, S, (int)d, (int)d,
@@ -378,7 +377,8 @@ int b2f_flux_forward(b2f_flux* h, const void* hidden, const void* enc, const voi
   if (last_block == total_blocks) {
     // norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows
     const bf16_t* mo = modp + (int64_t)g.num_double * 12 * d + (int64_t)g.num_single * 3 * d;
-    RUN(ln_modulate(h_img, d, h_bs, mo, mo + d, mod_ld, xn_img, d, h_bs, B, n_out_rows, (int)d, eps, st));
+    RUN(ln_modulate(h_img, d, h_bs, mo, mo + d, mod_ld, xn_img, d, h_bs, B, n_out_rows, (int)d, eps, 0, nullptr,
+                    nullptr, st));
     RUN(gemm_bf16(xn_img, d, h_bs, c->proj_out.w, d, c->proj_out.b, out, g.out_channels,
                   (int64_t)n_out_rows * g.out_channels, B, n_out_rows, g.out_channels, (int)d,
                   B2F_EPI_BIAS, nullptr, 0, 0, nullptr, 0, st));

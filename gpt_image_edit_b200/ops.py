@@ -86,8 +86,9 @@ def attention(q, k, v, *, out=None, causal: bool = False, scale: float | None = 
     return out
 
 
-def ln_modulate(x, scale, shift, *, out=None, eps: float = 1e-6) -> torch.Tensor:
-    """LayerNorm(x)*(1+scale[b])+shift[b]; x [B,rows,D] view, scale/shift [B,D] views."""
+def ln_modulate(x, scale, shift, *, out=None, eps: float = 1e-6, split_row: int = 0, scale_b=None, shift_b=None) -> torch.Tensor:
+    """LayerNorm(x)*(1+scale[b])+shift[b]; x [B,rows,D] view, scale/shift [B,D] views.  With split_row,
+    rows >= split_row use (scale_b, shift_b) instead (same pitch)."""
     _req(x, "x")
     _req(scale, "scale")
     _req(shift, "shift")
@@ -100,7 +101,8 @@ def ln_modulate(x, scale, shift, *, out=None, eps: float = 1e-6) -> torch.Tensor
         raise _lib.B2FError("scale/shift must be [B,D] views with equal pitch")
     check(
         _lib.lib.b2f_ln_modulate(ptr(x3), x3.stride(1), x3.stride(0), ptr(scale), ptr(shift), scale.stride(0),
-                                 ptr(o3), o3.stride(1), o3.stride(0), B, rows, D, eps, stream_ptr()),
+                                 ptr(o3), o3.stride(1), o3.stride(0), B, rows, D, eps, split_row, ptr(scale_b),
+                                 ptr(shift_b), stream_ptr()),
         "b2f_ln_modulate",
     )
     return out

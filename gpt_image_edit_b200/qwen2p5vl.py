@@ -61,7 +61,7 @@ def get_rope_index(input_ids: torch.Tensor, image_grid_thw: torch.Tensor | None,
         pos = pos.unsqueeze(0).expand(3, -1, -1).contiguous()
         delta = pos.max(0)[0].max(-1, keepdim=True)[0] + 1 - L
         return pos.to(input_ids.device), delta.to(input_ids.device)
-    grids = image_grid_thw.cpu().tolist()
+    grids = image_grid_thw.cpu().tolist() if torch.is_tensor(image_grid_thw) else [list(g) for g in image_grid_thw]
     pos = torch.ones(3, B, L, dtype=torch.long)
     deltas = []
     img_i = 0

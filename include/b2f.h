@@ -102,12 +102,14 @@ int b2f_gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_batch_stride, c
  * Replaces nn.LayerNorm + the broadcast multiply/add of diffusers AdaLayerNormZero /
  * AdaLayerNormZeroSingle / AdaLayerNormContinuous and the norm2 modulate inside
  * FluxTransformerBlock.  x/out: [batch, rows, D] views; scale/shift: [batch, D]
- * with pitch mod_ld.  D % 256 == 0, D <= 5120.
+ * with pitch mod_ld.  D % 256 == 0, D <= 5120.  With split_row > 0, rows [0, split_row) of every batch
+ * item use (scale, shift) and the remaining rows (scale_b, shift_b): the text and image streams of a
+ * double-stream block share one launch over the joint [txt; img] buffer.
  */
 int b2f_ln_modulate(const void* x, int64_t ldx, int64_t x_batch_stride, const void* scale,
                     const void* shift, int64_t mod_ld, void* out, int64_t ldo,
-                    int64_t out_batch_stride, int batch, int rows, int D, float eps,
-                    b2f_stream_t stream);
+                    int64_t out_batch_stride, int batch, int rows, int D, float eps, int split_row,
+                    const void* scale_b, const void* shift_b, b2f_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Per-head RMSNorm + interleaved-pair RoPE, in place on the Q and K blocks of a fused QKV buffer
