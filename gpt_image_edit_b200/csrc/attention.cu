@@ -423,6 +423,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   PV(t,u) needs P(t,u) from the same warpgroup.
 constexpr int SUB = 64;
 
+template <int POLY>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -438,7 +439,8 @@ attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* s_full = kv_empty + KV_SLOTS;    // [tile][buf] = 4
   uint64_t* p_full = s_full + 4;             // [tile][buf] = 4
   uint64_t* o_done = p_full + 4;             // [tile] = 2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_final = o_done + 2;            // 1: everything issued has completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_final + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -463,10 +465,11 @@ attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 4);
     }
     mbar_init(&o_done[0], 1);
     mbar_init(&o_done[1], 1);
+    mbar_init(o_final, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -503,78 +506,78 @@ attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, SUB, 0);  // S sub-block: 128 x 64
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 1);   // O: 128 x 128, V MN-major
-      const uint32_t q_addr = smem_u32(q_smem);
-      const uint32_t kv_addr = smem_u32(kv_smem);
-      // K rows [64 hh, 64 hh + 64) of a 128-row tile start 8 KB into each dh-half sub-tile
-      auto issue_qk = [&](int t, int buf, uint32_t k_tile, int hh) {
-        const uint32_t d = tmem_base + uint32_t(t * 128 + buf * SUB);
-        const uint32_t qa = q_addr + t * TILE_BYTES;
-        const uint32_t ka = k_tile + hh * (SUB * 128);
+    constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, SUB, 0);  // S sub-block: 128 x 64
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 1);   // O: 128 x 128, V MN-major
+    const uint64_t dq_base = make_sdesc_sw128(smem_u32(q_smem), 16, 1024);
+    const uint64_t dk_base = make_sdesc_sw128(smem_u32(kv_smem), 16, 1024);
+    const uint64_t dv_base = make_sdesc_sw128(smem_u32(kv_smem), TILE_BYTES / 2, 1024);
+    // K rows [64 hh, 64 hh + 64) of a 128-row tile start 8 KB into each dh-half sub-tile
+    auto issue_qk = [&](int t, int buf, int k_slot, int hh) {
+      const uint32_t d = tmem_base + uint32_t(t * 128 + buf * SUB);
+      const uint64_t qd = dq_base + uint64_t((t * TILE_BYTES) >> 4);
+      const uint64_t kd = dk_base + uint64_t((k_slot * TILE_BYTES + hh * (SUB * 128)) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
-          const uint32_t off = (k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32;
-          umma_ss(d, make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024), idesc_qk,
-                  k != 0 ? 1u : 0u);
+          const uint64_t off = uint64_t(((k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32) >> 4);
+          umma_ss(d, qd + off, kd + off, idesc_qk, k != 0 ? 1u : 0u);
         }
-      };
-      auto issue_pv = [&](int t, int buf, uint32_t v_tile, int hh, bool first) {
-        const uint32_t d = tmem_base + 256 + uint32_t(t * 128);
-        const uint32_t pa = tmem_base + uint32_t(t * 128 + buf * SUB);
-        const uint32_t va = v_tile + hh * (SUB * 128);
+        umma_commit(&s_full[t * 2 + buf]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int t, int buf, int v_slot, int hh, bool first) {
+      const uint32_t d = tmem_base + 256 + uint32_t(t * 128);
+      const uint32_t pa = tmem_base + uint32_t(t * 128 + buf * SUB);
+      const uint64_t vd = dv_base + uint64_t((v_slot * TILE_BYTES + hh * (SUB * 128)) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < SUB / 16; ++k)
-          umma_ts(d, pa + k * 8, make_sdesc_sw128(va + k * 2048, TILE_BYTES / 2, 1024), idesc_pv,
-                  (first && k == 0) ? 0u : 1u);
-      };
-      // ring bookkeeping: tile index i (0 = K_0, 1 = V_0, 2 = K_1, ...) lives in slot i % 4, phase (i / 4) & 1
-      auto slot_of = [](int i) { return i % KV_SLOTS; };
-      auto phase_of = [](int i) { return uint32_t((i / KV_SLOTS) & 1); };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      for (int u0 = 0; u0 < 2 && u0 < n_sub; ++u0)
-        for (int t = 0; t < 2; ++t) {
-          issue_qk(t, u0, kv_addr, u0);
-          umma_commit(&s_full[t * 2 + u0]);
-        }
-      if (n_sub <= 2) umma_commit(&kv_empty[0]);   // K_0 fully consumed (otherwise released below)
-      for (int u = 0; u < n_sub; ++u) {
-        const int j = u >> 1, hh = u & 1, buf = u & 1;
-        const int vi = 2 * j + 1;              // ring index of V_j
-        if (hh == 0 || u == 0) {
-          mbar_wait(&kv_full[slot_of(vi)], phase_of(vi));
-          tc_fence_after();
-        }
-        const uint32_t v_tile = kv_addr + slot_of(vi) * TILE_BYTES;
-        const int u2 = u + 2;                  // the QK that reuses this S buffer
-        const int ki2 = 2 * (u2 >> 1);         // ring index of K_{u2/2}
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t * 2 + buf], uint32_t(u >> 1) & 1);
-          tc_fence_after();
-          issue_pv(t, buf, v_tile, hh, u == 0);
-          umma_commit(&o_done[t]);
-          if (u2 < n_sub) {
-            if (t == 0 && hh == 0) {
-              mbar_wait(&kv_full[slot_of(ki2)], phase_of(ki2));
-              tc_fence_after();
-            }
-            issue_qk(t, buf, kv_addr + slot_of(ki2) * TILE_BYTES, hh);
-            umma_commit(&s_full[t * 2 + buf]);
+          umma_ts(d, pa + k * 8, vd + uint64_t((k * 2048) >> 4), idesc_pv, (first && k == 0) ? 0u : 1u);
+        umma_commit(&o_done[t]);
+      }
+      __syncwarp();
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+    };
+    // ring bookkeeping: tile index i (0 = K_0, 1 = V_0, 2 = K_1, ...) lives in slot i % 4, phase (i / 4) & 1
+    auto slot_of = [](int i) { return i % KV_SLOTS; };
+    auto phase_of = [](int i) { return uint32_t((i / KV_SLOTS) & 1); };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    for (int u0 = 0; u0 < 2 && u0 < n_sub; ++u0)
+      for (int t = 0; t < 2; ++t) issue_qk(t, u0, 0, u0);
+    if (n_sub <= 2) commit(&kv_empty[0]);   // K_0 fully consumed (otherwise released below)
+    for (int u = 0; u < n_sub; ++u) {
+      const int j = u >> 1, hh = u & 1, buf = u & 1;
+      const int vi = 2 * j + 1;              // ring index of V_j
+      if (hh == 0) {
+        mbar_wait(&kv_full[slot_of(vi)], phase_of(vi));
+        tc_fence_after();
+      }
+      const int u2 = u + 2;                  // the QK that reuses this S buffer
+      const int ki2 = 2 * (u2 >> 1);         // ring index of K_{u2/2}
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_full[t * 2 + buf], uint32_t(u >> 1) & 1);
+        tc_fence_after();
+        issue_pv(t, buf, slot_of(vi), hh, u == 0);
+        if (u2 < n_sub) {
+          if (t == 0 && hh == 0) {
+            mbar_wait(&kv_full[slot_of(ki2)], phase_of(ki2));
+            tc_fence_after();
           }
-        }
-        // releases: V_j after its second half (or the last sub-block); K tiles after their last QK
-        const bool last_of_v = (hh == 1) || (u == n_sub - 1);
-        if (last_of_v) umma_commit(&kv_empty[slot_of(vi)]);
-        if (u2 < n_sub && ((u2 & 1) == 1 || u2 == n_sub - 1)) umma_commit(&kv_empty[slot_of(ki2)]);
-        if (u == 0 && n_sub > 2) {
-          // K_0 was consumed by the prologue QKs (u = 0, 1): everything issued so far covers them
-          umma_commit(&kv_empty[0]);
+          issue_qk(t, buf, slot_of(ki2), hh);
         }
       }
+      // releases: V_j after its second half (or the last sub-block); K tiles after their last QK
+      if ((hh == 1) || (u == n_sub - 1)) commit(&kv_empty[slot_of(vi)]);
+      if (u2 < n_sub && ((u2 & 1) == 1 || u2 == n_sub - 1)) commit(&kv_empty[slot_of(ki2)]);
+      if (u == 0 && n_sub > 2) commit(&kv_empty[0]);   // K_0: consumed by the prologue QKs (u = 0, 1)
     }
+    commit(o_final);
   } else {
     const int t = (warp - 2) >> 2;
     const int quarter = warp & 3;
@@ -622,7 +625,13 @@ attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float x0, x1;
         ffma2(x0, x1, __uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]), p.scale_log2, p.scale_log2,
               neg_m, neg_m);
-        const float p0 = ex2(x0), p1 = ex2(x1);
+        float p0, p1;
+        if (POLY && (c % (POLY ? POLY : 1)) == (POLY ? POLY : 1) - 1) {
+          ex2_poly2(x0, x1, p0, p1);
+        } else {
+          p0 = ex2(x0);
+          p1 = ex2(x1);
+        }
         const int a = (c & 1) * 2;
         fadd2(sum4[a], sum4[a + 1], sum4[a], sum4[a + 1], p0, p1);
         pk[c] = pack_bf16x2(p0, p1);
@@ -646,9 +655,296 @@ attn_fwd_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[t * 2 + buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t * 2 + buf]);
     }
-    mbar_wait(&o_done[t], uint32_t(n_sub - 1) & 1);
+    mbar_wait(o_final, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const bool row_ok = q_row < p.Sq;
+    __nv_bfloat16* out_row = p.out + ((long long)b * p.Sq + q_row) * p.ldo + (long long)h * DH;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t o[32];
+      __syncwarp();
+      B2F_TMEM_LD_X32(o_tmem + c0, o);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(out_row + c0 + g * 8) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ================================================================================================
+// v3: ONE 128-row Q tile per CTA, S double-buffered in TMEM.
+//   TMEM: S0|P0 [0,128)  S1|P1 [128,256)  O [256,384)   (512 allocated)
+//   MMA warp:  QK(0)->S0, QK(1)->S1, then for every block j:  wait P(j) -> PV(j) -> QK(j+2) into the
+//              buffer PV(j) just released.  S(j+1) is therefore computed WHILE the warpgroup runs the
+//              softmax of block j: in steady state the softmax warpgroup never waits for the tensor pipe
+//              and the tensor pipe only waits for P — the two-tile kernel above serialises
+//              QK -> softmax -> PV inside each tile and leaves its warpgroups waiting for S a third of
+//              the time (ncu: 42 % of softmax-warp samples).
+//   P is still handed over in two 64-column halves; O is rescaled lazily.  `o_done` completes once per
+//   PV(j); the warpgroup consults it only before a rescale (unambiguous: PV(j) cannot be issued before the
+//   warpgroup publishes P(j)); the epilogue waits on a separate one-shot `o_final` barrier.
+constexpr int V3_SLOTS = 6;
+constexpr int V3_THREADS = 192;
+constexpr int V3_SMEM = (1 + V3_SLOTS) * TILE_BYTES + 256 + 1024;
+
+template <int POLY>
+__global__ void __launch_bounds__(V3_THREADS, 1)
+attn_fwd_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + V3_SLOTS) * TILE_BYTES);
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* kv_full = bars + 1;              // V3_SLOTS
+  uint64_t* kv_empty = kv_full + V3_SLOTS;   // V3_SLOTS
+  uint64_t* s_full = kv_empty + V3_SLOTS;    // [buf] = 2
+  uint64_t* p_full = s_full + 2;             // [buf][half] = 4
+  uint64_t* o_done = p_full + 4;             // 1
+  uint64_t* o_final = o_done + 1;            // 1: everything issued has completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_final + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.H / p.Hkv);
+  const int q0 = qt * BQ;
+  int kv_len = p.Skv;
+  if (p.causal) kv_len = min(p.Skv, q0 + BQ);
+  const int n_kv = (kv_len + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < V3_SLOTS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
+    mbar_init(o_done, 1);
+    mbar_init(o_final, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      for (int half = 0; half < 2; ++half)
+        tma_load_3d(q_smem + half * (TILE_BYTES / 2), &tmQ, q_full, h * DH + half * 64, q0, b);
+      // ring order: K_0, K_1, V_0, K_2, V_1, K_3, ... (the order in which the MMA warp consumes tiles)
+      int slot = 0;
+      uint32_t phase = 0;
+      auto load = [&](const CUtensorMap* tm, int j) {
+        mbar_wait(&kv_empty[slot], phase ^ 1);
+        mbar_expect_tx(&kv_full[slot], TILE_BYTES);
+        uint8_t* dst = kv_smem + slot * TILE_BYTES;
+        tma_load_3d(dst, tm, &kv_full[slot], hk * DH, j * BKV, b);
+        tma_load_3d(dst + TILE_BYTES / 2, tm, &kv_full[slot], hk * DH + 64, j * BKV, b);
+        if (++slot == V3_SLOTS) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      load(&tmK, 0);
+      if (n_kv > 1) load(&tmK, 1);
+      for (int j = 0; j < n_kv; ++j) {
+        load(&tmV, j);
+        if (j + 2 < n_kv) load(&tmK, j + 2);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 1);
+    const uint64_t dq_base = make_sdesc_sw128(smem_u32(q_smem), 16, 1024);
+    const uint64_t dk_base = make_sdesc_sw128(smem_u32(kv_smem), 16, 1024);
+    const uint64_t dv_base = make_sdesc_sw128(smem_u32(kv_smem), TILE_BYTES / 2, 1024);
+    int slot = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+      if (++slot == V3_SLOTS) {
+        slot = 0;
+        phase ^= 1;
+      }
+    };
+    auto issue_qk = [&](int buf, int k_slot) {
+      const uint32_t d = tmem_base + uint32_t(buf * 128);
+      const uint64_t kd = dk_base + uint64_t((k_slot * TILE_BYTES) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          const uint64_t off = uint64_t(((k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32) >> 4);
+          umma_ss(d, dq_base + off, kd + off, idesc_qk, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[buf]);
+        umma_commit(&kv_empty[k_slot]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int buf, int v_slot, int hf, bool first, bool last_half) {
+      const uint32_t d = tmem_base + 256;
+      const uint32_t pa = tmem_base + uint32_t(buf * 128 + hf * 32);
+      const uint64_t vd = dv_base + uint64_t((v_slot * TILE_BYTES + hf * 8192) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ts(d, pa + k * 8, vd + uint64_t((k * 2048) >> 4), idesc_pv, (first && k == 0) ? 0u : 1u);
+        if (last_half) {
+          umma_commit(o_done);
+          umma_commit(&kv_empty[v_slot]);
+        }
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    // prologue: S(0), S(1)
+    for (int j = 0; j < 2 && j < n_kv; ++j) {
+      mbar_wait(&kv_full[slot], phase);
+      tc_fence_after();
+      issue_qk(j, slot);
+      advance();
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&kv_full[slot], phase);      // V_j
+      const int v_slot = slot;
+      advance();
+      mbar_wait(&p_full[buf * 2 + 0], uint32_t(j >> 1) & 1);
+      tc_fence_after();
+      issue_pv(buf, v_slot, 0, j == 0, false);
+      mbar_wait(&p_full[buf * 2 + 1], uint32_t(j >> 1) & 1);
+      tc_fence_after();
+      issue_pv(buf, v_slot, 1, false, true);
+      if (j + 2 < n_kv) {
+        mbar_wait(&kv_full[slot], phase);    // K_{j+2}
+        tc_fence_after();
+        issue_qk(buf, slot);
+        advance();
+      }
+    }
+    if (elect_one()) umma_commit(o_final);
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + row_in_tile;
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const uint32_t o_tmem = tmem_base + lane_addr + 256;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int buf = j & 1;
+      const uint32_t s_tmem = tmem_base + lane_addr + uint32_t(buf * 128);
+      mbar_wait(&s_full[buf], uint32_t(j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr[128];
+      B2F_TMEM_LD_X32(s_tmem + 0, (sr + 0));
+      B2F_TMEM_LD_X32(s_tmem + 32, (sr + 32));
+      B2F_TMEM_LD_X32(s_tmem + 64, (sr + 64));
+      B2F_TMEM_LD_X32(s_tmem + 96, (sr + 96));
+      tmem_wait_ld();
+      const int kv0 = j * BKV;
+      const bool need_mask = (kv0 + BKV > p.Skv) || (p.causal && kv0 + BKV > q0);
+      if (need_mask) {
+        const int limit = p.causal ? min(p.Skv, q_row + 1) : p.Skv;
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (kv0 + c >= limit) sr[c] = 0xff800000u;
+      }
+      float mx4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx4[i] = fmaxf(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1]));
+#pragma unroll
+      for (int c = 8; c < 128; c += 8)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          mx4[i] = fmax3(mx4[i], __uint_as_float(sr[c + 2 * i]), __uint_as_float(sr[c + 2 * i + 1]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      const bool grow = (m_new - m) > 8.0f;
+      const float m_use = grow ? m_new : m;
+      const float alpha = grow ? ex2(m - m_use) : 1.0f;
+      const float neg_m = (m_use == -INFINITY) ? 0.f : -m_use;
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        // O must be quiescent: PV(j-1) is the last one issued (PV(j) needs the arrives below).  Completed
+        // phases of o_done are j-1 or j here, so the parity of phase j-1 is unambiguous.
+        mbar_wait(o_done, uint32_t(j - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t o[32];
+          B2F_TMEM_LD_X32(o_tmem + c0, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          B2F_TMEM_ST_X32(o_tmem + c0, o);
+        }
+      }
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float x0, x1;
+          ffma2(x0, x1, __uint_as_float(sr[half * 64 + 2 * c]), __uint_as_float(sr[half * 64 + 2 * c + 1]),
+                p.scale_log2, p.scale_log2, neg_m, neg_m);
+          float p0, p1;
+          if (POLY && (c % (POLY ? POLY : 1)) == (POLY ? POLY : 1) - 1) {
+            ex2_poly2(x0, x1, p0, p1);
+          } else {
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+          }
+          const int a = (c & 1) * 2;
+          fadd2(sum4[a], sum4[a + 1], sum4[a], sum4[a + 1], p0, p1);
+          pk[c] = pack_bf16x2(p0, p1);
+        }
+        B2F_TMEM_ST_X32(s_tmem + half * 32, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[buf * 2 + half]);
+      }
+      l = l * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+      m = m_use;
+    }
+    mbar_wait(o_final, 0);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const bool row_ok = q_row < p.Sq;
@@ -699,6 +995,7 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   // kernel variant: compile-time (POLY, TURNS); B2F_ATTN_VARIANT selects at run time for tuning
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   static KernelFn kernel = nullptr;
+  static bool single_tile = false;
   if (!kernel) {
     const char* v = getenv("B2F_ATTN_VARIANT");
     const int variant = v ? atoi(v) : B2F_ATTN_DEFAULT_VARIANT;
@@ -711,10 +1008,16 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
       case 6: kernel = attn_fwd_kernel<8, false>; break;   // 12.5 %
       case 21: kernel = attn_fwd_kernel<0, false, 1>; break;  // ablations for timing analysis only
 
-      case 10: kernel = attn_fwd_kernel_v2; break;
+      case 10: kernel = attn_fwd_kernel_v2<0>; break;
+      case 11: kernel = attn_fwd_kernel_v2<4>; break;
+      case 12: kernel = attn_fwd_kernel_v2<2>; break;
+      case 30: kernel = attn_fwd_kernel_v3<0>; single_tile = true; break;
+      case 31: kernel = attn_fwd_kernel_v3<4>; single_tile = true; break;
+      case 32: kernel = attn_fwd_kernel_v3<3>; single_tile = true; break;
       default: kernel = attn_fwd_kernel<0, false>; break;
     }
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         single_tile ? V3_SMEM : ATTN_SMEM);
     if (e != cudaSuccess) return cuda_err(e, "attention smem attribute");
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -734,9 +1037,9 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   p.causal = causal;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
-  dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
+  dim3 grid(single_tile ? (Sq + BQ - 1) / BQ : (Sq + 2 * BQ - 1) / (2 * BQ), H, B);
   prof_begin(KC_ATTN, stream);
-  kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  kernel<<<grid, single_tile ? V3_THREADS : ATTN_THREADS, single_tile ? V3_SMEM : ATTN_SMEM, stream>>>(tmQ, tmK, tmV, p);
   prof_end(KC_ATTN, stream, (causal ? 2.0 : 4.0) * B * H * (double)Sq * Skv * DH,
            2.0 * DH * B * (2.0 * H * Sq + 2.0 * Hkv * Skv));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
