@@ -87,6 +87,11 @@ _SIGNATURES = {
     "b2f_flux_modulation": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "b2f_flux_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, C.c_size_t, _i32, _i32, _vp]),
     "b2f_attention_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, _i32, _vp]),
+    "b2f_attention_bias_fwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, _i32,
+                                      _vp, _i64, _i64, _vp]),
+    "b2f_geglu": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "b2f_layernorm": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, C.c_float, _vp]),
+    "b2f_embed": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64, _i64, _i32, _vp]),
 }
 
 

@@ -46,6 +46,10 @@ struct AttnParams {
   int causal;
   __nv_bfloat16* out;
   long long ldo;
+  // additive score bias (BIAS kernels only): score = bias_scale * q.k + bias[h, q, kv]
+  const __nv_bfloat16* bias;
+  long long bias_h_stride, bias_row_stride;
+  float bias_scale;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -85,7 +89,9 @@ __device__ __forceinline__ void ex2_poly2(float x0, float x1, float& r0, float& 
 
 // POLY: one pair of exponentials in every POLY pairs goes to the polynomial (0 = never).
 // TURNS: the two softmax warpgroups take turns on the exp section (forces anti-phase).
-template <int POLY, bool TURNS, int ABL = 0>   // ABL: timing ablations (wrong results), see attention_fwd
+// ABL: timing ablations (wrong results), see attention_fwd.  BIAS: additive bf16 score bias (T5 relative
+// position bias); the bias kernel folds the score scale into the bias step and runs with scale_log2 = log2(e).
+template <int POLY, bool TURNS, int ABL = 0, bool BIAS = false>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -300,6 +306,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       B2F_TMEM_LD_X32(s_tmem + 96, (sr + 96));
       tmem_wait_ld();
       const int kv0 = j * BKV;
+      if (BIAS) {
+        if (q_row < p.Sq) {
+          const __nv_bfloat16* brow = p.bias + (long long)h * p.bias_h_stride +
+                                      (long long)q_row * p.bias_row_stride + kv0;
+          const int n_ok = min(BKV, p.Skv - kv0);
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c < n_ok)
+              sr[c] = __float_as_uint(fmaf(__uint_as_float(sr[c]), p.bias_scale, __bfloat162float(brow[c])));
+        }
+      }
       const bool need_mask = (kv0 + BKV > p.Skv) || (p.causal && kv0 + BKV > q0 + t * BQ);
       if (need_mask) {
         const int limit = p.causal ? min(p.Skv, q_row + 1) : p.Skv;
@@ -979,9 +996,10 @@ attn_fwd_kernel_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 }  // namespace
 
-int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                  int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
-                  int head_dim, float scale, int causal, cudaStream_t stream) {
+static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                          int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                          int head_dim, float scale, int causal, const void* bias, int64_t bias_h_stride,
+                          int64_t bias_row_stride, cudaStream_t stream) {
   if (!device_info().ok) return B2F_ERR_NODEVICE;
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || Hkv <= 0 || Sq <= 0 || Skv <= 0)
     return B2F_ERR_INVALID;
@@ -1019,6 +1037,9 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          single_tile ? V3_SMEM : ATTN_SMEM);
     if (e != cudaSuccess) return cuda_err(e, "attention smem attribute");
+    e = cudaFuncSetAttribute(attn_fwd_kernel<0, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ATTN_SMEM);
+    if (e != cudaSuccess) return cuda_err(e, "attention smem attribute");
   }
   CUtensorMap tmQ, tmK, tmV;
   int rc = make_tmap_3d_rows(&tmQ, q, (uint64_t)H * DH, Sq, B, ldq, (uint64_t)Sq * ldq);
@@ -1037,6 +1058,22 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   p.causal = causal;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
+  if (bias) {
+    // score = scale * q.k + bias, evaluated before the base-2 conversion
+    p.bias = static_cast<const __nv_bfloat16*>(bias);
+    p.bias_h_stride = bias_h_stride;
+    p.bias_row_stride = bias_row_stride;
+    p.bias_scale = scale;
+    p.scale_log2 = 1.4426950408889634f;
+    dim3 grid_b((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
+    prof_begin(KC_ATTN, stream);
+    attn_fwd_kernel<0, false, 0, true><<<grid_b, ATTN_THREADS, ATTN_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    prof_end(KC_ATTN, stream, (causal ? 2.0 : 4.0) * B * H * (double)Sq * Skv * DH,
+             2.0 * DH * B * (2.0 * H * Sq + 2.0 * Hkv * Skv) + 2.0 * H * (double)Sq * Skv);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    B2F_CHECK_LAUNCH("attn_fwd_kernel<bias>");
+    return B2F_OK;
+  }
   dim3 grid(single_tile ? (Sq + BQ - 1) / BQ : (Sq + 2 * BQ - 1) / (2 * BQ), H, B);
   prof_begin(KC_ATTN, stream);
   kernel<<<grid, single_tile ? V3_THREADS : ATTN_THREADS, single_tile ? V3_SMEM : ATTN_SMEM, stream>>>(tmQ, tmK, tmV, p);
@@ -1045,6 +1082,22 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("attn_fwd_kernel");
   return B2F_OK;
+}
+
+int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                  int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                  int head_dim, float scale, int causal, cudaStream_t stream) {
+  return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale, causal,
+                        nullptr, 0, 0, stream);
+}
+
+int attention_bias_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                       int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                       int head_dim, float scale, int causal, const void* bias, int64_t bias_h_stride,
+                       int64_t bias_row_stride, cudaStream_t stream) {
+  if (!bias || bias_row_stride < Skv || bias_h_stride < 0) return B2F_ERR_INVALID;
+  return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale, causal,
+                        bias, bias_h_stride, bias_row_stride, stream);
 }
 
 }  // namespace b2f

@@ -50,6 +50,15 @@ int rope_tables(const float* ids, int S, const int* axes_dim, double theta, floa
 int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                   int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
                   int head_dim, float scale, int causal, cudaStream_t stream);
+int attention_bias_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                       int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                       int head_dim, float scale, int causal, const void* bias, int64_t bias_h_stride,
+                       int64_t bias_row_stride, cudaStream_t stream);
+int geglu(const void* gu, int64_t ld, void* out, int64_t ldo, int64_t rows, int I, cudaStream_t stream);
+int layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+              int64_t rows, int D, float eps, cudaStream_t stream);
+int embed(const void* tok, int64_t ld_tok, const int64_t* ids, const void* pos, int64_t ld_pos, int period,
+          void* out, int64_t ldo, int64_t n, int D, cudaStream_t stream);
 }  // namespace b2f
 
 extern "C" {
@@ -193,6 +202,28 @@ int b2f_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, co
                       int head_dim, float scale, int causal, b2f_stream_t stream) {
   return b2f::attention_fwd(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale,
                             causal, static_cast<cudaStream_t>(stream));
+}
+
+int b2f_attention_bias_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                           int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                           int head_dim, float scale, int causal, const void* bias,
+                           int64_t bias_h_stride, int64_t bias_row_stride, b2f_stream_t stream) {
+  return b2f::attention_bias_fwd(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale,
+                                 causal, bias, bias_h_stride, bias_row_stride,
+                                 static_cast<cudaStream_t>(stream));
+}
+int b2f_geglu(const void* gu, int64_t ld, void* out, int64_t ldo, int64_t rows, int I,
+              b2f_stream_t stream) {
+  return b2f::geglu(gu, ld, out, ldo, rows, I, static_cast<cudaStream_t>(stream));
+}
+int b2f_layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+                  int64_t rows, int D, float eps, b2f_stream_t stream) {
+  return b2f::layernorm(x, ldx, w, b, y, ldy, rows, D, eps, static_cast<cudaStream_t>(stream));
+}
+int b2f_embed(const void* tok, int64_t ld_tok, const int64_t* ids, const void* pos, int64_t ld_pos,
+              int period, void* out, int64_t ldo, int64_t n, int D, b2f_stream_t stream) {
+  return b2f::embed(tok, ld_tok, ids, pos, ld_pos, period, out, ldo, n, D,
+                    static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

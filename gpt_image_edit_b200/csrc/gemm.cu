@@ -120,6 +120,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
     } else if (epi == B2F_EPI_SILU) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = silu_f(bf16r(v[j]));
+    } else if (epi == B2F_EPI_QUICK_GELU) {
+      // transformers QuickGELUActivation in bf16 eager: x * sigmoid(1.702 * x), each op rounded
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = bf16r(v[j]);
+        const float t = bf16r(1.702f * x);
+        v[j] = x * bf16r(1.0f / (1.0f + __expf(-t)));
+      }
     } else if (epi == B2F_EPI_GATE_RESID) {
       const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gate_row + n));
       const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
@@ -650,7 +658,7 @@ static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* 
        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
        reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(gate)) & 15)
     return B2F_ERR_ALIGN;
-  if (epilogue < 0 || epilogue > B2F_EPI_QKV_NORM_ROPE) return B2F_ERR_INVALID;
+  if (epilogue < 0 || epilogue > B2F_EPI_QUICK_GELU) return B2F_ERR_INVALID;
   if (epilogue == B2F_EPI_QKV_NORM_ROPE) {
     if (!qx || !qx->nw_q || !qx->nw_k || !qx->cos || !qx->sin || qx->d_model <= 0) return B2F_ERR_INVALID;
     if (N != 3 * qx->d_model + qx->n_extra || (qx->d_model % 128) || (qx->n_extra & 7)) return B2F_ERR_UNSUPPORTED;

@@ -129,6 +129,96 @@ __global__ void __launch_bounds__(256) move_rows_kernel(const __nv_bfloat16* src
     *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = *reinterpret_cast<const uint4*>(src + j * ld_src + c);
 }
 
+// T5 gated-GELU combine (T5DenseGatedActDense with gelu_new): out = bf16( bf16(gelu_tanh(g)) * u ),
+// g = gu[:, :I] (wi_0 x), u = gu[:, I:2I] (wi_1 x).
+__global__ void __launch_bounds__(256) geglu_kernel(const __nv_bfloat16* gu, long long ld,
+                                                    __nv_bfloat16* out, long long ldo, long long rows,
+                                                    int I) {
+  const int vec = I >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * vec) return;
+  const long long r = i / vec;
+  const int c = int(i - r * vec) * 8;
+  float g[8], u[8], o[8];
+  unpack8l(*reinterpret_cast<const uint4*>(gu + r * ld + c), g);
+  unpack8l(*reinterpret_cast<const uint4*>(gu + r * ld + I + c), u);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x = g[j];
+    const float t = tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x));
+    o[j] = bf16r(0.5f * x * (1.0f + t)) * u[j];
+  }
+  *reinterpret_cast<uint4*>(out + r * ldo + c) = pack8l(o);
+}
+
+// nn.LayerNorm with affine weight and bias (CLIP text encoder): fp32 statistics, one rounding.
+template <int MAXC>
+__global__ void __launch_bounds__(128) layernorm_kernel(const __nv_bfloat16* x, long long ldx,
+                                                        const __nv_bfloat16* w, const __nv_bfloat16* b,
+                                                        __nv_bfloat16* y, long long ldy, long long rows,
+                                                        int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 4 + warp;
+  if (r >= rows) return;
+  const int nchunk = D >> 8;
+  float v[MAXC][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+    if (c < nchunk) {
+      unpack8l(*reinterpret_cast<const uint4*>(x + r * ldx + c * 256 + lane * 8), v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[c][j];
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)D;
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+    if (c < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        ss += d * d;
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rs = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c)
+    if (c < nchunk) {
+      float g[8], bb[8], o[8];
+      unpack8l(__ldg(reinterpret_cast<const uint4*>(w + c * 256 + lane * 8)), g);
+      unpack8l(__ldg(reinterpret_cast<const uint4*>(b + c * 256 + lane * 8)), bb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rs * g[j] + bb[j];
+      *reinterpret_cast<uint4*>(y + r * ldy + c * 256 + lane * 8) = pack8l(o);
+    }
+}
+
+// out[i, :] = bf16(tok[ids[i], :] + pos[i % period, :])  (CLIPTextEmbeddings); pos may be null (T5 `shared`)
+__global__ void __launch_bounds__(256) embed_kernel(const __nv_bfloat16* tok, long long ld_tok,
+                                                    const long long* ids, const __nv_bfloat16* pos,
+                                                    long long ld_pos, int period, __nv_bfloat16* out,
+                                                    long long ldo, long long n, int D) {
+  const int vec = D >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * vec) return;
+  const long long r = i / vec;
+  const int c = int(i - r * vec) * 8;
+  float a[8];
+  unpack8l(*reinterpret_cast<const uint4*>(tok + ids[r] * ld_tok + c), a);
+  if (pos) {
+    float b[8];
+    unpack8l(*reinterpret_cast<const uint4*>(pos + (r % period) * ld_pos + c), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+  }
+  *reinterpret_cast<uint4*>(out + r * ldo + c) = pack8l(a);
+}
+
 }  // namespace
 
 int rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int64_t rows, int D,
@@ -188,6 +278,52 @@ int move_rows(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, const 
       reinterpret_cast<const long long*>(idx), n, D, scatter);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("move_rows_kernel");
+  return B2F_OK;
+}
+
+int geglu(const void* gu, int64_t ld, void* out, int64_t ldo, int64_t rows, int I, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!gu || !out || rows <= 0 || I <= 0 || (I & 7) || (ld & 7) || (ldo & 7)) return B2F_ERR_INVALID;
+  const long long n = rows * (I >> 3);
+  geglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(gu), ld, static_cast<__nv_bfloat16*>(out), ldo, rows, I);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("geglu_kernel");
+  return B2F_OK;
+}
+
+int layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+              int64_t rows, int D, float eps, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!x || !w || !b || !y || rows <= 0) return B2F_ERR_INVALID;
+  if (D <= 0 || (D & 255) || D > 5120) return B2F_ERR_UNSUPPORTED;
+  if ((ldx & 7) || (ldy & 7)) return B2F_ERR_ALIGN;
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto W = static_cast<const __nv_bfloat16*>(w);
+  auto Bv = static_cast<const __nv_bfloat16*>(b);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+  if (D <= 1280)
+    layernorm_kernel<5><<<grid, 128, 0, stream>>>(X, ldx, W, Bv, Y, ldy, rows, D, eps);
+  else
+    layernorm_kernel<20><<<grid, 128, 0, stream>>>(X, ldx, W, Bv, Y, ldy, rows, D, eps);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("layernorm_kernel");
+  return B2F_OK;
+}
+
+int embed(const void* tok, int64_t ld_tok, const int64_t* ids, const void* pos, int64_t ld_pos, int period,
+          void* out, int64_t ldo, int64_t n, int D, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (!tok || !ids || !out || n <= 0 || D <= 0 || (D & 7) || (ld_tok & 7) || (ldo & 7)) return B2F_ERR_INVALID;
+  if (pos && (period <= 0 || (ld_pos & 7))) return B2F_ERR_INVALID;
+  const long long tot = n * (D >> 3);
+  embed_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(tok), ld_tok, reinterpret_cast<const long long*>(ids),
+      static_cast<const __nv_bfloat16*>(pos), ld_pos, period > 0 ? period : 1,
+      static_cast<__nv_bfloat16*>(out), ldo, n, D);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("embed_kernel");
   return B2F_OK;
 }
 

@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 EPI_BIAS, EPI_GELU_TANH, EPI_SILU, EPI_GATE_RESID, EPI_RESID, EPI_GELU_ERF = 0, 1, 2, 3, 4, 5
+EPI_QUICK_GELU = 7
 
 
 def _req(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> None:
@@ -62,9 +63,10 @@ def linear(x, weight, bias=None, *, epilogue: int = EPI_BIAS, out=None, resid=No
     return out
 
 
-def attention(q, k, v, *, out=None, causal: bool = False, scale: float | None = None) -> torch.Tensor:
-    """softmax(q k^T * scale) v via b2f_attention_fwd.  q [B,Sq,H,128], k/v [B,Skv,Hkv,128] as
-    (possibly strided) views whose last two dims are contiguous; out [B,Sq,H*128]."""
+def attention(q, k, v, *, out=None, causal: bool = False, scale: float | None = None, bias=None) -> torch.Tensor:
+    """softmax(q k^T * scale [+ bias]) v via b2f_attention_fwd / b2f_attention_bias_fwd.  q [B,Sq,H,128],
+    k/v [B,Skv,Hkv,128] as (possibly strided) views whose last two dims are contiguous; out [B,Sq,H*128];
+    bias [H,Sq,Skv] bf16 (shared by the batch; T5 relative position bias)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, n)
         if t.dim() != 4 or t.stride(2) != t.shape[3] or (t.shape[0] > 1 and t.stride(0) != t.shape[1] * t.stride(1)):
@@ -76,6 +78,18 @@ def attention(q, k, v, *, out=None, causal: bool = False, scale: float | None = 
     _req(out, "out")
     if scale is None:
         scale = dh ** -0.5
+    if bias is not None:
+        _req(bias, "bias")
+        if bias.shape != (H, Sq, Skv) or bias.stride(2) != 1:
+            raise _lib.B2FError(f"bias: expected [H={H},Sq={Sq},Skv={Skv}] with unit inner stride, got {tuple(bias.shape)}")
+        check(
+            _lib.lib.b2f_attention_bias_fwd(
+                ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1), ptr(out), out.stride(1),
+                B, H, Hkv, Sq, Skv, dh, float(scale), int(causal), ptr(bias), bias.stride(0), bias.stride(1), stream_ptr(),
+            ),
+            "b2f_attention_bias_fwd",
+        )
+        return out
     check(
         _lib.lib.b2f_attention_fwd(
             ptr(q), q.stride(1), ptr(k), k.stride(1), ptr(v), v.stride(1), ptr(out), out.stride(1),
@@ -183,6 +197,45 @@ def swiglu(gu, inter: int, *, out=None) -> torch.Tensor:
     if out is None:
         out = torch.empty((rows, inter), device=gu.device, dtype=torch.bfloat16)
     check(_lib.lib.b2f_swiglu(ptr(gu), gu.stride(0), ptr(out), out.stride(0), rows, inter, stream_ptr()), "b2f_swiglu")
+    return out
+
+
+def geglu(gu, inter: int, *, out=None) -> torch.Tensor:
+    """T5 gated-GELU combine: bf16(bf16(gelu_tanh(gu[:, :inter])) * gu[:, inter:])."""
+    _req(gu, "gu")
+    rows = gu.shape[0]
+    if out is None:
+        out = torch.empty((rows, inter), device=gu.device, dtype=torch.bfloat16)
+    check(_lib.lib.b2f_geglu(ptr(gu), gu.stride(0), ptr(out), out.stride(0), rows, inter, stream_ptr()), "b2f_geglu")
+    return out
+
+
+def layernorm(x, weight, bias, *, out=None, eps: float = 1e-5) -> torch.Tensor:
+    """nn.LayerNorm (affine) over the last dim of x [..., D]."""
+    _req(x, "x")
+    _req(weight, "weight")
+    _req(bias, "bias")
+    x2 = x.reshape(-1, x.shape[-1])
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    o2 = out.reshape(-1, out.shape[-1])
+    check(_lib.lib.b2f_layernorm(ptr(x2), x2.stride(0), ptr(weight), ptr(bias), ptr(o2), o2.stride(0), x2.shape[0], x2.shape[1],
+                                 eps, stream_ptr()), "b2f_layernorm")
+    return out
+
+
+def embed(table, ids, pos=None, *, period: int = 0, out=None) -> torch.Tensor:
+    """out[i] = table[ids[i]] (+ pos[i % period])."""
+    _req(table, "table")
+    _req(ids, "ids", torch.int64)
+    n, D = ids.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((n, D), device=table.device, dtype=torch.bfloat16)
+    if pos is not None:
+        _req(pos, "pos")
+    check(_lib.lib.b2f_embed(ptr(table), table.stride(0), ptr(ids), ptr(pos) if pos is not None else None,
+                             pos.stride(0) if pos is not None else 0, period, ptr(out), out.stride(0), n, D, stream_ptr()),
+          "b2f_embed")
     return out
 
 

@@ -74,6 +74,7 @@ int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* fl
 #define B2F_EPI_RESID 4 /* out = bf16(resid + bf16(acc + bias))  (VAE attention to_out + residual) */
 #define B2F_EPI_QKV_NORM_ROPE 6 /* only through b2f_gemm_qkv_norm_rope */
 #define B2F_EPI_GELU_ERF 5 /* out = bf16(gelu_erf(bf16(acc + bias)))  (Qwen2.5-VL patch merger, nn.GELU()) */
+#define B2F_EPI_QUICK_GELU 7 /* out = bf16(x * bf16(sigmoid(bf16(1.702 x)))), x = bf16(acc + bias)  (CLIP-L MLP) */
 
 int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
                   const void* bias, void* out, int64_t ldc, int64_t out_batch_stride, int batch,
@@ -158,6 +159,30 @@ int b2f_silu(const void* x, void* y, int64_t n, b2f_stream_t stream);
 int b2f_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                       int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
                       int head_dim, float scale, int causal, b2f_stream_t stream);
+
+/* Same kernel with an additive score bias: softmax(scale * q.k^T + bias[h]) v, bias bf16 with
+ * element [h, s_q, s_kv] at bias + h*bias_h_stride + s_q*bias_row_stride + s_kv (shared by the
+ * batch).  Replaces T5Attention's eager `scores += position_bias` path (transformers T5, scale = 1)
+ * reached from encode_prompt — reference univa/utils/denoiser_prompt_embedding_flux.py:44. */
+int b2f_attention_bias_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                           int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
+                           int head_dim, float scale, int causal, const void* bias,
+                           int64_t bias_h_stride, int64_t bias_row_stride, b2f_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernels of the T5-XXL / CLIP-L prompt encoders (transformers T5EncoderModel / CLIPTextModel as
+ * called by encode_prompt, reference univa/utils/denoiser_prompt_embedding_flux.py:15-104).
+ */
+/* T5DenseGatedActDense combine: out = bf16(bf16(gelu_tanh(gu[:, :I])) * gu[:, I:2I]). */
+int b2f_geglu(const void* gu, int64_t ld, void* out, int64_t ldo, int64_t rows, int I,
+              b2f_stream_t stream);
+/* nn.LayerNorm with weight and bias, fp32 statistics; D % 256 == 0, D <= 5120. */
+int b2f_layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy,
+                  int64_t rows, int D, float eps, b2f_stream_t stream);
+/* out[i] = bf16(tok[ids[i]] + pos[i % period]) (CLIPTextEmbeddings); pos == NULL: plain lookup
+ * (T5 `shared`).  ids: int64 device array, D % 8 == 0. */
+int b2f_embed(const void* tok, int64_t ld_tok, const int64_t* ids, const void* pos, int64_t ld_pos,
+              int period, void* out, int64_t ldo, int64_t n, int D, b2f_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * FLUX-Kontext MMDiT (diffusers FluxTransformer2DModel) as one object.
