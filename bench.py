@@ -177,8 +177,8 @@ def workload_config(args, world):
             "parallelism": f"batch-sharded replicas x{world} (weights broadcast once over NCCL)",
             "l2": "inputs larger than L2 (23.8 GB of weights stream every forward)",
             "conditioning": ("synthetic prompt_embeds (no encoders in the timed region)" if getattr(args, "no_conditioning", False) else
-                             "Qwen2.5-VL-7B prefill (ViT 448x448 + 28-layer decoder, L=290) + MLP2 run inside the timed region on "
-                             "libb2f kernels; T5-XXL/CLIP-L outputs are synthetic stand-ins (SURVEY.md §8f)")}
+                             "inside the timed region, all on libb2f kernels: Qwen2.5-VL-7B prefill (ViT 448x448 + 28-layer decoder, "
+                             "L=288) + MLP2, T5-XXL encoder (256 tokens), CLIP-L text encoder (77 tokens)")}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -250,7 +250,19 @@ def main():
                 t.copy_((torch.randn(t.shape, device=dev, generator=gq) * 0.02).to(torch.bfloat16))
         D.broadcast_weights(qwen.storage(), src=0)
         D.broadcast_weights(list(mlp2.state_dict().values()), src=0)
-        cond = (qwen, mlp2, synthetic_chat_tokens(256))      # L = 4 + 256 + 1 + 24 + 5 = 290 tokens (~288)
+        # T5-XXL + CLIP-L prompt encoders (row a11), also inside the timed region
+        from gpt_image_edit_b200.text_encoders import B200CLIPTextModel, B200T5Encoder, SyntheticTokenizer
+        t5, clip = B200T5Encoder(device=dev), B200CLIPTextModel(device=dev)
+        if rank == 0:
+            t5.randomize_(seed=21)
+            clip.randomize_(seed=20)
+        D.broadcast_weights(t5.storage(), src=0)
+        D.broadcast_weights(clip.storage(), src=0)
+        prompt = "replace the red car with a blue bicycle and keep the background unchanged"
+        t5_ids = SyntheticTokenizer.t5()(prompt, max_length=256).input_ids          # padded to 256 as cli.py:225
+        clip_ids = SyntheticTokenizer.clip()(prompt, max_length=77).input_ids
+        # L_qwen = 4 + 256 + 1 + 22 + 5 = 288 tokens, + 256 T5 tokens = S_txt 544
+        cond = (qwen, mlp2, synthetic_chat_tokens(256, n_text=22), t5, clip, t5_ids, clip_ids)
 
     B, H, W = args.batch_per_gpu, args.height, args.width
     S_img = 2 * (H // 16) * (W // 16)
@@ -258,9 +270,11 @@ def main():
     src_u8 = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
     src = (src_u8.float() / 127.5 - 1.0).pin_memory()                       # [-1,1] fp32 NCHW, as cli.py:99-116
     g2 = torch.Generator().manual_seed(2 + rank)
-    L_qwen = cond[2].shape[1] if cond is not None else S_TXT - 256
-    n_t5 = S_TXT - L_qwen if cond is not None else 256
-    pe_h = torch.randn(B, S_TXT if cond is None else n_t5, 4096, generator=g2).bfloat16().pin_memory()   # T5 stand-in (§8f)
+    if cond is not None and cond[2].shape[1] + 256 != S_TXT:
+        raise SystemExit(f"conditioning layout gives S_txt = {cond[2].shape[1] + 256}, expected {S_TXT}")
+    pe_h = torch.randn(B, S_TXT, 4096, generator=g2).bfloat16().pin_memory()   # only used with --no-conditioning
+    t5_ids_h = (cond[5].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
+    clip_ids_h = (cond[6].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
     pix_h = torch.randn(B * 1024, 1176, generator=g2).bfloat16().pin_memory()      # 448x448 -> 1024 patches per image
     ids_h = (cond[2].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
     pp_h = torch.randn(B, 768, generator=g2).bfloat16().pin_memory()
@@ -271,17 +285,23 @@ def main():
     def one_edit(from_host: bool):
         nb = lambda t: t.to(dev, non_blocking=True)
         if from_host:
-            pe, pp, noise = nb(pe_h), nb(pp_h), nb(noise_h)
+            noise = nb(noise_h)
             image = nb(src) if vae is not None else nb(ctx_lat_h)
-            pix, ids = (nb(pix_h), nb(ids_h)) if cond is not None else (None, None)
+            if cond is not None:
+                pix, ids, t5_ids, clip_ids = nb(pix_h), nb(ids_h), nb(t5_ids_h), nb(clip_ids_h)
+            else:
+                pe, pp = nb(pe_h), nb(pp_h)
         else:
-            pe, pp, noise = dev_in["pe"], dev_in["pp"], dev_in["noise"].clone()
+            noise = dev_in["noise"].clone()
             image = dev_in["image"]
-            pix, ids = dev_in["pix"], dev_in["ids"]
+            pe, pp = dev_in["pe"], dev_in["pp"]
+            pix, ids, t5_ids, clip_ids = dev_in["pix"], dev_in["ids"], dev_in["t5_ids"], dev_in["clip_ids"]
         if cond is not None:
-            # VLM prefill (ViT + 28-layer decoder) -> MLP2 -> [B, L, 4096]; joined with the T5 embeddings (cli.py:210-234)
+            # VLM prefill (ViT + 28-layer decoder) -> MLP2 -> [B, L, 4096]; T5-XXL hidden states and the CLIP-L pooled
+            # vector from the libb2f encoders; joined as cli.py:210-234 does
             hidden = cond[0](ids, pixel_values=pix, image_grid_thw=[(1, 32, 32)] * B)
-            pe = torch.cat([cond[1](hidden), pe], dim=1)
+            pe = torch.cat([cond[1](hidden), cond[3](t5_ids)[0]], dim=1)
+            pp = cond[4](clip_ids, output_hidden_states=False).pooler_output
         out = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pp, height=H, width=W,
                    num_inference_steps=args.num_inference_steps, guidance_scale=3.5, latents=noise,
                    max_area=H * W, _auto_resize=False, output_type="pt_raw" if vae is not None else "latent").images
@@ -292,7 +312,8 @@ def main():
         return out
 
     dev_in = dict(pe=pe_h.to(dev), pp=pp_h.to(dev), noise=noise_h.to(dev),
-                  image=(src if vae is not None else ctx_lat_h).to(dev), pix=pix_h.to(dev), ids=ids_h.to(dev))
+                  image=(src if vae is not None else ctx_lat_h).to(dev), pix=pix_h.to(dev), ids=ids_h.to(dev),
+                  t5_ids=t5_ids_h.to(dev), clip_ids=clip_ids_h.to(dev))
 
     def barrier():
         if world > 1:
@@ -367,8 +388,8 @@ def main():
         "model_frac_of_sustained_peak": f_edit / (ms_per_edit / 1e3) / 1e12 / pk["tensor_sustained"],
         "e2e": {"value": e2e, "unit": "images/s",
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in
-                                              (pe_h, pp_h, noise_h, src if vae is not None else ctx_lat_h) +
-                                              ((pix_h, ids_h) if cond is not None else ()))),
+                                              (noise_h, src if vae is not None else ctx_lat_h) +
+                                              ((pix_h, ids_h, t5_ids_h, clip_ids_h) if cond is not None else (pe_h, pp_h)))),
                 "d2h_bytes_per_step": int(B * 3 * H * W if vae is not None else noise_h.numel() * 2)},
         "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
     }

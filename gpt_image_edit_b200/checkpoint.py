@@ -4,6 +4,8 @@ Directory layouts read (those the reference's `from_pretrained` calls consume, c
   flux_path/transformer/*.safetensors        diffusers FluxTransformer2DModel keys
   flux_path/vae/*.safetensors                diffusers AutoencoderKL keys
   flux_path/scheduler/scheduler_config.json  FlowMatchEulerDiscreteScheduler config
+  flux_path/text_encoder/*.safetensors       transformers CLIPTextModel keys (+ config.json), tokenizer/ beside it
+  flux_path/text_encoder_2/*.safetensors     transformers T5EncoderModel keys (+ config.json), tokenizer_2/ beside it
   model_path/*.safetensors                   Univa checkpoint: visual.*, model.*, denoise_tower.denoiser.*,
                                              denoise_tower.denoise_projector.{0,2}.*  (train_denoiser.py:112-115)
   model_path/task_head_final.pt              cli.py:49
@@ -63,6 +65,37 @@ def load_pipeline_components(flux_path, device="cuda"):
         scfg = {k: raw[k] for k in ("num_train_timesteps", "shift", "use_dynamic_shifting", "base_shift", "max_shift",
                                     "base_image_seq_len", "max_image_seq_len") if k in raw}
     return vae, FlowMatchEulerDiscreteScheduler(**scfg)
+
+
+def _tokenizer(directory, cls_name):
+    """Local-files tokenizer (transformers) when the directory exists; None otherwise (no network here)."""
+    if not Path(directory).is_dir():
+        return None
+    import transformers
+
+    return getattr(transformers, cls_name).from_pretrained(str(directory), local_files_only=True)
+
+
+def load_text_encoders(flux_path, device="cuda"):
+    """-> (clip, clip_tokenizer, t5, t5_tokenizer) from the FLUX.1 directory layout the reference's
+    `FluxKontextPipeline.from_pretrained` reads (cli.py:64-76); a missing sub-directory yields None."""
+    from .text_encoders import B200CLIPTextModel, B200T5Encoder, CLIPTextConfig, T5EncoderConfig
+
+    root = Path(flux_path)
+    clip = t5 = None
+    if (root / "text_encoder").is_dir():
+        raw = json.loads((root / "text_encoder" / "config.json").read_text()) if (root / "text_encoder" / "config.json").exists() else {}
+        keys = ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                "max_position_embeddings", "layer_norm_eps", "eos_token_id")
+        clip = B200CLIPTextModel(CLIPTextConfig(**{k: raw[k] for k in keys if k in raw}), device=device)
+        clip.load_state_dict(load_state_dict_from_dir(root / "text_encoder"))
+    if (root / "text_encoder_2").is_dir():
+        raw = json.loads((root / "text_encoder_2" / "config.json").read_text()) if (root / "text_encoder_2" / "config.json").exists() else {}
+        keys = ("vocab_size", "d_model", "d_kv", "num_heads", "d_ff", "num_layers", "relative_attention_num_buckets",
+                "relative_attention_max_distance", "layer_norm_epsilon")
+        t5 = B200T5Encoder(T5EncoderConfig(**{k: raw[k] for k in keys if k in raw}), device=device)
+        t5.load_state_dict(load_state_dict_from_dir(root / "text_encoder_2"))
+    return clip, _tokenizer(root / "tokenizer", "CLIPTokenizer"), t5, _tokenizer(root / "tokenizer_2", "T5TokenizerFast")
 
 
 def load_flux_transformer(directory, device="cuda", prefix: str = ""):

@@ -114,8 +114,36 @@ class FluxKontextPipeline:
         one handed in, as in the reference."""
         from .checkpoint import load_pipeline_components
 
-        vae, scheduler = load_pipeline_components(flux_path, device=getattr(transformer, "device", "cuda"))
-        return cls(transformer=transformer, vae=vae, scheduler=scheduler)
+        from .checkpoint import load_text_encoders
+
+        dev = getattr(transformer, "device", "cuda")
+        vae, scheduler = load_pipeline_components(flux_path, device=dev)
+        clip, tok, t5, tok2 = load_text_encoders(flux_path, device=dev)
+        return cls(transformer=transformer, vae=vae, scheduler=scheduler, text_encoder=clip, tokenizer=tok,
+                   text_encoder_2=t5, tokenizer_2=tok2)
+
+    tokenizer_max_length = 77
+
+    def encode_prompt(self, prompt, prompt_2=None, device=None, num_images_per_prompt: int = 1, prompt_embeds=None,
+                      pooled_prompt_embeds=None, max_sequence_length: int = 512, lora_scale=None):
+        """(prompt_embeds [B*n, L, 4096], pooled [B*n, 768], text_ids [L, 3]) — reference flux_pipeline.py:361-440:
+        `prompt` goes to CLIP (pooled output only), `prompt_2 or prompt` to T5."""
+        from .text_encoders import _encode_prompt_with_clip, _encode_prompt_with_t5
+
+        device = device or self._execution_device
+        if prompt_embeds is None:
+            if self.text_encoder is None or self.text_encoder_2 is None or self.tokenizer is None or self.tokenizer_2 is None:
+                raise ValueError("string prompts need text_encoder/tokenizer (CLIP) and text_encoder_2/tokenizer_2 (T5); "
+                                 "this pipeline was built without them — pass prompt_embeds + pooled_prompt_embeds")
+            prompt = [prompt] if isinstance(prompt, str) else prompt
+            prompt_2 = prompt_2 or prompt
+            pooled_prompt_embeds = _encode_prompt_with_clip(self.text_encoder, self.tokenizer, prompt, device=device,
+                                                            num_images_per_prompt=num_images_per_prompt)
+            prompt_embeds = _encode_prompt_with_t5(self.text_encoder_2, self.tokenizer_2, max_sequence_length, prompt_2,
+                                                   num_images_per_prompt, device)
+        dtype = self.text_encoder.dtype if self.text_encoder is not None else self.transformer.dtype
+        text_ids = torch.zeros(prompt_embeds.shape[1], 3, device=device, dtype=dtype)
+        return prompt_embeds, pooled_prompt_embeds, text_ids
 
     def to(self, *a, **k):
         for comp in (self.transformer, self.vae):
@@ -190,9 +218,17 @@ class FluxKontextPipeline:
                  output_type: str = "pil", return_dict: bool = True, joint_attention_kwargs=None,
                  callback_on_step_end: Optional[Callable] = None, callback_on_step_end_tensor_inputs=("latents",),
                  max_sequence_length: int = 512, max_area: int = 1024 ** 2, _auto_resize: bool = True):
-        if prompt is not None or prompt_embeds is None or pooled_prompt_embeds is None:
-            raise ValueError("this pipeline is driven with `prompt_embeds` + `pooled_prompt_embeds` (as univa.serve.cli "
-                             "does, reference cli.py:239-248); string prompts need the T5/CLIP encoders")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError("Cannot forward both `prompt` and `prompt_embeds`. Please make sure to only forward one of the two.")
+        if prompt_embeds is not None and pooled_prompt_embeds is None:
+            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+        if prompt_embeds is None:
+            if prompt is None:
+                raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both undefined.")
+            # string prompts: CLIP pooled + T5 hidden states through the libb2f encoders (reference :925-944)
+            prompt_embeds, pooled_prompt_embeds, _ = self.encode_prompt(
+                prompt, prompt_2, device=self._execution_device, num_images_per_prompt=1,
+                max_sequence_length=max_sequence_length)
         if true_cfg_scale > 1 and negative_prompt_embeds is not None:
             raise NotImplementedError("true-CFG second forward (reference :1080-1095) is off by default and not built")
         height = height or self.default_sample_size * self.vae_scale_factor

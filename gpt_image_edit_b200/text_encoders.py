@@ -194,7 +194,7 @@ class B200T5Encoder(_Base):
             elif k.endswith("qkv.w"):
                 v = t.view(3, c.num_heads, HP, c.d_model)
                 v[:, :, : c.d_kv] = (torch.randn(3, c.num_heads, c.d_kv, c.d_model, device=self._dev, generator=g) * std).to(torch.bfloat16)
-            elif k.endswith("o.w"):
+            elif k.endswith(".o.w"):
                 v = t.view(c.d_model, c.num_heads, HP)
                 v[:, :, : c.d_kv] = (torch.randn(c.d_model, c.num_heads, c.d_kv, device=self._dev, generator=g) * std).to(torch.bfloat16)
             elif k == "rel_bias":
@@ -321,7 +321,7 @@ class B200CLIPTextModel(_Base):
                 t.view(3, H, HP, d)[:, :, :hd] = rnd((3, H, hd, d))
             elif k.endswith("qkv.b"):
                 t.view(3, H, HP)[:, :, :hd] = rnd((3, H, hd))
-            elif k.endswith("o.w"):
+            elif k.endswith(".o.w"):
                 t.view(d, H, HP)[:, :, :hd] = rnd((d, H, hd))
             elif t.dim() == 1 and k.endswith(".w"):
                 t.fill_(1.0)

@@ -52,3 +52,49 @@ def test_checkpoint_roundtrip_through_safetensors(tmp_path):
     assert all(torch.equal(sa[k], sb[k]) for k in sa)
     assert sa["encoder.conv_in.weight"].shape == (64, 3, 3, 3)          # diffusers OIHW layout at the boundary
     assert sched.config.max_shift == 1.15
+
+
+def test_text_encoder_checkpoints_and_string_prompts(tmp_path):
+    """FLUX.1 directory layout round trip for text_encoder / text_encoder_2, then a string-prompt pipeline call
+    (reference flux_pipeline.py:925-944) that must equal the prompt_embeds-driven call with the same encoders."""
+    import json
+
+    from gpt_image_edit_b200 import checkpoint as ck
+    from gpt_image_edit_b200.flux_transformer import B200FluxTransformer2DModel, FluxTransformerConfig
+    from gpt_image_edit_b200.pipeline import FluxKontextPipeline
+    from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    from gpt_image_edit_b200.text_encoders import (B200CLIPTextModel, B200T5Encoder, CLIPTextConfig, SyntheticTokenizer,
+                                                   T5EncoderConfig, encode_prompt)
+    from gpt_image_edit_b200.vae import B200AutoencoderKL, VaeConfig
+
+    ccfg = dict(vocab_size=200, hidden_size=256, intermediate_size=512, num_hidden_layers=1, num_attention_heads=4)
+    tcfg = dict(vocab_size=128, d_model=256, d_kv=64, num_heads=4, d_ff=512, num_layers=1)
+    clip = B200CLIPTextModel(CLIPTextConfig(**ccfg)).randomize_(5)
+    t5 = B200T5Encoder(T5EncoderConfig(**tcfg)).randomize_(6)
+    ck.save_state_dict(clip.state_dict(), tmp_path / "text_encoder", "model.safetensors")
+    ck.save_state_dict(t5.state_dict(), tmp_path / "text_encoder_2", "model.safetensors")
+    (tmp_path / "text_encoder" / "config.json").write_text(json.dumps(ccfg))
+    (tmp_path / "text_encoder_2" / "config.json").write_text(json.dumps(tcfg))
+    clip2, tok, t52, tok2 = ck.load_text_encoders(tmp_path)
+    assert tok is None and tok2 is None                       # no tokenizer directories were written
+    toks = [SyntheticTokenizer.clip(200), SyntheticTokenizer.t5(128)]
+    e1, p1 = encode_prompt([clip, t5], toks, "turn the car blue", 32, "cuda")
+    e2, p2 = encode_prompt([clip2, t52], toks, "turn the car blue", 32, "cuda")
+    assert torch.equal(e1, e2) and torch.equal(p1, p2) and e1.shape == (1, 32, 256) and p1.shape == (1, 256)
+
+    tr = B200FluxTransformer2DModel(FluxTransformerConfig(num_layers=1, num_single_layers=1, attention_head_dim=128,
+                                                          num_attention_heads=2, joint_attention_dim=256,
+                                                          pooled_projection_dim=256)).randomize_(3)
+    vae = B200AutoencoderKL(VaeConfig(block_out_channels=(64, 128, 256, 256))).randomize_(4)
+    pipe = FluxKontextPipeline(transformer=tr, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler(), text_encoder=clip2,
+                               tokenizer=toks[0], text_encoder_2=t52, tokenizer_2=toks[1])
+    noise = torch.randn(1, 64, 64, generator=torch.Generator().manual_seed(42)).bfloat16().cuda()
+    kw = dict(height=128, width=128, num_inference_steps=2, max_area=128 * 128, output_type="latent")
+    a = pipe(prompt="turn the car blue", max_sequence_length=32, latents=noise.clone(), **kw).images
+    b = pipe(prompt_embeds=e1, pooled_prompt_embeds=p1, latents=noise.clone(), **kw).images
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError, match="Cannot forward both"):
+        pipe(prompt="x", prompt_embeds=e1, pooled_prompt_embeds=p1, **kw)
+    bare = FluxKontextPipeline(transformer=tr, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler())
+    with pytest.raises(ValueError, match="string prompts need"):
+        bare(prompt="x", **kw)

@@ -10,8 +10,9 @@ Differences, all forced by this environment and all explicit:
     gpt_image_edit_b200.checkpoint read the reference's checkpoint directories (safetensors).
   * one VLM prefill per turn instead of the reference's two identical ones (cli.py:200 and :211):
     `hidden_states[-1]` of the first equals the pre-MLP2 tensor of the second.
-  * T5-XXL / CLIP-L prompt encoders are SURVEY.md §8f "next": with `--synthetic` their outputs are
-    seeded stand-ins of the right shape; the text-reply branch (`model.generate`) is not built.
+  * with `--synthetic` the T5-XXL / CLIP-L encoders carry seeded random weights and the prompt is
+    tokenised by `SyntheticTokenizer` (no vocabulary files offline); the text-reply branch
+    (`model.generate`) is not built.
   * `--prompt/--image/--output` run one non-interactive turn (the reference is REPL-only).
 """
 from __future__ import annotations
@@ -26,6 +27,8 @@ from gpt_image_edit_b200 import ops
 from gpt_image_edit_b200.image_io import image_to_condition_tensor, qwen_pixel_values, resize_u8
 from gpt_image_edit_b200.pipeline import FluxKontextPipeline
 from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
+from gpt_image_edit_b200.text_encoders import (B200CLIPTextModel, B200T5Encoder, CLIPTextConfig, SyntheticTokenizer,
+                                               T5EncoderConfig, encode_prompt)
 from gpt_image_edit_b200.vae import B200AutoencoderKL
 from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig, UnivaQwen2p5VLForConditionalGeneration
 from univa.utils.anyres_util import dynamic_resize
@@ -70,12 +73,20 @@ def load_main_model_and_processor(model_path, device, synthetic=False, small=Fal
     return model, head, None
 
 
-def load_pipe(denoiser, flux_path, device, synthetic=False):
+def load_pipe(denoiser, flux_path, device, synthetic=False, small=False):
+    """-> (pipe, [clip_tokenizer, t5_tokenizer], [clip, t5])  (reference cli.py:58-76)."""
     if not synthetic:
         pipe = FluxKontextPipeline.from_pretrained(flux_path, transformer=denoiser, torch_dtype=torch.bfloat16)
-        return pipe, None, None
-    vae = B200AutoencoderKL(device=device).randomize_(seed=1)
-    return FluxKontextPipeline(transformer=denoiser, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler()), None, None
+    else:
+        vae = B200AutoencoderKL(device=device).randomize_(seed=1)
+        ccfg = CLIPTextConfig(num_hidden_layers=2) if small else CLIPTextConfig()
+        tcfg = T5EncoderConfig(num_layers=1) if small else T5EncoderConfig()
+        pipe = FluxKontextPipeline(transformer=denoiser, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler(),
+                                   text_encoder=B200CLIPTextModel(ccfg, device=device).randomize_(seed=20),
+                                   tokenizer=SyntheticTokenizer.clip(ccfg.vocab_size),
+                                   text_encoder_2=B200T5Encoder(tcfg, device=device).randomize_(seed=21),
+                                   tokenizer_2=SyntheticTokenizer.t5(tcfg.vocab_size))
+    return pipe, [pipe.tokenizer, pipe.tokenizer_2], [pipe.text_encoder, pipe.text_encoder_2]
 
 
 def update_size(shapes, anyres="any_11ratio", anchor_pixels=1024 * 1024):
@@ -98,7 +109,8 @@ def synthetic_chat_tokens(n_image_tokens: int, n_text: int = 24, vocab: int = 15
 
 
 @torch.no_grad()
-def run_turn(args, model, task_head, pipe, image_u8: np.ndarray | None, text: str, device):
+def run_turn(args, model, task_head, pipe, image_u8: np.ndarray | None, text: str, device, tokenizers=None,
+             text_encoders=None):
     shapes = [(image_u8.shape[1], image_u8.shape[0])] if image_u8 is not None else []
     new_h, new_w = (args.height, args.width) if args.no_auto_hw or not shapes else \
         update_size(shapes, "any_11ratio", anchor_pixels=args.height * args.width)
@@ -115,13 +127,9 @@ def run_turn(args, model, task_head, pipe, image_u8: np.ndarray | None, text: st
     if not (task[0] < task[1]):
         raise NotImplementedError("the text-reply branch (model.generate, reference cli.py:256-267) is outside the hot path")
     lvlm_embeds = model.denoise_tower.denoise_projector(hidden)                          # MLP2 -> [1, L, 4096]
-    g = torch.Generator(device=device).manual_seed(seed + 1)
-    pooled = torch.randn(1, 768, device=device, generator=g).bfloat16()                 # CLIP-L stand-in (§8f)
-    if not args.no_joint_with_t5:
-        t5 = torch.randn(1, 256, 4096, device=device, generator=g).bfloat16()           # T5-XXL stand-in (§8f)
-        prompt_embeds = torch.cat([lvlm_embeds, t5], dim=1)
-    else:
-        prompt_embeds = lvlm_embeds
+    # [T5 ‖ CLIP] on the libb2f encoders; an empty T5 prompt under --no_joint_with_t5 (reference cli.py:221-234)
+    t5_embeds, pooled = encode_prompt(text_encoders, tokenizers, text if not args.no_joint_with_t5 else "", 256, device, 1)
+    prompt_embeds = lvlm_embeds if args.no_joint_with_t5 else torch.cat([lvlm_embeds, t5_embeds], dim=1)
     cond = None if image_u8 is None else image_to_condition_tensor(image_u8).to(device)
     return pipe(image=cond, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled, height=new_h, width=new_w,
                 num_inference_steps=args.num_inference_steps, guidance_scale=args.guidance_scale,
@@ -134,14 +142,14 @@ def main(args):
         raise SystemExit("univa.serve.cli runs on a B200 through libb2f; there is no CPU path")
     device = torch.device("cuda")
     model, task_head, _ = load_main_model_and_processor(args.model_path, device, args.synthetic, args.small)
-    pipe, _, _ = load_pipe(model.denoise_tower.denoiser, args.flux_path, device, args.synthetic)
+    pipe, tokenizers, text_encoders = load_pipe(model.denoise_tower.denoiser, args.flux_path, device, args.synthetic, args.small)
     from PIL import Image
 
     def load(path):
         return None if not path else np.asarray(Image.open(path).convert("RGB"))
 
     if args.prompt is not None or args.image is not None:
-        img = run_turn(args, model, task_head, pipe, load(args.image), args.prompt or "", device)
+        img = run_turn(args, model, task_head, pipe, load(args.image), args.prompt or "", device, tokenizers, text_encoders)
         img.save(args.output)
         print(f"Assistant: generate image at {args.output}")
         return
@@ -156,7 +164,7 @@ def main(args):
         urls = [u.strip() for u in img_input.split(",") if u.strip()]
         if len(urls) > 1:
             print("only one context image per edit is supported (as in the reference pipeline, SURVEY.md §3.1)")
-        out = run_turn(args, model, task_head, pipe, load(urls[0]) if urls else None, txt, device)
+        out = run_turn(args, model, task_head, pipe, load(urls[0]) if urls else None, txt, device, tokenizers, text_encoders)
         path = os.path.join(os.getcwd(), f"output_{k}.png")
         out.save(path)
         k += 1
