@@ -463,10 +463,16 @@ struct Gemm2Cfg {
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const GemmParams p) {
+// CL = CTAs per cluster: 2 = one CTA pair; 4 = two CTA pairs side by side in N (a 256 x 512 super tile) that
+// SHARE their A rows: each CTA fetches a 64-row slice of its 128 A rows and TMA-multicasts it to the CTA of the
+// same half in the other pair, so a k-step costs 24 KB of L2->SM traffic per CTA instead of 32 KB (the pair
+// kernel runs at the L2->SM bandwidth cap: ncu shows ~11.6 TB/s of xbar2l1tex reads at 75 % tensor activity).
+// A stage may be overwritten only when BOTH pairs have consumed it, so every CTA's `empty` barrier takes one
+// multicast commit from each pair leader.
+template <int CL>
+__device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p) {
   using Cfg = Gemm2Cfg;
+  constexpr int PAIRS = CL / 2;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -479,19 +485,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;        // half of the pair tile this CTA owns
+  const int pc = int(crank >> 1);         // pair inside the cluster
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
+  const int pair = blockIdx.x / CL;       // work unit index: one (super) tile per cluster
+  const int num_pairs = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(tmA);
+    tma_prefetch_desc(tmB);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 2);   // one arrive per CTA's producer (+ both CTAs' TMA bytes)
-      mbar_init(&empty_bar[i], 1);  // one multicast commit
+      mbar_init(&empty_bar[i], PAIRS);  // one multicast commit per pair leader
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -519,6 +527,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int t = pair; t < num_tiles; t += num_pairs) {
         int m_blk, n_blk;
         tile_coords(p, t, m_blk, n_blk);
+        n_blk = n_blk * PAIRS + pc;
         const int bb = m_blk / p.m_blocks_per_batch;
         const int mb = m_blk - bb * p.m_blocks_per_batch;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -529,8 +538,15 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           else
             mbar_arrive_cta0(&full_bar[stage]);
-          tma_load_3d_2cta(sa, &tmA, &full_bar[stage], kb * BLOCK_K, mb * 256 + int(rank) * BLOCK_M, bb);
-          tma_load_2d_2cta(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN + int(rank) * (BN / 2));
+          if (CL == 2) {
+            tma_load_3d_2cta(sa, tmA, &full_bar[stage], kb * BLOCK_K, mb * 256 + int(rank) * BLOCK_M, bb);
+          } else {
+            // 64-row slice `pc` of this half's A rows, to the same smem offset of both CTAs holding this half
+            tma_load_3d_2cta_mc(sa + pc * (Cfg::A_BYTES / 2), tmA, &full_bar[stage], kb * BLOCK_K,
+                                mb * 256 + int(rank) * BLOCK_M + pc * (BLOCK_M / 2), bb,
+                                uint16_t((1u << rank) | (1u << (2 + rank))));
+          }
+          tma_load_2d_2cta(sb, tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN + int(rank) * (BN / 2));
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -560,8 +576,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
               umma_ss_2cta(d_tmem, da + uint64_t((k * UMMA_K * 2) >> 4), db + uint64_t((k * UMMA_K * 2) >> 4),
                            idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_2cta(&empty_bar[stage]);
-            if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[as]);
+            umma_commit_mc(&empty_bar[stage], uint16_t((1u << CL) - 1));
+            if (kb == num_kb - 1) umma_commit_mc(&tmem_full[as], uint16_t(3u << (2 * pc)));
           }
           __syncwarp();
           if (++stage == Cfg::STAGES) {
@@ -583,6 +599,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int t = pair; t < num_tiles; t += num_pairs) {
       int m_blk, n_blk;
       tile_coords(p, t, m_blk, n_blk);
+      n_blk = n_blk * PAIRS + pc;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int bidx = m_blk / p.m_blocks_per_batch;
@@ -609,15 +626,33 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const GemmParams p) {
+  gemm_pair_body<2>(&tmA, &tmB, p);
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_4cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const GemmParams p) {
+  gemm_pair_body<4>(&tmA, &tmB, p);
+}
+
+static int pair_kernel_attrs_once() {
+  static int rc = -1;
+  if (rc >= 0) return rc;
+  cudaError_t e = cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Gemm2Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_err(e, "gemm 2cta smem attribute");
+  e = cudaFuncSetAttribute(gemm_bf16_4cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_err(e, "gemm 4cta smem attribute");
+  rc = B2F_OK;
+  return rc;
+}
+
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_err(e, "gemm 2cta smem attribute");
-    attr_set = true;
-  }
+  if (int rc = pair_kernel_attrs_once()) return rc;
   p.m_blocks_per_batch = (p.M + 255) / 256;
   p.num_m_blocks = p.batch * p.m_blocks_per_batch;
   p.num_n_blocks = (p.N + Cfg::BN - 1) / Cfg::BN;
@@ -631,6 +666,49 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams 
            2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("gemm_bf16_2cta_kernel");
+  return B2F_OK;
+}
+
+// co-resident 4-CTA clusters of the quad kernel (a GPC holds floor(SMs_in_GPC / 4) of them), queried once
+static int max_quad_clusters() {
+  static int n = -1;
+  if (n >= 0) return n;
+  if (pair_kernel_attrs_once() != B2F_OK) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(4 * 64, 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Gemm2Cfg::SMEM_BYTES;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 4;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int c = 0;
+  if (cudaOccupancyMaxActiveClusters(&c, gemm_bf16_4cta_kernel, &cfg) != cudaSuccess || c <= 0) {
+    cudaGetLastError();
+    c = 0;
+  }
+  n = c;
+  return n;
+}
+
+int launch_gemm_4cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  p.m_blocks_per_batch = (p.M + 255) / 256;
+  p.num_m_blocks = p.batch * p.m_blocks_per_batch;
+  p.num_n_blocks = (p.N + 2 * Cfg::BN - 1) / (2 * Cfg::BN);   // 512-column super tiles
+  p.panel_n = 8;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int max_clusters = max_quad_clusters();
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  prof_begin(KC_GEMM, stream);
+  gemm_bf16_4cta_kernel<<<4 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * p.K,
+           2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("gemm_bf16_4cta_kernel");
   return B2F_OK;
 }
 
@@ -714,12 +792,15 @@ static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* 
   static const int mode_2cta = [] { const char* v = getenv("B2F_GEMM_2CTA"); return v ? atoi(v) : B2F_GEMM_2CTA_DEFAULT; }();
   const long long pair_tiles = (long long)batch * ((M + 255) / 256) * ((N + 255) / 256);
   if (mode_2cta && N >= 256 && pair_tiles >= device_info().num_sms / 2) {
+    // mode 2: 4-CTA clusters (two pairs sharing A by TMA multicast) when there is at least a wave of super tiles
+    const bool quad = mode_2cta == 2 && N >= 512 && max_quad_clusters() > 0 &&
+                      (long long)batch * ((M + 255) / 256) * ((N + 511) / 512) >= max_quad_clusters();
     int rc2 = make_tmap_3d_rows(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)lda,
-                                batch > 1 ? (uint64_t)a_bs : (uint64_t)M * lda);
+                                batch > 1 ? (uint64_t)a_bs : (uint64_t)M * lda, quad ? 64 : 128);
     if (rc2 != B2F_OK) return rc2;
     rc2 = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, BLOCK_K);
     if (rc2 != B2F_OK) return rc2;
-    return launch_gemm_2cta(tmA, tmB, p, stream);
+    return quad ? launch_gemm_4cta(tmA, tmB, p, stream) : launch_gemm_2cta(tmA, tmB, p, stream);
   }
   int rc = make_tmap_3d_rows(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)lda,
                              batch > 1 ? (uint64_t)a_bs : (uint64_t)M * lda);

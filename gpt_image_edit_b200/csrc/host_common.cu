@@ -134,12 +134,12 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 }
 
 int make_tmap_3d_rows(CUtensorMap* out, const void* gptr, uint64_t width, uint64_t rows,
-                      uint64_t batch, uint64_t ld_elems, uint64_t batch_stride_elems) {
+                      uint64_t batch, uint64_t ld_elems, uint64_t batch_stride_elems, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return B2F_ERR_CUDA;
   cuuint64_t dims[3] = {width, rows, batch};
   cuuint64_t strides[2] = {ld_elems * 2, batch_stride_elems * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -24,7 +24,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_
 // 3-D bf16 tensor map over [batch, rows, width] with box [1, 128, 64] (attention Q/K/V tiles):
 // out-of-range rows are zero-filled per batch item.
 int make_tmap_3d_rows(CUtensorMap* out, const void* gptr, uint64_t width, uint64_t rows,
-                      uint64_t batch, uint64_t ld_elems, uint64_t batch_stride_elems);
+                      uint64_t batch, uint64_t ld_elems, uint64_t batch_stride_elems, uint32_t box_rows = 128);
 // 4-D bf16 tensor map for NHWC activations: global [n, h, w, c], box [1, box_h, box_w, box_c].
 // `stride` (1 or 2) is the traversal stride in h and w: the box still delivers box_h x box_w pixels.
 int make_tmap_4d_bf16(CUtensorMap* out, const void* gptr, uint64_t n, uint64_t h, uint64_t w,

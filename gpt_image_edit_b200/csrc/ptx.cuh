@@ -236,6 +236,17 @@ __device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const CUtensorM
       "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// multicast variant: the box lands at the same smem offset of every CTA in `mask`; each destination's bytes are
+// counted on the barrier (same offset) of the even CTA of ITS pair
+__device__ __forceinline__ void tma_load_3d_2cta_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                                    int32_t c0, int32_t c1, int32_t c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask),
+      "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]; issued by CTA 0 only
 __device__ __forceinline__ void umma_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                              uint32_t idesc, uint32_t accumulate) {
@@ -250,6 +261,13 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask` (cluster ranks)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
 
