@@ -174,6 +174,7 @@ class B200Qwen2p5VL(torch.nn.Module):
             W[p + "gu.w"] = z(2 * tc.intermediate_size, d)
             W[p + "down.w"] = z(d, tc.intermediate_size)
         W["model.norm"] = o(d)
+        W["lm_head"] = z(tc.vocab_size, d)                    # text-reply branch (generate)
         for k, t in W.items():
             self.register_buffer("w__" + k.replace(".", "__"), t, persistent=False)
 
@@ -231,7 +232,12 @@ class B200Qwen2p5VL(torch.nn.Module):
             W[p + "gu.w"][I:].copy_(g(s + "mlp.up_proj.weight"))
             W[p + "down.w"].copy_(g(s + "mlp.down_proj.weight"))
         W["model.norm"].copy_(g("model.norm.weight"))
-        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+        missing = []
+        if "lm_head.weight" in sd:
+            W["lm_head"].copy_(g("lm_head.weight"))
+        else:
+            missing.append("lm_head.weight")                 # only the text-reply branch needs it
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=[])
 
     @torch.no_grad()
     def randomize_(self, seed: int = 0, std: float = 0.02):
@@ -331,8 +337,111 @@ class B200Qwen2p5VL(torch.nn.Module):
 
     # ------------------------------------------------------------------ decoder prefill
     @torch.no_grad()
+    def _rope_tables(self, pos):
+        """M-RoPE cos/sin for position ids [3, B, L]: fp32 angles, values rounded to bf16 (transformers casts the
+        tables to the model dtype), flattened to [B*L, head_dim] fp32 on the device."""
+        tc, hd = self.tc, self.thd
+        inv = 1.0 / (tc.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+        freqs = pos.cpu()[:, :, :, None].float() * inv[None, None, None, :]           # [3,B,L,hd/2]
+        emb = torch.cat((freqs, freqs), dim=-1)
+        sec = list(tc.mrope_section) * 2
+        pick = lambda t: torch.cat([m[i % 3] for i, m in enumerate(t.split(sec, dim=-1))], dim=-1)
+        n = pos.shape[1] * pos.shape[2]
+        cos = pick(emb.cos()).bfloat16().float().reshape(n, hd).to(self._dev).contiguous()
+        sin = pick(emb.sin()).bfloat16().float().reshape(n, hd).to(self._dev).contiguous()
+        return cos, sin
+
+    def _decoder(self, x, cos, sin, B, L, kv_cache=None, past: int = 0):
+        """The 28 decoder layers + final norm on x [B*L, hidden] (updated in place).  With `kv_cache`
+        ([layers, 2, B, Lmax, Hkv, head_dim]) the post-RoPE K and V of these L tokens are stored at
+        [past, past+L) and attention runs over the cached prefix as well (L == 1: decode step)."""
+        tc, W, hd = self.tc, self.W, self.thd
+        nq, nkv = tc.num_attention_heads, tc.num_key_value_heads
+        o = torch.empty((B * L, nq * hd), device=self._dev, dtype=torch.bfloat16)
+        if past and L != 1:
+            raise _lib.B2FError("chunked prefill is not implemented: use past == 0 (prefill) or one new token (decode)")
+        for i in range(tc.num_hidden_layers):
+            p = f"model.layers.{i}."
+            xn = ops.rmsnorm(x, W[p + "ln1"], eps=tc.rms_norm_eps)
+            qkv = ops.linear(xn, W[p + "qkv.w"], W[p + "qkv.b"])
+            ops.rope_half_(qkv, nq + nkv, hd, cos, sin, fp32_math=False)
+            q = qkv[:, : nq * hd].unflatten(1, (nq, hd)).unflatten(0, (B, L))
+            k = qkv[:, nq * hd: (nq + nkv) * hd].unflatten(1, (nkv, hd)).unflatten(0, (B, L))
+            v = qkv[:, (nq + nkv) * hd:].unflatten(1, (nkv, hd)).unflatten(0, (B, L))
+            if kv_cache is not None:
+                kv_cache[i, 0, :, past:past + L].copy_(k)
+                kv_cache[i, 1, :, past:past + L].copy_(v)
+            if past:
+                # decode: the new token attends to every cached position (no mask needed); one launch per sequence
+                # because the cache's batch pitch (Lmax rows) differs from the attended length
+                for b in range(B):
+                    ops.attention(q[b:b + 1], kv_cache[i, 0, b:b + 1, :past + 1], kv_cache[i, 1, b:b + 1, :past + 1],
+                                  out=o.unflatten(0, (B, L))[b:b + 1])
+            else:
+                ops.attention(q, k, v, out=o.unflatten(0, (B, L)), causal=True)
+            ops.linear(o, W[p + "o.w"], None, epilogue=ops.EPI_RESID, resid=x, out=x)
+            xn = ops.rmsnorm(x, W[p + "ln2"], eps=tc.rms_norm_eps)
+            gu = ops.linear(xn, W[p + "gu.w"])
+            a = ops.swiglu(gu, tc.intermediate_size)
+            ops.linear(a, W[p + "down.w"], None, epilogue=ops.EPI_RESID, resid=x, out=x)
+        return ops.rmsnorm(x, W["model.norm"], eps=tc.rms_norm_eps)
+
+    def lm_logits(self, hidden):
+        """lm_head on [n, hidden] -> [n, vocab] bf16 (tcgen05 GEMM; vocab rows stream once from HBM)."""
+        return ops.linear(hidden.reshape(-1, self.tc.hidden_size), self.W["lm_head"])
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor, pixel_values=None, attention_mask=None, image_grid_thw=None,
+                 max_new_tokens: int = 128, eos_token_id=(151645, 151643), pad_token_id: int = 151643,
+                 repetition_penalty: float = 1.0, forced_tokens=None, output_scores: bool = False, **kw):
+        """Greedy text reply with a KV cache (the `model.generate(**inputs, max_new_tokens=128)` call of the
+        reference's understanding branch, univa/serve/cli.py:256-267): prefill through the same kernels as
+        the conditioning path, then one token per step — M = B GEMMs (weight-streaming, HBM-bound), single-query
+        attention over the cache, lm_head, argmax.  Returns ids [B, L + new] (prompt included, as transformers
+        does); with `output_scores` also the per-step fp32 logits.  `forced_tokens` [B, T] replaces the argmax
+        (teacher forcing for tests).  Sampling is not implemented: Qwen2.5-VL's generation_config asks for
+        temperature 1e-6, i.e. greedy up to ties; `repetition_penalty` follows transformers' processor."""
+        tc = self.tc
+        B, L = input_ids.shape
+        ids = input_ids.to(self._dev)
+        steps = int(forced_tokens.shape[1]) if forced_tokens is not None else int(max_new_tokens)
+        cache = torch.empty((tc.num_hidden_layers, 2, B, L + steps, tc.num_key_value_heads, self.thd), device=self._dev,
+                            dtype=torch.bfloat16)
+        hidden, deltas = self.forward(ids, pixel_values=pixel_values, attention_mask=attention_mask,
+                                      image_grid_thw=image_grid_thw, kv_cache=cache, return_rope_deltas=True)
+        last = hidden[:, -1]                                            # [B, hidden]
+        eos = torch.tensor(list(eos_token_id) if not isinstance(eos_token_id, int) else [eos_token_id], device=self._dev)
+        out = [ids]
+        scores = []
+        done = torch.zeros(B, dtype=torch.bool, device=self._dev)
+        seen = ids.clone()
+        for t in range(steps):
+            logits = self.lm_logits(last).float()                         # [B, vocab]
+            if repetition_penalty != 1.0:
+                g = logits.gather(1, seen)
+                logits.scatter_(1, seen, torch.where(g < 0, g * repetition_penalty, g / repetition_penalty))
+            if output_scores:
+                scores.append(logits)
+            nxt = logits.argmax(dim=-1) if forced_tokens is None else forced_tokens[:, t].to(self._dev)
+            nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
+            out.append(nxt[:, None])
+            seen = torch.cat([seen, nxt[:, None]], dim=1)
+            done = done | torch.isin(nxt, eos)
+            if forced_tokens is None and bool(done.all()):
+                break
+            if t == steps - 1:
+                break
+            # text continues on all three M-RoPE axes at (past length + delta)
+            pos = (torch.full((B, 1), L + t, dtype=torch.long) + deltas.cpu().view(B, 1))[None].expand(3, B, 1)
+            cos, sin = self._rope_tables(pos)
+            x = ops.gather_rows(self.W["model.embed_tokens"], nxt.contiguous())
+            last = self._decoder(x, cos, sin, B, 1, cache, past=L + t)
+        seq = torch.cat(out, dim=1)
+        return (seq, scores) if output_scores else seq
+
+    @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, pixel_values=None, attention_mask=None, image_grid_thw=None,
-                return_image_embeds: bool = False):
+                return_image_embeds: bool = False, kv_cache=None, return_rope_deltas: bool = False):
         """-> last hidden state after model.norm, [B, L, hidden] (what the reference feeds to MLP2)."""
         tc, W = self.tc, self.W
         if attention_mask is not None and not bool((attention_mask == 1).all()):
@@ -348,33 +457,11 @@ class B200Qwen2p5VL(torch.nn.Module):
                 raise ValueError(f"Image features and image tokens do not match: tokens: {where.numel()}, "
                                  f"features {image_embeds.shape[0]}")
             ops.scatter_rows_(x, where, image_embeds)
-        pos, _ = get_rope_index(ids, image_grid_thw if pixel_values is not None else None, attention_mask,
+        pos, deltas = get_rope_index(ids, image_grid_thw if pixel_values is not None else None, attention_mask,
                                 spatial_merge_size=self.vc.spatial_merge_size, image_token_id=tc.image_token_id,
                                 vision_start_token_id=tc.vision_start_token_id)
-        # M-RoPE tables: fp32 angles, cos/sin rounded to bf16 (transformers casts them to the model dtype)
-        hd = self.thd
-        inv = 1.0 / (tc.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
-        freqs = pos.cpu()[:, :, :, None].float() * inv[None, None, None, :]           # [3,B,L,hd/2]
-        emb = torch.cat((freqs, freqs), dim=-1)
-        sec = list(tc.mrope_section) * 2
-        pick = lambda t: torch.cat([m[i % 3] for i, m in enumerate(t.split(sec, dim=-1))], dim=-1)
-        cos = pick(emb.cos()).bfloat16().float().reshape(B * L, hd).to(self._dev).contiguous()
-        sin = pick(emb.sin()).bfloat16().float().reshape(B * L, hd).to(self._dev).contiguous()
-        nq, nkv = tc.num_attention_heads, tc.num_key_value_heads
-        o = torch.empty((B * L, nq * hd), device=self._dev, dtype=torch.bfloat16)
-        for i in range(tc.num_hidden_layers):
-            p = f"model.layers.{i}."
-            xn = ops.rmsnorm(x, W[p + "ln1"], eps=tc.rms_norm_eps)
-            qkv = ops.linear(xn, W[p + "qkv.w"], W[p + "qkv.b"])
-            ops.rope_half_(qkv, nq + nkv, hd, cos, sin, fp32_math=False)
-            q = qkv[:, : nq * hd].unflatten(1, (nq, hd)).unflatten(0, (B, L))
-            k = qkv[:, nq * hd: (nq + nkv) * hd].unflatten(1, (nkv, hd)).unflatten(0, (B, L))
-            v = qkv[:, (nq + nkv) * hd:].unflatten(1, (nkv, hd)).unflatten(0, (B, L))
-            ops.attention(q, k, v, out=o.unflatten(0, (B, L)), causal=True)
-            ops.linear(o, W[p + "o.w"], None, epilogue=ops.EPI_RESID, resid=x, out=x)
-            xn = ops.rmsnorm(x, W[p + "ln2"], eps=tc.rms_norm_eps)
-            gu = ops.linear(xn, W[p + "gu.w"])
-            a = ops.swiglu(gu, tc.intermediate_size)
-            ops.linear(a, W[p + "down.w"], None, epilogue=ops.EPI_RESID, resid=x, out=x)
-        h = ops.rmsnorm(x, W["model.norm"], eps=tc.rms_norm_eps).view(B, L, tc.hidden_size)
+        cos, sin = self._rope_tables(pos)
+        h = self._decoder(x, cos, sin, B, L, kv_cache).view(B, L, tc.hidden_size)
+        if return_rope_deltas:
+            return h, deltas
         return (h, image_embeds) if return_image_embeds else h

@@ -27,6 +27,24 @@ def test_cli_single_turn_writes_png(tmp_path):
     assert np.asarray(img).std() > 0
 
 
+def test_cli_text_reply_branch(tmp_path, capsys):
+    """The understanding branch (reference cli.py:256-267): prefill -> task head -> greedy KV-cache decode."""
+    from PIL import Image
+
+    from univa.serve import cli
+
+    rng = np.random.default_rng(1)
+    src = tmp_path / "src.png"
+    Image.fromarray(rng.integers(0, 256, size=(224, 224, 3), dtype=np.uint8)).save(src)
+    args = cli.build_parser().parse_args(["--synthetic", "--small", "--prompt", "what is in the picture?", "--image", str(src),
+                                          "--force_text_reply", "--max_new_tokens", "6"])
+    cli.main(args)
+    out = capsys.readouterr().out
+    assert "Assistant: <token ids>" in out
+    toks = out.split("<token ids>")[1].split()
+    assert 1 <= len(toks) <= 6 and all(0 <= int(t) < 152064 for t in toks)
+
+
 def test_checkpoint_roundtrip_through_safetensors(tmp_path):
     from gpt_image_edit_b200 import checkpoint as ck
     from gpt_image_edit_b200.flux_transformer import B200FluxTransformer2DModel, FluxTransformerConfig

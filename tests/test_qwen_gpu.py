@@ -22,7 +22,7 @@ def _models():
     from gpt_image_edit_b200.qwen2p5vl import B200Qwen2p5VL, QwenTextConfig, QwenVisionConfig
 
     tc = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1, intermediate_size=512,
-              vocab_size=1000)
+              vocab_size=1000, rms_norm_eps=1e-6)       # the checkpoint's value; transformers' class default is 1e-5
     vcfg = dict(depth=3, hidden_size=256, num_heads=4, intermediate_size=340, out_hidden_size=256,
                 fullatt_block_indexes=[1])
     cfg = Qwen2_5_VLConfig(
@@ -50,17 +50,24 @@ def test_vision_tower_and_prefill_match_transformers():
     grid = torch.tensor([[1, 16, 8]])                       # 128 patches -> 32 merged tokens, two 4x4 windows
     pix = torch.randn(128, 1176, generator=g)
     ids = torch.tensor([[1, 2, 3, VSTART] + [IMG] * 32 + [903] + list(range(10, 31))])
+    # M-RoPE positions follow the REFERENCE's get_rope_index (univa modeling :139-318, pinned by tests/golden/
+    # rope_index_ref.pt); transformers 5.5 computes image positions differently, so the checker is given ours
+    from gpt_image_edit_b200.qwen2p5vl import get_rope_index
+    pos, _ = get_rope_index(ids, grid, None, spatial_merge_size=2, image_token_id=IMG, vision_start_token_id=VSTART)
+    pos = pos.cuda()
     ref16 = ref.to("cuda", torch.bfloat16)
     with torch.no_grad():
         v16 = ref16.visual(pix.cuda().bfloat16(), grid_thw=grid.cuda()).pooler_output
-        h16 = ref16(input_ids=ids.cuda(), pixel_values=pix.cuda().bfloat16(), image_grid_thw=grid.cuda()).last_hidden_state
+        h16 = ref16(input_ids=ids.cuda(), pixel_values=pix.cuda().bfloat16(), image_grid_thw=grid.cuda(),
+                    position_ids=pos).last_hidden_state
     ref32 = ref.to("cuda", torch.float32)
     with torch.no_grad():
         # the checker's fp32 run uses the same bf16-rounded weights
         for p in ref32.parameters():
             p.copy_(p.bfloat16().float())
         v32 = ref32.visual(pix.cuda().bfloat16().float(), grid_thw=grid.cuda()).pooler_output
-        h32 = ref32(input_ids=ids.cuda(), pixel_values=pix.cuda().bfloat16().float(), image_grid_thw=grid.cuda()).last_hidden_state
+        h32 = ref32(input_ids=ids.cuda(), pixel_values=pix.cuda().bfloat16().float(), image_grid_thw=grid.cuda(),
+                    position_ids=pos).last_hidden_state
     v = mine.forward_visual(pix.cuda().bfloat16(), grid)
     h = mine(ids.cuda(), pixel_values=pix.cuda().bfloat16(), image_grid_thw=grid)
     ev_k, ev_t = _rel_l2(v, v32), _rel_l2(v16, v32)
@@ -98,3 +105,75 @@ def test_llm_kernels_match_eager_chains():
     o = ops.linear(a, wl, b, epilogue=ops.EPI_GELU_ERF)
     r = torch.nn.functional.gelu((a.float() @ wl.float().t() + b.float()).bfloat16().float())
     assert _rel_l2(o, r) < 6e-3
+
+
+def test_generate_kv_cache_decode_matches_transformers():
+    """Text-reply branch (reference cli.py:256-267): greedy KV-cache decode.  transformers' generate() gives the
+    token sequence and per-step logits; the libb2f decode is teacher-forced with those tokens and must reproduce
+    the logits (same 2x-of-bf16 rule, fp32 checker), pick the same token wherever the checker's top-2 margin is
+    not a numerical tie, and — run free — must emit the same reply when no step is a tie."""
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLConfig
+
+    from gpt_image_edit_b200.qwen2p5vl import B200Qwen2p5VL, QwenTextConfig, QwenVisionConfig
+
+    tc = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1, intermediate_size=512,
+              vocab_size=1000, rms_norm_eps=1e-6)       # the checkpoint's value; transformers' class default is 1e-5
+    vcfg = dict(depth=2, hidden_size=256, num_heads=4, intermediate_size=340, out_hidden_size=256, fullatt_block_indexes=[1])
+    cfg = Qwen2_5_VLConfig(
+        text_config=dict(tc, rope_parameters=dict(rope_type="default", rope_theta=1e6, mrope_section=[16, 24, 24])),
+        vision_config=vcfg, image_token_id=IMG, video_token_id=901, vision_start_token_id=VSTART, vision_end_token_id=903)
+    torch.manual_seed(1)
+    ref = hf.Qwen2_5_VLForConditionalGeneration(cfg).eval()
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+        ref.lm_head.weight.normal_(0, 0.2)          # spread the logits so that most steps have a clear winner
+    sd = {k.replace("model.language_model.", "model.").replace("model.visual.", "visual."): v.detach().to(torch.bfloat16)
+          for k, v in ref.state_dict().items()}
+    mine = B200Qwen2p5VL(QwenTextConfig(**tc, image_token_id=IMG, video_token_id=901, vision_start_token_id=VSTART),
+                         QwenVisionConfig(**vcfg))
+    assert mine.load_state_dict(sd).missing_keys == []
+
+    # text-only prompt: with images transformers 5.5 assigns different M-RoPE positions than the reference's
+    # get_rope_index (see the prefill test), and generate() cannot be handed ours
+    ids = torch.tensor([[1, 2, 3] + list(range(10, 45))])
+    steps = 12
+    ref32 = ref.to("cuda", torch.float32)
+    with torch.no_grad():
+        for p in ref32.parameters():
+            p.copy_(p.bfloat16().float())
+        gen = ref32.generate(input_ids=ids.cuda(), attention_mask=torch.ones_like(ids).cuda(), max_new_tokens=steps, min_new_tokens=steps,
+                             do_sample=False, output_scores=True, return_dict_in_generate=True, repetition_penalty=1.0,
+                             eos_token_id=None, pad_token_id=0)
+    want_tokens = gen.sequences[:, ids.shape[1]:]
+    want_logits = torch.stack(gen.scores, dim=1).float()                 # [1, steps, vocab]
+    ref16 = ref32.to(torch.bfloat16)
+    with torch.no_grad():
+        gen16 = ref16.generate(input_ids=ids.cuda(), attention_mask=torch.ones_like(ids).cuda(), max_new_tokens=steps, min_new_tokens=steps,
+                               do_sample=False, output_scores=True, return_dict_in_generate=True, repetition_penalty=1.0,
+                               eos_token_id=None, pad_token_id=0)
+    # teacher-forced libb2f decode
+    seq, scores = mine.generate(ids.cuda(), forced_tokens=want_tokens,
+                                output_scores=True, eos_token_id=(999999,))
+    got_logits = torch.stack(scores, dim=1)
+    assert torch.equal(seq[:, ids.shape[1]:], want_tokens)
+    same16 = torch.equal(gen16.sequences, gen.sequences)
+    l16 = torch.stack(gen16.scores, dim=1).float()
+    ek = _rel_l2(got_logits, want_logits)
+    et = _rel_l2(l16, want_logits) if same16 else float("nan")
+    print(f"decode logits over {steps} steps: kernel-vs-fp32 {ek:.3e}  torch-bf16-vs-fp32 {et:.3e} (bf16 run same tokens: {same16})")
+    assert ek <= (2.0 * et + 3e-3 if same16 else 2e-2)
+    top2 = want_logits.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 8 * (got_logits - want_logits).abs().max()
+    assert torch.equal(got_logits.argmax(-1)[clear], want_tokens[clear])
+    assert int(clear.sum()) >= steps // 2, "test vectors degenerate: too many ties"
+    if bool(clear.all()):
+        free = mine.generate(ids.cuda(), max_new_tokens=steps, eos_token_id=(999999,))
+        assert torch.equal(free, gen.sequences)
+    # eos handling: stop early and pad the rest of the batch row
+    eos_tok = int(want_tokens[0, 2])
+    short = mine.generate(ids.cuda(), forced_tokens=None, max_new_tokens=steps,
+                          eos_token_id=(eos_tok,))
+    if bool(clear[0, :3].all()):
+        assert short.shape[1] == ids.shape[1] + 3 and int(short[0, -1]) == eos_tok

@@ -7,10 +7,12 @@
     model.denoise_tower.denoise_projector   MLP2
     model.forward_denoiser_context()        pass-through mode used by FSDP / log_validation (:352-355)
 
-`output_type="lvlm"` (text generation with lm_head / KV-cache decode) is outside the hot path
- and raises.  One prefill serves both of cli.py's forward calls: the hidden state
-`hidden_states[-1]` the task head reads (cli.py:199-206) is exactly the pre-MLP2 tensor returned by
-`prefill_hidden()`.
+    model(..., output_type="lvlm", output_hidden_states=True)
+        -> namespace(logits [B, L, vocab], hidden_states=(last,))   what cli.py:199-206 reads for the task head
+    model.generate(input_ids, ..., max_new_tokens=128)              greedy KV-cache decode (cli.py:256-267)
+
+One prefill serves both of cli.py's forward calls: `hidden_states[-1]` of the "lvlm" call is exactly the
+pre-MLP2 tensor `prefill_hidden()` returns.
 """
 from __future__ import annotations
 
@@ -86,8 +88,15 @@ class UnivaQwen2p5VLForConditionalGeneration(torch.nn.Module):
                 vlm_residual_image_factor: float = 0.0, **kwargs):
         if not only_use_t5 and self.forward_denoiser:           # reference :352-355
             return self.denoise_tower.denoiser(**kwargs)
+        if output_type == "lvlm":
+            # the understanding branch's forward: logits + the last hidden state (after the final norm; earlier layers'
+            # states are not kept — the reference only reads hidden_states[-1], cli.py:201)
+            from types import SimpleNamespace
+            hidden = self.prefill_hidden(input_ids, pixel_values, attention_mask, image_grid_thw)
+            B, L, _ = hidden.shape
+            return SimpleNamespace(logits=self.lvlm.lm_logits(hidden).view(B, L, -1), hidden_states=(hidden,))
         if not output_type.startswith("denoise"):
-            raise B2FError('output_type="lvlm" (lm_head / generate) is outside the denoising hot path')
+            raise ValueError(f"Unknown output_type: {output_type}.")
         outputs = None
         if not only_use_t5:
             if vlm_residual_image_factor > 0.0:
@@ -102,6 +111,13 @@ class UnivaQwen2p5VLForConditionalGeneration(torch.nn.Module):
             kw["enc_attention_mask"] = attention_mask
             return self.denoise_tower(encoder_hidden_states=outputs, **kw)
         raise ValueError(f"Unknown output_type: {output_type}.")
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, attention_mask=None, pixel_values=None, image_grid_thw=None, max_new_tokens: int = 128,
+                 **kw):
+        """ids [B, L + new], prompt included (transformers' `generate` contract; reference cli.py:258)."""
+        return self.lvlm.generate(input_ids, pixel_values=pixel_values, attention_mask=attention_mask,
+                                  image_grid_thw=image_grid_thw, max_new_tokens=max_new_tokens, **kw)
 
     @contextmanager
     def forward_denoiser_context(self):                          # reference :604-621

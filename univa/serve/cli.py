@@ -12,7 +12,7 @@ Differences, all forced by this environment and all explicit:
     `hidden_states[-1]` of the first equals the pre-MLP2 tensor of the second.
   * with `--synthetic` the T5-XXL / CLIP-L encoders carry seeded random weights and the prompt is
     tokenised by `SyntheticTokenizer` (no vocabulary files offline); the text-reply branch
-    (`model.generate`) is not built.
+    (`model.generate`, greedy KV-cache decode) prints token ids when no tokenizer files are available.
   * `--prompt/--image/--output` run one non-interactive turn (the reference is REPL-only).
 """
 from __future__ import annotations
@@ -124,8 +124,14 @@ def run_turn(args, model, task_head, pipe, image_u8: np.ndarray | None, text: st
                                   attention_mask=torch.ones_like(input_ids), image_grid_thw=grid)
     assistant_vec = hidden[input_ids == ASSISTANT_TOKEN_ID][-1:]
     task = task_head(assistant_vec)[0].float()
+    if getattr(args, "force_text_reply", False):
+        task = torch.tensor([1.0, 0.0])
     if not (task[0] < task[1]):
-        raise NotImplementedError("the text-reply branch (model.generate, reference cli.py:256-267) is outside the hot path")
+        # understanding branch (reference cli.py:256-267): greedy KV-cache decode, reply = the newly generated ids
+        generated = model.generate(input_ids=input_ids, pixel_values=None if pixel_values is None else pixel_values.to(device),
+                                   attention_mask=torch.ones_like(input_ids), image_grid_thw=grid,
+                                   max_new_tokens=args.max_new_tokens)
+        return generated[0, input_ids.shape[1]:].tolist()
     lvlm_embeds = model.denoise_tower.denoise_projector(hidden)                          # MLP2 -> [1, L, 4096]
     # [T5 ‖ CLIP] on the libb2f encoders; an empty T5 prompt under --no_joint_with_t5 (reference cli.py:221-234)
     t5_embeds, pooled = encode_prompt(text_encoders, tokenizers, text if not args.no_joint_with_t5 else "", 256, device, 1)
@@ -135,6 +141,13 @@ def run_turn(args, model, task_head, pipe, image_u8: np.ndarray | None, text: st
                 num_inference_steps=args.num_inference_steps, guidance_scale=args.guidance_scale,
                 generator=torch.Generator(device=device).manual_seed(seed),
                 **({"max_area": args.max_area, "_auto_resize": False} if args.max_area else {})).images[0]
+
+
+def reply_text(token_ids, processor=None):
+    """Decoded reply when a processor / tokenizer is available (reference cli.py:261-263), else the raw ids."""
+    if processor is not None:
+        return processor.batch_decode([token_ids], skip_special_tokens=True, clean_up_tokenization_spaces=False)[0]
+    return "<token ids> " + " ".join(str(t) for t in token_ids)
 
 
 def main(args):
@@ -150,6 +163,9 @@ def main(args):
 
     if args.prompt is not None or args.image is not None:
         img = run_turn(args, model, task_head, pipe, load(args.image), args.prompt or "", device, tokenizers, text_encoders)
+        if isinstance(img, list):
+            print(f"Assistant: {reply_text(img)}")
+            return
         img.save(args.output)
         print(f"Assistant: generate image at {args.output}")
         return
@@ -165,6 +181,9 @@ def main(args):
         if len(urls) > 1:
             print("only one context image per edit is supported (as in the reference pipeline, SURVEY.md §3.1)")
         out = run_turn(args, model, task_head, pipe, load(urls[0]) if urls else None, txt, device, tokenizers, text_encoders)
+        if isinstance(out, list):
+            print(f"Assistant: {reply_text(out)}\n")
+            continue
         path = os.path.join(os.getcwd(), f"output_{k}.png")
         out.save(path)
         k += 1
@@ -187,6 +206,9 @@ def build_parser():
     p.add_argument("--small", action="store_true", help="with --synthetic: a few layers only (plumbing runs)")
     p.add_argument("--max_area", type=int, default=0, help="pass max_area to the pipeline and disable _auto_resize "
                    "(the reference always rescales to ~1 MP, SURVEY.md §0 item 8)")
+    p.add_argument("--max_new_tokens", type=int, default=128, help="text-reply branch (reference: 128)")
+    p.add_argument("--force_text_reply", action="store_true", help="with --synthetic: route the turn to the text-reply "
+                   "branch (the synthetic task head otherwise always chooses 'generate image')")
     p.add_argument("--prompt", type=str, default=None)
     p.add_argument("--image", type=str, default=None)
     p.add_argument("--output", type=str, default="output.png")
