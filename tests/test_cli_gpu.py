@@ -116,3 +116,33 @@ def test_text_encoder_checkpoints_and_string_prompts(tmp_path):
     bare = FluxKontextPipeline(transformer=tr, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler())
     with pytest.raises(ValueError, match="string prompts need"):
         bare(prompt="x", **kw)
+
+
+def test_gedit_sampling_driver_writes_strided_outputs(tmp_path, monkeypatch):
+    """The multi-GPU caller of the path (reference univa/eval/gedit/step1_gen_samples.py): as rank 1 of 2 (no process
+    group: the ranks never communicate while sampling) it must produce exactly items 1, 3 and skip existing files."""
+    import json
+
+    from PIL import Image
+
+    from univa.eval.configuration_eval import EvalConfig
+    from univa.eval.gedit import step1_gen_samples as drv
+
+    rng = np.random.default_rng(3)
+    (tmp_path / "imgs" / "en").mkdir(parents=True)
+    spec = {}
+    for i, (h, w) in enumerate([(200, 300), (256, 256), (300, 200), (240, 320)]):
+        Image.fromarray(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).save(tmp_path / "imgs" / "en" / f"{i}.png")
+        spec[f"k{i}"] = {"prompt": f"make it {i}", "id": f"en/{i}.png"}
+    (tmp_path / "gedit.json").write_text(json.dumps(spec))
+    cfg = EvalConfig(output_dir=str(tmp_path / "out"), gedit_prompt_path=str(tmp_path / "gedit.json"),
+                     gedit_image_dir=str(tmp_path / "imgs"), height=256, width=256, num_inference_steps=2, synthetic=True,
+                     small=True, joint_with_t5=True)
+    monkeypatch.setattr(drv.D, "env_world", lambda: (2, 1, 0))
+    monkeypatch.setattr(drv.D, "init_from_env", lambda **kw: (2, 1, 0))
+    assert drv.main(cfg) == 2
+    outs = sorted(p.name for p in (tmp_path / "out" / "en").iterdir())
+    assert outs == ["1.png", "3.png"]
+    im = Image.open(tmp_path / "out" / "en" / "3.png")
+    assert im.size[0] % 16 == 0 and im.size[1] % 16 == 0 and im.size[0] > im.size[1]      # 240x320 source -> landscape
+    assert drv.main(cfg) == 0                                                             # everything already exists

@@ -116,3 +116,31 @@ def test_anyres_dynamic_resize_matches_reference_semantics():
     assert dynamic_resize(512, 768) == (832, 1248)
     assert pick_ratio(600, 800, "any_11ratio") == (4, 3)
     assert compute_size(4, 3, 32, anchor_pixels=448 * 448) == (384, 512)
+
+
+def test_gedit_driver_host_logic(tmp_path):
+    """Prompt-file format, output paths, rank striding and the generation-size rule of the GEdit sampling driver
+    (reference univa/eval/gedit/step1_gen_samples.py:100-114, 228-239)."""
+    import json
+
+    from gpt_image_edit_b200 import distributed as D
+    from univa.eval.configuration_eval import EvalConfig
+    from univa.eval.gedit.step1_gen_samples import generation_size, load_items
+
+    spec = {f"k{i}": {"prompt": f"edit {i}", "id": f"en/{i}.png", "extra": 1} for i in range(7)}
+    pf = tmp_path / "gedit.json"
+    pf.write_text(json.dumps(spec))
+    items = load_items(pf, str(tmp_path / "out"))
+    assert [it[2] for it in items] == [f"k{i}" for i in range(7)]
+    assert items[3][1].endswith("out/en/3.png") and items[3][0] == "edit 3" and items[3][3] == "en/3.png"
+    parts = [D.shard(items, r, 3) for r in range(3)]
+    assert [len(p) for p in parts] == [3, 2, 2] and parts[1][0][2] == "k1" and parts[1][1][2] == "k4"
+    assert sorted(it[2] for p in parts for it in p) == sorted(spec)
+    # size rule: a multiple of 16 in both directions, area close to the anchor, aspect of the nearest listed ratio
+    for (h, w) in [(768, 1024), (1024, 1024), (500, 1500), (1365, 1024)]:
+        gh, gw = generation_size(h, w, 1024, 1024)
+        assert gh % 16 == 0 and gw % 16 == 0 and abs(gh * gw - 1024 * 1024) / (1024 * 1024) < 0.08
+        assert (gh >= gw) == (h >= w)
+    assert generation_size(1024, 1024, 512, 512) == (512, 512)
+    cfg = EvalConfig.from_mapping({"seed": 7, "gedit_image_dir": "x", "genai_prompt_path": "ignored", "joint_with_t5": True})
+    assert cfg.seed == 7 and cfg.joint_with_t5 and cfg.num_inference_steps == 32 and cfg.guidance_scale == 3.5
