@@ -42,6 +42,8 @@ def _rel_l2(a, b):
         (1, 2, 2, 1056, 1056, False),   # 256^2 config: S = 1056 = 8*128 + 32
         (1, 24, 24, 2592, 2592, False), # 512^2 config, all heads
         (1, 4, 4, 8736, 8736, False),   # C1024 sequence length (4 of 24 heads)
+        (2, 2, 2, 640, 640, False),     # CTA-pair kernel: batch > 1, second pair = one partial tile
+        (1, 4, 2, 768, 1000, False),    # CTA-pair kernel: GQA, Sq != Skv, ragged kv tail
         (1, 4, 2, 384, 384, True),      # causal + GQA (Qwen2.5-VL style)
         (2, 28, 4, 290, 290, True),     # Qwen2.5-VL-7B head layout, L=290
     ],
