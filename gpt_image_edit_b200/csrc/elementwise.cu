@@ -114,9 +114,15 @@ __global__ void __launch_bounds__(128, 6) ln_modulate_kernel(const LnModParams p
         unpack8(__ldg(reinterpret_cast<const uint4*>(sc + c * 256 + lane * 8)), a);
         unpack8(__ldg(reinterpret_cast<const uint4*>(sh + c * 256 + lane * 8)), h);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float y = bf16r((v[j] - mean) * rstd);
-          o[j] = bf16r(y * bf16r(1.0f + a[j])) + h[j];
+        for (int j = 0; j < 8; j += 2) {   // the rounding chain of the eager bf16 ops, two elements per conversion
+          float y0 = (v[j] - mean) * rstd, y1 = (v[j + 1] - mean) * rstd;
+          bf16r2(y0, y1);
+          float t0 = 1.0f + a[j], t1 = 1.0f + a[j + 1];
+          bf16r2(t0, t1);
+          float z0 = y0 * t0, z1 = y1 * t1;
+          bf16r2(z0, z1);
+          o[j] = z0 + h[j];
+          o[j + 1] = z1 + h[j + 1];
         }
         *reinterpret_cast<uint4*>(orow + c * 256 + lane * 8) = pack8(o);
       }

@@ -326,6 +326,15 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, 
 __device__ __forceinline__ float bf16r(float x) {  // round-to-nearest-even through bf16
   return __bfloat162float(__float2bfloat16_rn(x));
 }
+// The same rounding for a PAIR through one packed conversion (F2FP.BF16.PACK_AB, not an XU-pipe instruction)
+// and two ALU unpacks: the scalar F2F conversion above runs on the XU pipe (16 lanes/clk/SM) and made the
+// LN-modulate kernel XU-bound (ncu: XU 65 %, DRAM 22 %).
+__device__ __forceinline__ void bf16r2(float& a, float& b) {
+  uint32_t u;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
