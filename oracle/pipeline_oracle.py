@@ -5,6 +5,11 @@ and of diffusers 0.32.2 `FlowMatchEulerDiscreteScheduler` in pla
 dtype-agnostic, wired to the oracle transformer/VAE.  This is (a) the checker for the product
 pipeline and (b) the CPU baseline `bench.py --impl reference` times (the reference's own diffusers
 path cannot be imported here: diffusers is absent).
+
+Pin: `sample()` is bit-identical (fp32) to the reference's own `FluxKontextPipeline.__call__` executed from
+/root/reference/univa/utils/flux_pipeline.py with stand-ins for the diffusers base classes
+(tests/golden/make_pipeline_ref_golden.py -> tests/golden/pipeline_ref_loop.pt, checked by
+tests/test_oracle_cpu.py).  The scheduler arithmetic itself (diffusers, not on disk) remains unpinned by the reference.
 """
 from __future__ import annotations
 

@@ -146,3 +146,54 @@ def test_gedit_sampling_driver_writes_strided_outputs(tmp_path, monkeypatch):
     im = Image.open(tmp_path / "out" / "en" / "3.png")
     assert im.size[0] % 16 == 0 and im.size[1] % 16 == 0 and im.size[0] > im.size[1]      # 240x320 source -> landscape
     assert drv.main(cfg) == 0                                                             # everything already exists
+
+
+def test_denoise_tower_glue_and_mlp2_match_the_references_own_module():
+    """tests/golden/tower_ref.pt was produced by executing the reference's modeling_univa_denoise_tower.py with a
+    recording denoiser (tests/golden/make_tower_ref_golden.py): same forwarded keywords, same [vlm ; prefix] order, same
+    zero txt_ids, same dropped arguments; MLP2 = Linear-SiLU-Linear with the reference's weights."""
+    from pathlib import Path
+
+    from univa.models.configuration_univa_denoise_tower import UnivaDenoiseTowerConfig
+    from univa.models.modeling_univa_denoise_tower import DenoiseProjector, UnivaDenoiseTower
+
+    fx = torch.load(Path(__file__).parent / "golden" / "tower_ref.pt", weights_only=False)
+    cfg = UnivaDenoiseTowerConfig(input_hidden_size=64, output_hidden_size=32,
+                                  denoiser_config=dict(num_layers=1, num_single_layers=1, attention_head_dim=128,
+                                                       num_attention_heads=2, joint_attention_dim=32, pooled_projection_dim=8))
+    tower = UnivaDenoiseTower(cfg)
+    calls = []
+
+    class Recorder(torch.nn.Module):
+        def forward(self, **kw):
+            calls.append(kw)
+            return (kw["hidden_states"] * 2,)
+
+    tower.denoiser = Recorder()
+    i = {k: v.cuda() for k, v in fx["inputs"].items()}
+    runs = {
+        "vlm_plus_prefix": lambda: tower(i["hs"], i["t"], i["vlm"], i["pooled"], prefix_prompt_embeds=i["t5"], img_ids=i["img_ids"],
+                                         guidance=i["guidance"], joint_attention_kwargs={"attention_mask": torch.ones(2, 18)},
+                                         enc_attention_mask=torch.ones(2, 5)),
+        "vlm_only": lambda: tower(i["hs"], i["t"], i["vlm"], i["pooled"], img_ids=i["img_ids"], guidance=i["guidance"]),
+        "prefix_only": lambda: tower(i["hs"], i["t"], None, i["pooled"], prefix_prompt_embeds=i["t5"], img_ids=i["img_ids"],
+                                     guidance=i["guidance"]),
+    }
+    for name, run in runs.items():
+        out = run()
+        want = fx["cases"][name]
+        got = {k: v for k, v in calls[-1].items() if k != "return_dict"}      # ours asks for the tuple form explicitly
+        assert sorted(got) == sorted(want["call"]), name
+        for k, v in want["call"].items():
+            assert torch.equal(got[k].cpu(), v) if torch.is_tensor(v) else got[k] == v, (name, k)
+        assert torch.equal(out.cpu(), want["out"])
+    pj = fx["projector"]
+    assert pj["structure"] == ["Linear", "SiLU", "Linear"]
+    assert pj["keys"] == sorted("denoise_projector." + k for k in DenoiseProjector(64, 32).state_dict())
+    mlp2 = DenoiseProjector(64, 32)
+    mlp2.load_state_dict({k: v.cuda().bfloat16() for k, v in pj["state_dict"].items()})
+    y = mlp2(pj["x"].cuda().bfloat16()).float().cpu()
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    ek, et = rel(y, pj["y_fp32"]), rel(pj["y_bf16"].float(), pj["y_fp32"])
+    print(f"MLP2 vs the reference module: kernel {ek:.3e}, reference-in-bf16 {et:.3e}")
+    assert y.shape == pj["y_fp32"].shape and ek <= 2.0 * et + 2e-3

@@ -104,3 +104,60 @@ def test_vae_oracle_matches_torchtitan_golden():
     # fp32 run stays within fp32 round-off of the float64 golden
     sd32 = {k: v.float() for k, v in sd.items()}
     assert _rel_l2(vo.decode(sd32, cfg, blob["z"]), blob["image"]) < 1e-4
+
+
+def test_oracle_loop_equals_the_references_own_pipeline_code():
+    """tests/golden/pipeline_ref_loop.pt was produced by EXECUTING /root/reference/univa/utils/flux_pipeline.py
+    (FluxKontextPipeline.__call__ and its helpers) with oracle-backed transformer / VAE / scheduler adapters and
+    stand-ins for the missing diffusers base classes (tests/golden/make_pipeline_ref_golden.py).  The oracle's
+    restatement of that loop, and the product pipeline's host helpers, must reproduce it."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).parent / "golden"))
+    from make_pipeline_ref_golden import TOY_FLUX, TOY_VAE
+
+    from gpt_image_edit_b200 import pipeline as prod
+    from oracle import flux_oracle as fo
+    from oracle import pipeline_oracle as po
+    from oracle import vae_oracle as vo
+
+    fx = torch.load(Path(__file__).parent / "golden" / "pipeline_ref_loop.pt", weights_only=False)
+    for name, case in fx.items():
+        a = case["args"]
+        assert torch.equal(case["latents"], case["oracle_latents"])          # bit-identical when the fixture was made
+        fcfg, vcfg = fo.FluxConfig(**TOY_FLUX), vo.VaeConfig(**TOY_VAE)
+        fsd = fo.make_synthetic_state_dict(fcfg, seed=3, dtype=torch.float32)
+        vsd = vo.make_synthetic_state_dict(vcfg, seed=4, dtype=torch.float32)
+        g = torch.Generator().manual_seed(a["seed"])
+        H, W, B = a["H"], a["W"], a["B"]
+        image = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+        pe = torch.randn(B, 12, TOY_FLUX["joint_attention_dim"], generator=g)
+        pooled = torch.randn(B, TOY_FLUX["pooled_projection_dim"], generator=g)
+        noise = torch.randn(B, (H // 16) * (W // 16), 64, generator=g)
+        seen = []
+        mine = po.sample(fsd, fcfg, vsd, vcfg, image, pe, pooled, height=H, width=W, num_inference_steps=a["steps"],
+                         guidance_scale=3.5, latents=noise.clone(), output="latent", max_area=H * W,
+                         callback=lambda i, x: seen.append(i))
+        assert len(seen) == a["steps"] and case["timesteps"].shape[0] == a["steps"]
+        err = ((mine - case["latents"]).norm() / case["latents"].norm()).item()
+        assert err < 1e-5, (name, err)                                       # same fp32 ops; thread-count dependent sums only
+        # what the reference handed to the transformer: [target ; context] tokens, t / 1000, guidance vector, id layout
+        n_tgt = (H // 16) * (W // 16)
+        assert case["n_tokens"] == 2 * n_tgt
+        assert torch.all(case["timesteps"][0] == 1.0) and torch.all(case["timesteps"][1:] < 1.0)
+        assert case["guidance"].shape == (B,) and torch.all(case["guidance"] == 3.5)
+        ids = case["img_ids"]
+        assert ids.shape == (2 * n_tgt, 3) and torch.all(ids[:n_tgt, 0] == 0) and torch.all(ids[n_tgt:, 0] == 1)
+        assert torch.equal(ids[:n_tgt, 1:], ids[n_tgt:, 1:]) and torch.all(case["txt_ids"] == 0)
+        assert torch.equal(prod.FluxKontextPipeline._prepare_latent_image_ids(1, H // 16, W // 16, "cpu", torch.float32),
+                           ids[:n_tgt])
+    h = fx["case_64x96"]["helpers"]
+    assert [float(po.calculate_shift(n)) for n in (256, 1024, 4096)] == pytest.approx(h["calculate_shift"], rel=1e-12)
+    assert [float(prod.calculate_shift(n)) for n in (256, 1024, 4096)] == pytest.approx(h["calculate_shift"], rel=1e-12)
+    x = torch.arange(2 * 16 * 4 * 6.0).view(2, 16, 4, 6)
+    assert torch.equal(prod.FluxKontextPipeline._pack_latents(x, 2, 16, 4, 6), h["pack"])
+    assert torch.equal(po.pack_latents(x), h["pack"])
+    assert torch.equal(prod.FluxKontextPipeline._unpack_latents(h["pack"], 32, 48, 8), x)
+    assert torch.equal(prod.FluxKontextPipeline._prepare_latent_image_ids(1, 3, 2, "cpu", torch.float32), h["ids"])
+    assert [tuple(r) for r in prod.PREFERRED_KONTEXT_RESOLUTIONS] == [tuple(r) for r in h["preferred"]]

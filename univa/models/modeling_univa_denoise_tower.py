@@ -65,6 +65,10 @@ class UnivaDenoiseTower(torch.nn.Module):
             assert prefix is not None
             encoder_hidden_states = prefix
         txt_ids = torch.zeros(encoder_hidden_states.shape[1], 3, device=hidden_states.device, dtype=hidden_states.dtype)
+        # the reference pops BOTH of these and forwards neither (its mask assembly is commented out, :79-100; pinned by
+        # tests/golden/tower_ref.pt, which was produced by running that file)
+        kwargs.pop("joint_attention_kwargs", None)
         kwargs.pop("enc_attention_mask", None)
+        kwargs.pop("return_dict", None)
         return self.denoiser(hidden_states=hidden_states, timestep=timestep, encoder_hidden_states=encoder_hidden_states,
                              pooled_projections=pooled_projections, txt_ids=txt_ids, return_dict=False, **kwargs)[0]
