@@ -137,8 +137,11 @@ class FluxKontextPipeline:
                                  "this pipeline was built without them — pass prompt_embeds + pooled_prompt_embeds")
             prompt = [prompt] if isinstance(prompt, str) else prompt
             prompt_2 = prompt_2 or prompt
+            # pooled CLIP vector, copies of a prompt adjacent (`repeat(1, n).view(B*n, -1)`, reference :354-355)
             pooled_prompt_embeds = _encode_prompt_with_clip(self.text_encoder, self.tokenizer, prompt, device=device,
-                                                            num_images_per_prompt=num_images_per_prompt)
+                                                            num_images_per_prompt=1)
+            pooled_prompt_embeds = pooled_prompt_embeds.repeat(1, num_images_per_prompt).view(
+                len(prompt) * num_images_per_prompt, -1)
             prompt_embeds = _encode_prompt_with_t5(self.text_encoder_2, self.tokenizer_2, max_sequence_length, prompt_2,
                                                    num_images_per_prompt, device)
         dtype = self.text_encoder.dtype if self.text_encoder is not None else self.transformer.dtype

@@ -405,7 +405,11 @@ def _encode_prompt_with_clip(text_encoder, tokenizer, prompt, device=None, text_
     ids = _ids_or_raise(tokenizer, prompt, 77, text_input_ids)
     enc = getattr(text_encoder, "module", text_encoder)
     pooled = text_encoder(ids.to(device), output_hidden_states=False).pooler_output.to(dtype=enc.dtype, device=device)
-    return _tile(pooled, len(prompt), num_images_per_prompt)
+    # The reference duplicates the 2-D pooled tensor with `repeat(1, n, 1)` (:100-101): torch treats it as [1, B, d], so
+    # for B > 1 and n > 1 the copies come out INTERLEAVED (b0, b1, b0, b1, ...) while the T5 embeddings above are
+    # grouped (b0, b0, ..., b1, ...).  Reproduced as is (pinned by tests/golden/host_ref.pt, generated by the
+    # reference's own function); the pipeline's own encode_prompt (flux_pipeline.py:354-355) groups them.
+    return pooled.repeat(1, num_images_per_prompt, 1).view(len(prompt) * num_images_per_prompt, -1)
 
 
 def encode_prompt(text_encoders, tokenizers, prompt, max_sequence_length, device=None, num_images_per_prompt: int = 1,

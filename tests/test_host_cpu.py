@@ -144,3 +144,48 @@ def test_gedit_driver_host_logic(tmp_path):
     assert generation_size(1024, 1024, 512, 512) == (512, 512)
     cfg = EvalConfig.from_mapping({"seed": 7, "gedit_image_dir": "x", "genai_prompt_path": "ignored", "joint_with_t5": True})
     assert cfg.seed == 7 and cfg.joint_with_t5 and cfg.num_inference_steps == 32 and cfg.guidance_scale == 3.5
+
+
+def test_host_modules_match_the_references_own_outputs():
+    """tests/golden/host_ref.pt: outputs of the reference's own anyres_util.py and denoiser_prompt_embedding_flux.py
+    (imported by path, tests/golden/make_host_ref_golden.py) on a grid of sizes / with stub encoders."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).parent / "golden"))
+    from make_host_ref_golden import StubClip, StubT5, StubTok
+
+    from gpt_image_edit_b200 import text_encoders as te
+    from univa.utils import denoiser_prompt_embedding_flux as shim
+    from univa.utils.anyres_util import compute_size, dynamic_resize, pick_ratio
+
+    fx = torch.load(Path(__file__).parent / "golden" / "host_ref.pt", weights_only=False)
+    assert len(fx["anyres"]) == 112
+    for (mode, h, w), want in fx["anyres"].items():
+        rw, rh = pick_ratio(h, w, anyres=mode)
+        assert (rw, rh) == tuple(want["ratio"]), (mode, h, w)
+        assert tuple(compute_size(rw, rh, stride=16, anchor_pixels=1024 * 1024)) == tuple(want["size16"])
+        assert tuple(compute_size(rw, rh, stride=28, min_pixels=448 * 448, max_pixels=448 * 448)) == tuple(want["size28"])
+        assert tuple(dynamic_resize(h, w, mode, anchor_pixels=1024 * 1024)) == tuple(want["dyn"])
+        assert tuple(dynamic_resize(h, w, mode, anchor_pixels=512 * 512)) == tuple(want["dyn512"])
+    toks, encs = [StubTok(100), StubTok(500)], [StubClip(), StubT5()]
+    ep = fx["encode_prompt"]
+    assert shim.encode_prompt is te.encode_prompt
+
+    def same(got, want):
+        assert (got is None) == (want is None)
+        if want is not None:
+            assert got.shape == want.shape and torch.equal(got, want)
+
+    e, p = te.encode_prompt(encs, toks, ["turn the sky red", "b"], 16, device="cpu", num_images_per_prompt=3)
+    same(e, ep["both_n3"]["embeds"]); same(p, ep["both_n3"]["pooled"])
+    e, p = te.encode_prompt(encs, toks, "single", 8, device="cpu", num_images_per_prompt=1)
+    same(e, ep["single"]["embeds"]); same(p, ep["single"]["pooled"])
+    e, p = te.encode_prompt(encs, [None, toks[1]], "single", 8, device="cpu")
+    same(e, ep["no_clip_tokenizer"]["embeds"]); same(p, ep["no_clip_tokenizer"]["pooled"])
+    e, p = te.encode_prompt([encs[0], None], toks, "single", 8, device="cpu")
+    same(e, ep["no_t5_encoder"]["embeds"]); same(p, ep["no_t5_encoder"]["pooled"])
+    assert torch.equal(te.tokenize_prompt(toks[1], ["x y"], 6), ep["tokenize_prompt"])
+    with pytest.raises(ValueError) as ei:
+        te._encode_prompt_with_t5(encs[1], None, 8, "p")
+    assert str(ei.value) == ep["error_no_ids"]

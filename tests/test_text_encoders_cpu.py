@@ -46,7 +46,9 @@ def test_encode_prompt_contract():
     # the reference duplicates by repeat(1, n, 1).view(B*n, L, -1): each prompt's copies are adjacent
     assert torch.equal(emb[0], emb[1]) and torch.equal(emb[0], emb[2]) and torch.equal(emb[3], emb[5])
     assert not torch.equal(emb[0], emb[3])
-    assert torch.equal(pooled[0], pooled[2])
+    # ... while the 2-D pooled tensor goes through repeat(1, n, 1) and comes out interleaved (b0, b1, b0, b1, ...):
+    # the reference's behaviour, pinned by tests/golden/host_ref.pt
+    assert torch.equal(pooled[0], pooled[2]) and torch.equal(pooled[1], pooled[3])
     # an encoder runs only when both it and its tokenizer are given (reference :120, :133)
     emb, pooled = encode_prompt([_StubClip(), _StubT5()], [None, toks[1]], "a", 16)
     assert pooled is None and emb.shape == (1, 16, 6)
