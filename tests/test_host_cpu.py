@@ -189,3 +189,34 @@ def test_host_modules_match_the_references_own_outputs():
     with pytest.raises(ValueError) as ei:
         te._encode_prompt_with_t5(encs[1], None, 8, "p")
     assert str(ei.value) == ep["error_no_ids"]
+
+
+def test_cli_and_training_host_functions_match_the_references_source():
+    """host_ref.pt["host"]: outputs of the reference's own `update_size` / `prepare_condition_images` (cli.py) and
+    `get_trainable_params` / `check_param_is_in_components` (train_denoiser.py), whose function sources were executed
+    by tests/golden/make_host_ref_golden.py."""
+    from pathlib import Path
+
+    from gpt_image_edit_b200.image_io import image_to_condition_tensor
+    from oracle import flux_oracle as fo
+    from univa.serve.cli import update_size
+
+    h = torch.load(Path(__file__).parent / "golden" / "host_ref.pt", weights_only=False)["host"]
+    imgs = h["images"]
+    shape = lambda i: (imgs[i].shape[1], imgs[i].shape[0])                      # (w, h) as PIL reports it
+    for (key, anchor), want in h["update_size"].items():
+        shapes = [] if key == "none" else [shape(0), shape(2)] if key == "0+2" else [shape(key)]
+        assert tuple(update_size(shapes, "any_11ratio", anchor_pixels=anchor)) == tuple(want), (key, anchor)
+    assert torch.equal(image_to_condition_tensor(imgs[0]), h["condition"])     # [1,3,H,W] fp32 in [-1,1]
+    # parameter-name contract (SURVEY.md §8b): every component the reference un-freezes names real parameters of the
+    # denoiser, under the diffusers key names this repo's state_dict exposes
+    keys = ["denoise_tower.denoiser." + k for k in fo.state_dict_spec(fo.FluxConfig())]
+    for mode, comps in h["components"].items():
+        for c in comps:
+            assert any(c in k for k in keys), (mode, c)
+    hit = lambda name, comps: any(c in name for c in comps)
+    for mode, want in h["probe_result"].items():
+        assert [hit(n, h["components"][mode]) for n in h["probe"]] == want
+    n_default = sum(hit(k, h["components"]["default"]) for k in keys)
+    n_both = sum(hit(k, h["components"]["both_branches"]) for k in keys)
+    assert 0 < n_default < n_both < len(keys)
