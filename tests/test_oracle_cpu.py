@@ -161,3 +161,39 @@ def test_oracle_loop_equals_the_references_own_pipeline_code():
     assert torch.equal(prod.FluxKontextPipeline._unpack_latents(h["pack"], 32, 48, 8), x)
     assert torch.equal(prod.FluxKontextPipeline._prepare_latent_image_ids(1, 3, 2, "cpu", torch.float32), h["ids"])
     assert [tuple(r) for r in prod.PREFERRED_KONTEXT_RESOLUTIONS] == [tuple(r) for r in h["preferred"]]
+
+
+def test_sigma_schedule_matches_torchtitan_and_pins():
+    """The shifted flow-matching schedule (diffusers FlowMatchEulerDiscreteScheduler.set_timesteps with dynamic
+    shifting; not on disk) cross-checked against the independent BFL-style `get_schedule` that ships
+    with torchtitan in this image: sigmas(linspace(1, 1/N, N), mu(seq)) + [0] == get_schedule(N, seq).  Values are
+    also pinned as literals so the check runs where torchtitan is absent."""
+    import numpy as np
+
+    from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    from gpt_image_edit_b200 import pipeline as prod
+    from oracle import pipeline_oracle as po
+
+    def ours(n, seq, cls):
+        s = cls()
+        s.set_timesteps(sigmas=np.linspace(1.0, 1 / n, n), mu=prod.calculate_shift(seq), device="cpu")
+        return s.sigmas.double()
+
+    class OracleAdapter(po.EulerSchedulerOracle):
+        def set_timesteps(self, sigmas=None, mu=None, device=None):
+            super().set_timesteps(sigmas, mu, device=device)
+
+    pins = {(28, 4096): [1.0, 0.9884086, 0.9762225], (4, 256): [1.0, 0.8318243, 0.6224593], (3, 1024): [1.0, 0.7897048, 0.4842184]}   # closed form e^mu / (e^mu + 1/s - 1)
+    for (n, seq), first in pins.items():
+        a, b = ours(n, seq, FlowMatchEulerDiscreteScheduler), ours(n, seq, OracleAdapter)
+        assert a.shape == (n + 1,) and float(a[-1]) == 0.0
+        assert torch.allclose(a, b, rtol=0, atol=1e-7)
+        assert a[:3].tolist() == pytest.approx(first, abs=2e-6), (n, seq, a[:3].tolist())
+    try:
+        from torchtitan.experiments.flux.sampling import get_schedule
+    except Exception:
+        return
+    for n, seq in [(28, 4096), (28, 1024), (4, 256), (50, 2304), (3, 1024)]:
+        want = torch.tensor(get_schedule(n, seq), dtype=torch.float64)
+        got = ours(n, seq, FlowMatchEulerDiscreteScheduler)
+        assert torch.allclose(got, want, rtol=0, atol=2e-6), (n, seq, (got - want).abs().max())
