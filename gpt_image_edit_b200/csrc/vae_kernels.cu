@@ -40,13 +40,11 @@ constexpr int GN_PIX_PER_BLOCK = 512;
 
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* x, double* stats,
                                                               long long P, int C) {
-  __shared__ float s_sum[32], s_sq[32];
+  // Per-thread partial sums go through shared memory and are combined in a FIXED order by one thread per group:
+  // with fp32 shared-memory atomics the block sums depended on the arrival order, E[x^2] - mean^2 amplified the
+  // last-bit differences, and the VAE (hence the whole edit) was not bit-reproducible run to run.
+  __shared__ float part[GN_THREADS][17];
   const int n = blockIdx.y;
-  if (threadIdx.x < 32) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
   const int octets = C >> 3;
   const int oct = threadIdx.x % octets;
   const int prow = threadIdx.x / octets;
@@ -66,17 +64,25 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat1
       }
     }
   }
-  const int cpg = C / 32;  // channels per group: 4, 8 or 16 (or 1/2 for toy widths)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (oct * 8 + j) / cpg;
-    atomicAdd(&s_sum[g], s[j]);
-    atomicAdd(&s_sq[g], q[j]);
+    part[threadIdx.x][j] = s[j];
+    part[threadIdx.x][8 + j] = q[j];
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    atomicAdd(&stats[((long long)n * 32 + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
-    atomicAdd(&stats[((long long)n * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+    const int cpg = C / 32;  // channels per group: 4, 8 or 16 (1 or 2 for toy widths)
+    double a = 0.0, b = 0.0;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+      const int o = c >> 3, j = c & 7;
+      for (int r = 0; r < rows_per_iter; ++r) {
+        a += (double)part[r * octets + o][j];
+        b += (double)part[r * octets + o][8 + j];
+      }
+    }
+    // across blocks: double atomics (order-dependent only at the 1e-16 level)
+    atomicAdd(&stats[((long long)n * 32 + threadIdx.x) * 2 + 0], a);
+    atomicAdd(&stats[((long long)n * 32 + threadIdx.x) * 2 + 1], b);
   }
 }
 

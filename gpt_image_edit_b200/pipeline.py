@@ -232,8 +232,16 @@ class FluxKontextPipeline:
             prompt_embeds, pooled_prompt_embeds, _ = self.encode_prompt(
                 prompt, prompt_2, device=self._execution_device, num_images_per_prompt=1,
                 max_sequence_length=max_sequence_length)
-        if true_cfg_scale > 1 and negative_prompt_embeds is not None:
-            raise NotImplementedError("true-CFG second forward (reference :1080-1095) is off by default and not built")
+        # true classifier-free guidance (reference :925-957): a second forward on the negative prompt per step
+        has_neg_prompt = negative_prompt is not None or (negative_prompt_embeds is not None and
+                                                         negative_pooled_prompt_embeds is not None)
+        do_true_cfg = true_cfg_scale > 1 and has_neg_prompt
+        if negative_prompt_embeds is not None and negative_pooled_prompt_embeds is None:
+            raise ValueError("If `negative_prompt_embeds` are provided, `negative_pooled_prompt_embeds` also have to be passed.")
+        if do_true_cfg and negative_prompt_embeds is None:
+            negative_prompt_embeds, negative_pooled_prompt_embeds, _ = self.encode_prompt(
+                negative_prompt, negative_prompt_2, device=self._execution_device, num_images_per_prompt=1,
+                max_sequence_length=max_sequence_length)
         height = height or self.default_sample_size * self.vae_scale_factor
         width = width or self.default_sample_size * self.vae_scale_factor
         # size rule: rescale to `max_area` keeping aspect, floor to a multiple of 16 (reference :874-889)
@@ -249,7 +257,11 @@ class FluxKontextPipeline:
         if num_images_per_prompt != 1:
             prompt_embeds = prompt_embeds.repeat_interleave(num_images_per_prompt, dim=0)
             pooled_prompt_embeds = pooled_prompt_embeds.repeat_interleave(num_images_per_prompt, dim=0)
+            if do_true_cfg:
+                negative_prompt_embeds = negative_prompt_embeds.repeat_interleave(num_images_per_prompt, dim=0)
+                negative_pooled_prompt_embeds = negative_pooled_prompt_embeds.repeat_interleave(num_images_per_prompt, dim=0)
         text_ids = torch.zeros(prompt_embeds.shape[1], 3, device=device, dtype=dtype)
+        negative_text_ids = torch.zeros(negative_prompt_embeds.shape[1], 3, device=device, dtype=dtype) if do_true_cfg else None
 
         if image is not None and not (isinstance(image, torch.Tensor) and image.size(1) == self.latent_channels):
             ih, iw = self.image_processor.get_default_height_width(image)
@@ -299,6 +311,15 @@ class FluxKontextPipeline:
                 encoder_hidden_states=prompt_embeds, txt_ids=text_ids, img_ids=latent_ids, joint_attention_kwargs=jak,
                 return_dict=False)[0]
             noise_pred = noise_pred[:, :n_tgt]
+            if do_true_cfg:
+                # the hoisted modulation belongs to the positive pooled vector: the negative forward computes its own
+                neg_jak = {k: v for k, v in jak.items() if k != "_b2f_schedule_step"}
+                neg_noise_pred = self.transformer(
+                    hidden_states=x_in, timestep=timestep / 1000, guidance=guidance,
+                    pooled_projections=negative_pooled_prompt_embeds, encoder_hidden_states=negative_prompt_embeds,
+                    txt_ids=negative_text_ids, img_ids=latent_ids, joint_attention_kwargs=neg_jak, return_dict=False)[0]
+                neg_noise_pred = neg_noise_pred[:, :n_tgt]
+                noise_pred = neg_noise_pred + true_cfg_scale * (noise_pred - neg_noise_pred)
             latents = self.scheduler.step(noise_pred, t, latents, return_dict=False)[0]
             if callback_on_step_end is not None:
                 out = callback_on_step_end(self, i, t, {"latents": latents})

@@ -92,7 +92,7 @@ def target_size(height, width, max_area, mult=16):
 @torch.no_grad()
 def sample(flux_sd, flux_cfg: fo.FluxConfig, vae_sd, vae_cfg: vo.VaeConfig, image, prompt_embeds, pooled, *,
            height, width, num_inference_steps=28, guidance_scale=3.5, latents=None, max_area=None, output="image",
-           callback=None):
+           callback=None, true_cfg_scale=1.0, negative_prompt_embeds=None, negative_pooled=None):
     """image: [B,3,H,W] in [-1,1] (already at its final resolution, i.e. `_auto_resize=False`);
     latents: packed initial noise [B,S_tgt,64] (the run is deterministic given it).
     Returns decoded image [B,3,H,W] (output="image") or the final packed latents (output="latent")."""
@@ -121,6 +121,11 @@ def sample(flux_sd, flux_cfg: fo.FluxConfig, vae_sd, vae_cfg: vo.VaeConfig, imag
         v = fo.flux_forward(flux_sd, flux_cfg, x_in, prompt_embeds, pooled, timestep / 1000, latent_ids, text_ids,
                             guidance=guidance)
         v = v[:, : latents.size(1)]
+        if true_cfg_scale > 1 and negative_prompt_embeds is not None:          # reference flux_pipeline.py:1080-1095
+            neg_ids = torch.zeros(negative_prompt_embeds.shape[1], 3, device=device, dtype=dtype)
+            vn = fo.flux_forward(flux_sd, flux_cfg, x_in, negative_prompt_embeds, negative_pooled, timestep / 1000, latent_ids,
+                                 neg_ids, guidance=guidance)[:, : latents.size(1)]
+            v = vn + true_cfg_scale * (v - vn)
         latents = sched.step(v, t, latents)
         if callback is not None:
             callback(i, latents)

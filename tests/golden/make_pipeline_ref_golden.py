@@ -182,7 +182,7 @@ class OracleScheduler(po.EulerSchedulerOracle):
         self._config = v
 
 
-def run(dtype=torch.float32, H=64, W=96, steps=3, B=1, seed=5):
+def run(dtype=torch.float32, H=64, W=96, steps=3, B=1, seed=5, true_cfg_scale=1.0):
     ref = load_reference_pipeline_module()
     fcfg, vcfg = fo.FluxConfig(**TOY_FLUX), vo.VaeConfig(**TOY_VAE)
     fsd = fo.make_synthetic_state_dict(fcfg, seed=3, dtype=dtype)
@@ -192,15 +192,22 @@ def run(dtype=torch.float32, H=64, W=96, steps=3, B=1, seed=5):
     pe = torch.randn(B, 12, TOY_FLUX["joint_attention_dim"], generator=g).to(dtype)
     pooled = torch.randn(B, TOY_FLUX["pooled_projection_dim"], generator=g).to(dtype)
     noise = torch.randn(B, (H // 16) * (W // 16), 64, generator=g).to(dtype)
+    cfg_kw, cfg_kw_oracle = {}, {}
+    if true_cfg_scale > 1:      # true classifier-free guidance: negative prompt of a different length
+        npe = torch.randn(B, 7, TOY_FLUX["joint_attention_dim"], generator=g).to(dtype)
+        npool = torch.randn(B, TOY_FLUX["pooled_projection_dim"], generator=g).to(dtype)
+        cfg_kw = dict(true_cfg_scale=true_cfg_scale, negative_prompt_embeds=npe, negative_pooled_prompt_embeds=npool)
+        cfg_kw_oracle = dict(true_cfg_scale=true_cfg_scale, negative_prompt_embeds=npe, negative_pooled=npool)
     tr = OracleTransformer(fsd, fcfg)
     pipe = ref.FluxKontextPipeline(scheduler=OracleScheduler(), vae=OracleVae(vsd, vcfg), text_encoder=None, tokenizer=None,
                                    text_encoder_2=None, tokenizer_2=None, transformer=tr)
     out = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pooled, height=H, width=W, num_inference_steps=steps,
-               guidance_scale=3.5, latents=noise.clone(), output_type="latent", max_area=H * W, _auto_resize=False)
+               guidance_scale=3.5, latents=noise.clone(), output_type="latent", max_area=H * W, _auto_resize=False, **cfg_kw)
     latents = out.images
     mine = po.sample(fsd, fcfg, vsd, vcfg, image, pe, pooled, height=H, width=W, num_inference_steps=steps, guidance_scale=3.5,
-                     latents=noise.clone(), output="latent", max_area=H * W)
-    return dict(args=dict(H=H, W=W, steps=steps, B=B, seed=seed, dtype=str(dtype)), latents=latents, oracle_latents=mine,
+                     latents=noise.clone(), output="latent", max_area=H * W, **cfg_kw_oracle)
+    return dict(args=dict(H=H, W=W, steps=steps, B=B, seed=seed, dtype=str(dtype), true_cfg_scale=true_cfg_scale),
+                n_forwards=len(tr.calls), latents=latents, oracle_latents=mine,
                 timesteps=torch.stack([c["timestep"] for c in tr.calls]), guidance=tr.calls[0]["guidance"],
                 n_tokens=tr.calls[0]["n_tokens"], img_ids=tr.calls[0]["img_ids"], txt_ids=tr.calls[0]["txt_ids"],
                 helpers=dict(
@@ -213,7 +220,8 @@ def run(dtype=torch.float32, H=64, W=96, steps=3, B=1, seed=5):
 if __name__ == "__main__":
     if not REF_FILE.exists():
         raise SystemExit("needs /root/reference (run in the build container)")
-    fx = {"case_64x96": run(), "case_batch2_128x64": run(H=128, W=64, steps=2, B=2, seed=9)}
+    fx = {"case_64x96": run(), "case_batch2_128x64": run(H=128, W=64, steps=2, B=2, seed=9),
+          "case_true_cfg": run(H=64, W=64, steps=2, seed=11, true_cfg_scale=2.5)}
     for k, v in fx.items():
         d = (v["latents"] - v["oracle_latents"]).abs().max().item()
         print(k, "max |reference loop - oracle loop| =", d, " tokens per forward:", v["n_tokens"])

@@ -135,17 +135,23 @@ def test_oracle_loop_equals_the_references_own_pipeline_code():
         pe = torch.randn(B, 12, TOY_FLUX["joint_attention_dim"], generator=g)
         pooled = torch.randn(B, TOY_FLUX["pooled_projection_dim"], generator=g)
         noise = torch.randn(B, (H // 16) * (W // 16), 64, generator=g)
+        kw = {}
+        if a.get("true_cfg_scale", 1.0) > 1:     # true classifier-free guidance: a second (negative) forward per step
+            kw = dict(true_cfg_scale=a["true_cfg_scale"],
+                      negative_prompt_embeds=torch.randn(B, 7, TOY_FLUX["joint_attention_dim"], generator=g),
+                      negative_pooled=torch.randn(B, TOY_FLUX["pooled_projection_dim"], generator=g))
         seen = []
         mine = po.sample(fsd, fcfg, vsd, vcfg, image, pe, pooled, height=H, width=W, num_inference_steps=a["steps"],
                          guidance_scale=3.5, latents=noise.clone(), output="latent", max_area=H * W,
-                         callback=lambda i, x: seen.append(i))
-        assert len(seen) == a["steps"] and case["timesteps"].shape[0] == a["steps"]
+                         callback=lambda i, x: seen.append(i), **kw)
+        per_step = 2 if kw else 1
+        assert len(seen) == a["steps"] and case["n_forwards"] == case["timesteps"].shape[0] == per_step * a["steps"]
         err = ((mine - case["latents"]).norm() / case["latents"].norm()).item()
         assert err < 1e-5, (name, err)                                       # same fp32 ops; thread-count dependent sums only
         # what the reference handed to the transformer: [target ; context] tokens, t / 1000, guidance vector, id layout
         n_tgt = (H // 16) * (W // 16)
         assert case["n_tokens"] == 2 * n_tgt
-        assert torch.all(case["timesteps"][0] == 1.0) and torch.all(case["timesteps"][1:] < 1.0)
+        assert torch.all(case["timesteps"][:per_step] == 1.0) and torch.all(case["timesteps"][per_step:] < 1.0)
         assert case["guidance"].shape == (B,) and torch.all(case["guidance"] == 3.5)
         ids = case["img_ids"]
         assert ids.shape == (2 * n_tgt, 3) and torch.all(ids[:n_tgt, 0] == 0) and torch.all(ids[n_tgt:, 0] == 1)

@@ -73,3 +73,37 @@ def test_pipeline_pil_output_and_reference_size_rule():
     out = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pooled, height=128, width=128, num_inference_steps=2,
                max_area=128 * 128, _auto_resize=False, generator=torch.Generator(device="cuda").manual_seed(42)).images
     assert len(out) == 1 and out[0].size == (128, 128)
+
+
+def test_true_cfg_second_forward_matches_oracle_loop():
+    """true_cfg_scale > 1 with negative embeddings (reference flux_pipeline.py:925-957, 1080-1095): a second forward per
+    step on the negative prompt, `neg + s * (pos - neg)`.  The oracle loop for this case is bit-identical to the
+    reference's own __call__ (tests/golden/pipeline_ref_loop.pt: case_true_cfg)."""
+    from oracle import pipeline_oracle as po
+
+    pipe, (fsd, fcfg, vsd, vcfg) = _build()
+    g = torch.Generator().manual_seed(13)
+    H = W = 128
+    image = (torch.randint(0, 256, (1, 3, H, W), generator=g).float() / 127.5 - 1.0).cuda()
+    pe = torch.randn(1, 24, 256, generator=g).bfloat16().cuda()
+    pooled = torch.randn(1, 64, generator=g).bfloat16().cuda()
+    npe = torch.randn(1, 9, 256, generator=g).bfloat16().cuda()          # a negative prompt of another length
+    npooled = torch.randn(1, 64, generator=g).bfloat16().cuda()
+    noise = torch.randn(1, 64, 64, generator=g).bfloat16().cuda()
+    common = dict(height=H, width=W, num_inference_steps=3, guidance_scale=3.5, max_area=H * W)
+    lat = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pooled, negative_prompt_embeds=npe,
+               negative_pooled_prompt_embeds=npooled, true_cfg_scale=6.0, latents=noise.clone(), _auto_resize=False,
+               output_type="latent", **common).images
+    ref = po.sample(fsd, fcfg, vsd, vcfg, image.bfloat16(), pe, pooled, latents=noise.clone(), output="latent",
+                    true_cfg_scale=6.0, negative_prompt_embeds=npe, negative_pooled=npooled, **common)
+    plain = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pooled, latents=noise.clone(), _auto_resize=False,
+                 output_type="latent", **common).images
+    e = _rel_l2(lat, ref)
+    print(f"true-CFG latents rel-L2 vs torch-bf16 oracle {e:.3e}; distance from the plain run {_rel_l2(lat, plain):.3e}")
+    assert e < 2e-2
+    assert _rel_l2(lat, plain) > 3 * e                                  # the guidance really changed the trajectory
+    # scale 1 or no negative prompt: the second forward is skipped (reference :925-928)
+    same = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pooled, negative_prompt_embeds=npe,
+                negative_pooled_prompt_embeds=npooled, true_cfg_scale=1.0, latents=noise.clone(), _auto_resize=False,
+                output_type="latent", **common).images
+    assert torch.equal(same, plain)

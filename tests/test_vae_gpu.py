@@ -123,3 +123,17 @@ def test_vae_encode_decode_match_oracle(boc, H, W):
     print(f"decode {boc[0]}: kernel-vs-fp32 {e_k:.3e}  torch-bf16-vs-fp32 {e_t:.3e}")
     assert e_k <= 2.0 * e_t + 3e-3
     assert img.shape == (1, 3, H, W)
+
+
+def test_vae_is_bit_reproducible_run_to_run():
+    """GroupNorm statistics are combined in a fixed order (fp32 shared-memory atomics used to make the encoder, and
+    with it the whole edit, differ in the last bf16 bit from run to run)."""
+    from gpt_image_edit_b200.vae import B200AutoencoderKL, VaeConfig
+
+    vae = B200AutoencoderKL(VaeConfig(block_out_channels=(64, 128, 256, 256))).randomize_(4)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    img = (torch.rand(2, 3, 96, 160, device="cuda", generator=g) * 2 - 1).bfloat16()
+    z = [vae.encode(img).latent_dist.mode() for _ in range(3)]
+    assert torch.equal(z[0], z[1]) and torch.equal(z[0], z[2])
+    d = [vae.decode(z[0], return_dict=False)[0] for _ in range(3)]
+    assert torch.equal(d[0], d[1]) and torch.equal(d[0], d[2])
