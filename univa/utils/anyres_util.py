@@ -1,53 +1,74 @@
-"""Aspect-ratio bucketing used by the CLI to pick the generation size (reference
-univa/utils/anyres_util.py:22-78; host logic, results must be identical)."""
+"""Aspect-ratio bucketing behind `--anyres` (the reference's univa/utils/anyres_util.py: pick_ratio :22-30,
+compute_size :33-57, dynamic_resize :60-78).  Host logic; results are pinned to the reference's own outputs on a
+112-case grid (tests/golden/host_ref.pt).
+
+The bucket families are nested: every smaller family drops one landscape/portrait pair from the 11-ratio list, and
+the 17-ratio family is the reduced form of the Kontext training resolutions the pipeline already carries."""
 from __future__ import annotations
 
-import math
+from fractions import Fraction
+from math import sqrt
 
-RESOLUTIONS_17 = [(672, 1568), (688, 1504), (720, 1456), (752, 1392), (800, 1328), (832, 1248), (880, 1184),
-                  (944, 1104), (1024, 1024), (1104, 944), (1184, 880), (1248, 832), (1328, 800), (1392, 752),
-                  (1456, 720), (1504, 688), (1568, 672)]
+from gpt_image_edit_b200.pipeline import PREFERRED_KONTEXT_RESOLUTIONS as RESOLUTIONS_17
+
+_ELEVEN = ((16, 9), (7, 5), (5, 4), (4, 3), (3, 2))        # landscape members, each followed by its transpose
 
 
-def _reduced(pairs):
-    return [(w // math.gcd(w, h), h // math.gcd(w, h)) for w, h in pairs]
+def _family(drop=()):
+    out = []
+    for w, h in _ELEVEN:
+        if (w, h) not in drop:
+            out += [(w, h), (h, w)]
+    return out + [(1, 1)]
+
+
+def _lowest_terms(w, h):
+    f = Fraction(w, h)
+    return f.numerator, f.denominator
 
 
 RATIO = {
-    "any_17ratio": _reduced(RESOLUTIONS_17),
-    "any_11ratio": [(16, 9), (9, 16), (7, 5), (5, 7), (5, 4), (4, 5), (4, 3), (3, 4), (3, 2), (2, 3), (1, 1)],
-    "any_9ratio": [(16, 9), (9, 16), (5, 4), (4, 5), (4, 3), (3, 4), (3, 2), (2, 3), (1, 1)],
-    "any_7ratio": [(16, 9), (9, 16), (4, 3), (3, 4), (3, 2), (2, 3), (1, 1)],
-    "any_5ratio": [(16, 9), (9, 16), (4, 3), (3, 4), (1, 1)],
+    "any_17ratio": [_lowest_terms(w, h) for w, h in RESOLUTIONS_17],
+    "any_11ratio": _family(),
+    "any_9ratio": _family(drop={(7, 5)}),
+    "any_7ratio": _family(drop={(7, 5), (5, 4)}),
+    "any_5ratio": _family(drop={(7, 5), (5, 4), (3, 2)}),
     "any_1ratio": [(1, 1)],
 }
 
 
 def pick_ratio(orig_h: int, orig_w: int, anyres: str = "any_17ratio"):
-    """Closest (w, h) ratio of the bucket list to the image's aspect ratio; first wins on ties."""
-    target = orig_w / orig_h
-    return min(RATIO[anyres], key=lambda wh: abs(wh[0] / wh[1] - target))
+    """(rw, rh) of the bucket whose w/h is nearest to the image's; the earlier entry wins a tie."""
+    aspect = orig_w / orig_h
+    best, best_d = None, float("inf")
+    for rw, rh in RATIO[anyres]:
+        d = abs(rw / rh - aspect)
+        if d < best_d:
+            best, best_d = (rw, rh), d
+    return best
+
+
+def _snap(v: float, stride: int) -> int:
+    return max(stride, int(v)) // stride * stride
 
 
 def compute_size(rw: int, rh: int, stride: int, *, min_pixels=None, max_pixels=None, anchor_pixels=None):
-    bw, bh = rw * stride, rh * stride
-    area = bw * bh
+    """(h, w): the `stride`-unit bucket rescaled (real factor) to the anchor area, or clamped into
+    [min_pixels, max_pixels], then floored to the stride grid."""
+    unit_area = (rw * stride) * (rh * stride)
     if anchor_pixels is not None:
-        goal = anchor_pixels
-    elif min_pixels is not None and max_pixels is not None:
-        goal = max_pixels if area > max_pixels else min_pixels if area < min_pixels else area
+        want = anchor_pixels
+    elif min_pixels is None or max_pixels is None:
+        want = unit_area
     else:
-        goal = area
-    k = math.sqrt(goal / area)
-    new_w = max(stride, int(bw * k)) // stride * stride
-    new_h = max(stride, int(bh * k)) // stride * stride
-    return new_h, new_w
+        want = min(max(unit_area, min_pixels), max_pixels)
+    k = sqrt(want / unit_area)
+    return _snap(rh * stride * k, stride), _snap(rw * stride * k, stride)
 
 
 def dynamic_resize(orig_h: int, orig_w: int, anyres: str = "any_17ratio", anchor_pixels: int = 1024 * 1024,
                    stride: int = 32):
-    """(h, w): the bucket ratio scaled by an INTEGER factor so the area lands near `anchor_pixels`."""
+    """(h, w): the bucket in `stride` units times an INTEGER factor chosen so that the area lands near the anchor."""
     rw, rh = pick_ratio(orig_h, orig_w, anyres)
-    bw, bh = rw * stride, rh * stride
-    s = max(1, round(math.sqrt(anchor_pixels / (bw * bh))))
-    return (bh * s) // stride * stride, (bw * s) // stride * stride
+    factor = max(1, round(sqrt(anchor_pixels / (rw * rh * stride * stride))))
+    return rh * stride * factor, rw * stride * factor
