@@ -220,3 +220,28 @@ def test_cli_and_training_host_functions_match_the_references_source():
     n_default = sum(hit(k, h["components"]["default"]) for k in keys)
     n_both = sum(hit(k, h["components"]["both_branches"]) for k in keys)
     assert 0 < n_default < n_both < len(keys)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line on stdout with the
+    same metric / unit / config as the GPU arm, `impl: reference`, a `cpu_baseline` describing the run and a zero-copy
+    `e2e`.  (The sample is one double + one single block of the oracle at C1024 shapes: ~30 s on 8 cores.)"""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "edited images/sec @1024px 28-step" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["config"]["workload"].startswith("C1024") and d["dtype"] == "f32"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "extrapolated" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(d["ms_per_step"] - 1000.0 / d["value"]) / d["ms_per_step"] < 1e-6
