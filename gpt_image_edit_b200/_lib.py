@@ -13,7 +13,7 @@ from pathlib import Path
 import torch  # noqa: F401  (loads libcudart.so.12 into the process before libb2f.so)
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libb2f.so"
+LIB_PATH = Path(os.environ["B2F_LIB"]) if os.environ.get("B2F_LIB") else _HERE / "lib" / "libb2f.so"   # override: A/B builds
 HEADER_PATH = _HERE.parent / "include" / "b2f.h"
 
 
