@@ -27,7 +27,6 @@ import sys
 import types
 from pathlib import Path
 
-import numpy as np
 import torch
 
 ROOT = Path(__file__).resolve().parents[2]
