@@ -149,3 +149,27 @@ def test_realistic_timestep_and_guidance_follow_the_bf16_chain():
     e = _rel_l2(out, ref16)
     print(f"realistic t/g: kernel-vs-torch-bf16 {e:.3e}")
     assert e < 1e-2
+
+
+def test_full_model_at_c1024_matches_oracle():
+    """The flagship configuration itself: all 19 double + 38 single blocks at d=3072, 1024x1024 target + 1024x1024
+    context (S_txt=544, S_img=8192, S=8736) — one forward of the denoising step, against the oracle in fp32 and bf16
+    on the same bf16-rounded synthetic weights (BASELINE.json configs[1])."""
+    from oracle import flux_oracle as fo
+
+    ocfg, sd, model, inp = _setup({}, 1, 544, 64, 64, seed=11)
+    assert ocfg.num_layers == 19 and ocfg.num_single_layers == 38
+    out = model(**inp, return_dict=False)[0]
+    assert out.shape == (1, 8192, 64) and torch.isfinite(out.float()).all()
+    del model
+    torch.cuda.empty_cache()
+    ref16 = _oracle(fo, sd, ocfg, inp, torch.bfloat16)
+    for k in list(sd):                      # bf16 -> fp32 in place of the dict, one tensor at a time (48 GB)
+        sd[k] = sd[k].float()
+    torch.cuda.empty_cache()
+    ref32 = fo.flux_forward(sd, ocfg, inp["hidden_states"].float(), inp["encoder_hidden_states"].float(),
+                            inp["pooled_projections"].float(), inp["timestep"], inp["img_ids"], inp["txt_ids"],
+                            guidance=inp["guidance"])
+    e_k, e_t, e_kt = _rel_l2(out, ref32), _rel_l2(ref16, ref32), _rel_l2(out, ref16)
+    print(f"C1024 full model: kernel-vs-fp32 {e_k:.3e}   torch-bf16-vs-fp32 {e_t:.3e}   kernel-vs-torch-bf16 {e_kt:.3e}")
+    assert e_k <= 2.0 * e_t + 2e-3
