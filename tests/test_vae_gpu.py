@@ -105,7 +105,9 @@ def _vae_pair(boc, seed=0):
     return vo, ocfg, sd, vae
 
 
-@pytest.mark.parametrize("boc,H,W", [((64, 128, 256, 256), 64, 96), ((128, 256, 512, 512), 128, 128)])
+@pytest.mark.parametrize("boc,H,W", [((64, 128, 256, 256), 64, 96), ((128, 256, 512, 512), 128, 128),
+                                     ((128, 256, 512, 512), 1024, 1024)],      # the last one: the FLUX VAE at the C1024 size
+                         ids=["toy", "full-width-128", "c1024"])
 def test_vae_encode_decode_match_oracle(boc, H, W):
     vo, ocfg, sd, vae = _vae_pair(boc)
     g = torch.Generator(device="cuda").manual_seed(5)
