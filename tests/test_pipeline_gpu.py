@@ -107,3 +107,46 @@ def test_true_cfg_second_forward_matches_oracle_loop():
                 negative_pooled_prompt_embeds=npooled, true_cfg_scale=1.0, latents=noise.clone(), _auto_resize=False,
                 output_type="latent", **common).images
     assert torch.equal(same, plain)
+
+
+def test_c1024_full_edit_trajectory_matches_oracle_loop():
+    """The whole flagship job — FLUX VAE encode of a 1024x1024 context image, 28 Euler steps of the full 19+38-block
+    MMDiT at S = 8736, VAE decode — against the oracle loop (bit-identical to the reference's own __call__, see
+    tests/golden/pipeline_ref_loop.pt) run in torch bf16 on the same synthetic weights, inputs and initial noise."""
+    from gpt_image_edit_b200.flux_transformer import B200FluxTransformer2DModel, FluxTransformerConfig
+    from gpt_image_edit_b200.pipeline import FluxKontextPipeline
+    from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
+    from gpt_image_edit_b200.vae import B200AutoencoderKL, VaeConfig
+    from oracle import flux_oracle as fo
+    from oracle import pipeline_oracle as po
+    from oracle import vae_oracle as vo
+
+    fcfg, vcfg = fo.FluxConfig(), vo.VaeConfig()
+    fsd = fo.make_synthetic_state_dict(fcfg, seed=3, dtype=torch.bfloat16, device="cuda")
+    vsd = vo.make_synthetic_state_dict(vcfg, seed=4, dtype=torch.bfloat16, device="cuda")
+    tr = B200FluxTransformer2DModel(FluxTransformerConfig())
+    tr.load_state_dict(fsd)
+    vae = B200AutoencoderKL(VaeConfig())
+    vae.load_state_dict(vsd)
+    pipe = FluxKontextPipeline(transformer=tr, vae=vae, scheduler=FlowMatchEulerDiscreteScheduler())
+    g = torch.Generator().manual_seed(21)
+    H = W = 1024
+    image = (torch.randint(0, 256, (1, 3, H, W), generator=g).float() / 127.5 - 1.0).cuda()
+    pe = torch.randn(1, 544, 4096, generator=g).bfloat16().cuda()
+    pooled = torch.randn(1, 768, generator=g).bfloat16().cuda()
+    noise = torch.randn(1, 4096, 64, generator=torch.Generator().manual_seed(42)).bfloat16().cuda()
+    kw = dict(height=H, width=W, num_inference_steps=28, guidance_scale=3.5, max_area=H * W)
+    lat = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pooled, latents=noise.clone(), _auto_resize=False,
+               output_type="latent", **kw).images
+    img = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pooled, latents=noise.clone(), _auto_resize=False,
+               output_type="pt", **kw).images
+    del pipe, tr
+    torch.cuda.empty_cache()
+    steps_seen = []
+    ref_img = po.sample(fsd, fcfg, vsd, vcfg, image.bfloat16(), pe, pooled, latents=noise.clone(), output="image",
+                        callback=lambda i, x: steps_seen.append(x.clone()) if i == 27 else None, **kw)
+    e_lat = _rel_l2(lat, steps_seen[-1])
+    e_img = _rel_l2(img, (ref_img.float() / 2 + 0.5).clamp(0, 1))
+    print(f"C1024, 28 steps: final latents rel-L2 vs torch-bf16 oracle loop {e_lat:.3e}; decoded image {e_img:.3e}")
+    assert lat.shape == (1, 4096, 64) and img.shape == (1, 3, H, W) and torch.isfinite(img).all()
+    assert e_lat < 5e-2 and e_img < 5e-2
