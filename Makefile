@@ -5,7 +5,13 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall 
              --expt-relaxed-constexpr -Xptxas -v
 CSRC      := gpt_image_edit_b200/csrc
 LIBDIR    := gpt_image_edit_b200/lib
-SRCS      := $(wildcard $(CSRC)/*.cu)
+# attention_experiments.cu (alternative kernel structures kept for the record) is not part of
+# the product library: `make EXPERIMENTS=1` links it and enables B2F_ATTN_VARIANT 10-12 / 30-32 / 40-42 / 60-62.
+SRCS      := $(filter-out $(CSRC)/attention_experiments.cu,$(wildcard $(CSRC)/*.cu))
+ifeq ($(EXPERIMENTS),1)
+SRCS      += $(CSRC)/attention_experiments.cu
+NVFLAGS   += -DB2F_WITH_EXPERIMENTS
+endif
 OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/b2f.h
 

@@ -92,6 +92,32 @@ _SIGNATURES = {
     "b2f_geglu": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
     "b2f_layernorm": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, C.c_float, _vp]),
     "b2f_embed": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64, _i64, _i32, _vp]),
+    # training step
+    "b2f_gemm_dgrad": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp]),
+    "b2f_gemm_wgrad": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b2f_attention_fwd_lse": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, C.c_float, _i32,
+                                     _vp, _i64, _vp]),
+    "b2f_attn_delta": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "b2f_attention_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                                 _i32, _i32, _i32, _i32, C.c_float, _vp]),
+    "b2f_train_chunks": (_i32, [_i32]),
+    "b2f_train_ln_chunks": (_i32, [_i32]),
+    "b2f_gate_resid_fwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "b2f_gate_bwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b2f_col_reduce": (_i32, [_vp, _i32, _i32, _vp, _i64, _i32, _i32, _vp]),
+    "b2f_ln_modulate_bwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp,
+                                   _i32, _i32, _i32, C.c_float, _i32, _i32, _vp]),
+    "b2f_rmsnorm_rope_out": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                    C.c_float, _vp]),
+    "b2f_rmsnorm_rope_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
+                                    _i32, C.c_float, _vp]),
+    "b2f_gelu_rows": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "b2f_outer_acc": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "b2f_mse_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, _vp]),
+    "b2f_grad_sumsq": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp]),
+    "b2f_clip_coef": (_i32, [_vp, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "b2f_adamw_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i32, _vp, _vp]),
+    "b2f_cast_bf16_f32": (_i32, [_vp, _vp, _i64, _i32, _vp]),
 }
 
 

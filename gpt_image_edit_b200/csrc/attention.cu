@@ -40,6 +40,12 @@ extern std::atomic<uint64_t> g_launch_count;
 
 using namespace attn;
 
+#ifndef B2F_WITH_EXPERIMENTS
+namespace attn {
+bool experimental_variant(int, Variant*) { return false; }   // `make EXPERIMENTS=1` links attention_experiments.cu
+}  // namespace attn
+#endif
+
 namespace {
 
 // POLY: one pair of exponentials in every POLY pairs goes to the polynomial (0 = never).
@@ -350,6 +356,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const bool row_ok = q_row < p.Sq;
+    if (p.lse && row_ok) p.lse[((long long)b * p.H + h) * p.lse_stride + q_row] = m + log2f(l);
     __nv_bfloat16* out_row =
         p.out + ((long long)b * p.Sq + q_row) * p.ldo + (long long)h * DH;
 #pragma unroll 1
@@ -674,6 +681,7 @@ attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       const float inv_l = 1.0f / l;
       const bool row_ok = q_row < p.Sq;
+      if (p.lse && row_ok) p.lse[((long long)b * p.H + h) * p.lse_stride + q_row] = m + log2f(l);
       __nv_bfloat16* out_row = p.out + ((long long)b * p.Sq + q_row) * p.ldo + (long long)h * DH;
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -709,8 +717,9 @@ attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                           int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
                           int head_dim, float scale, int causal, const void* bias, int64_t bias_h_stride,
-                          int64_t bias_row_stride, cudaStream_t stream) {
+                          int64_t bias_row_stride, float* lse, int64_t lse_stride, cudaStream_t stream) {
   if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (lse && lse_stride < Sq) return B2F_ERR_INVALID;
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || Hkv <= 0 || Sq <= 0 || Skv <= 0)
     return B2F_ERR_INVALID;
   if (head_dim != DH) return B2F_ERR_UNSUPPORTED;
@@ -734,7 +743,6 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
       case 4: sel.fn = attn_fwd_kernel<4, true>; break;
       case 5: sel.fn = attn_fwd_kernel<3, false>; break;         // 33 %
       case 6: sel.fn = attn_fwd_kernel<8, false>; break;         // 12.5 %
-      case 21: sel.fn = attn_fwd_kernel<0, false, 1>; break;     // ablation for timing analysis only (wrong results)
       default:
         if (!experimental_variant(variant, &sel)) sel.fn = attn_fwd_kernel<0, false>;
         break;
@@ -776,6 +784,8 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     pp.causal = 0;
     pp.out = static_cast<__nv_bfloat16*>(out);
     pp.ldo = ldo;
+    pp.lse = lse;
+    pp.lse_stride = lse_stride;
     dim3 grid_p(2 * ((Sq + 4 * BQ - 1) / (4 * BQ)), H, B);
     prof_begin(KC_ATTN, stream);
     pk<<<grid_p, ATTN_THREADS, P2_SMEM, stream>>>(tQ, tK, tV, pp);
@@ -801,6 +811,8 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
   p.causal = causal;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
+  p.lse = lse;
+  p.lse_stride = lse_stride;
   if (bias) {
     // score = scale * q.k + bias, evaluated before the base-2 conversion
     p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -831,7 +843,16 @@ int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
                   int64_t ldv, void* out, int64_t ldo, int B, int H, int Hkv, int Sq, int Skv,
                   int head_dim, float scale, int causal, cudaStream_t stream) {
   return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale, causal,
-                        nullptr, 0, 0, stream);
+                        nullptr, 0, 0, nullptr, 0, stream);
+}
+
+// forward that also emits the base-2 log-sum-exp rows the backward kernels need (attention_bwd.cu)
+int attention_fwd_lse(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                      int64_t ldo, int B, int H, int Hkv, int Sq, int Skv, int head_dim, float scale, int causal,
+                      float* lse, int64_t lse_stride, cudaStream_t stream) {
+  if (!lse) return B2F_ERR_INVALID;
+  return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale, causal, nullptr, 0, 0,
+                        lse, lse_stride, stream);
 }
 
 int attention_bias_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -840,7 +861,7 @@ int attention_bias_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        int64_t bias_row_stride, cudaStream_t stream) {
   if (!bias || bias_row_stride < Skv || bias_h_stride < 0) return B2F_ERR_INVALID;
   return attention_impl(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale, causal,
-                        bias, bias_h_stride, bias_row_stride, stream);
+                        bias, bias_h_stride, bias_row_stride, nullptr, 0, stream);
 }
 
 }  // namespace b2f

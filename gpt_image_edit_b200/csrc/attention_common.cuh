@@ -25,6 +25,10 @@ struct AttnParams {
   const __nv_bfloat16* bias;
   long long bias_h_stride, bias_row_stride;
   float bias_scale;
+  // optional log-sum-exp output for the backward pass, base-2 domain: lse2[b, h, q] = max2 + log2(sum), where the scores
+  // are scale_log2 * q.k; element (b, h, q) at lse + (b*H + h)*lse_stride + q
+  float* lse;
+  long long lse_stride;
 };
 
 static __device__ __forceinline__ float ex2(float x) {

@@ -59,6 +59,51 @@ int layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y,
               int64_t rows, int D, float eps, cudaStream_t stream);
 int embed(const void* tok, int64_t ld_tok, const int64_t* ids, const void* pos, int64_t ld_pos, int period,
           void* out, int64_t ldo, int64_t n, int D, cudaStream_t stream);
+// training step (train_kernels.cu, attention_bwd.cu, gemm.cu)
+int gemm_dgrad(const void* dY, int64_t ldy, int64_t dy_bs, const void* W, int64_t ldw, void* dX, int64_t ldx,
+               int64_t dx_bs, int batch, int M, int N, int K, int epilogue, const void* aux, int64_t ld_aux,
+               int64_t aux_bs, cudaStream_t stream);
+int gemm_wgrad(const void* dY, int64_t ldy, int64_t dy_bs, const void* X, int64_t ldx, int64_t x_bs, float* dW,
+               int64_t ldw, int batch, int rows, int M, int N, int accumulate, cudaStream_t stream);
+int attention_fwd_lse(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                      int64_t ldo, int B, int H, int Hkv, int Sq, int Skv, int head_dim, float scale, int causal,
+                      float* lse, int64_t lse_stride, cudaStream_t stream);
+int attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
+                  int64_t lddo, const float* lse, const float* delta, int64_t S_pad, void* dq, int64_t lddq, void* dk,
+                  int64_t lddk, void* dv, int64_t lddv, int B, int H, int S, int head_dim, float scale,
+                  cudaStream_t stream);
+int train_chunks(int rows);
+int train_ln_chunks(int rows);
+int gate_resid_fwd(const void* x, int64_t ldx, int64_t x_bs, const void* y, int64_t ldy, int64_t y_bs, const void* gate,
+                   const void* gate_b, int64_t gate_ld, void* out, int64_t ldo, int64_t o_bs, int batch, int rows, int D,
+                   int split_row, cudaStream_t st);
+int gate_bwd(const void* dout, int64_t ldd, int64_t d_bs, const void* y, int64_t ldy, int64_t y_bs, const void* gate,
+             const void* gate_b, int64_t gate_ld, void* dy, int64_t ldo, int64_t o_bs, float* partial, int batch,
+             int rows, int D, int split_row, int part_row0, cudaStream_t st);
+int col_reduce(const float* partial, int nchunks, int D, float* out, int64_t out_ld, int batch, int accumulate,
+               cudaStream_t st);
+int ln_modulate_bwd(const void* x, int64_t ldx, int64_t x_bs, const void* dy, int64_t ldy, int64_t dy_bs,
+                    const void* scale, const void* scale_b, int64_t mod_ld, const void* dres_in, int64_t ldr, int64_t r_bs,
+                    void* dres_out, int64_t ldo, int64_t o_bs, float* partial, int batch, int rows, int D, float eps,
+                    int split_row, int part_row0, cudaStream_t st);
+int rmsnorm_rope_out(const void* xq, const void* xk, int64_t ldx, int64_t x_bs, void* oq, void* ok, int64_t ldo,
+                     int64_t o_bs, const void* wq_a, const void* wk_a, const void* wq_b, const void* wk_b,
+                     const float* cos, const float* sin, int batch, int S, int H, int n_a, float eps, cudaStream_t st);
+int rmsnorm_rope_bwd(void* dq, void* dk, int64_t ld, int64_t bs, const void* xq, const void* xk, int64_t ldx, int64_t x_bs,
+                     const void* wq_a, const void* wk_a, const void* wq_b, const void* wk_b, const float* cos,
+                     const float* sin, float* partial, int batch, int S, int H, int n_a, float eps, cudaStream_t st);
+int gelu_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int D, cudaStream_t st);
+int outer_acc(const float* dmod, int64_t dmod_ld, const void* act, int64_t act_ld, float* dW, int64_t ldw, int B, int N,
+              int K, int accumulate, cudaStream_t st);
+int attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, float* lse, int B, int H, int S,
+               int S_pad, cudaStream_t st);
+int mse_loss(const void* pred, const float* target, const float* w, void* dpred, float* loss_out, float* ws, int64_t n,
+             float grad_scale, cudaStream_t st);
+int grad_sumsq(const float* g, int64_t n, float* sumsq_out, float* ws, int accumulate, cudaStream_t st);
+int clip_coef(const float* sumsq, float max_norm, float pre_scale, float* coef, float* norm_out, cudaStream_t st);
+int adamw_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1, float beta2,
+               float eps, float wd, int step, const float* gscale, cudaStream_t st);
+int cast_bf16_f32(const void* src, void* dst, int64_t n, int to_f32, cudaStream_t st);
 }  // namespace b2f
 
 extern "C" {
@@ -225,5 +270,99 @@ int b2f_embed(const void* tok, int64_t ld_tok, const int64_t* ids, const void* p
   return b2f::embed(tok, ld_tok, ids, pos, ld_pos, period, out, ldo, n, D,
                     static_cast<cudaStream_t>(stream));
 }
+
+// ------------------------------------------------------------------ training step
+#define ST static_cast<cudaStream_t>(stream)
+int b2f_gemm_dgrad(const void* dY, int64_t ldy, int64_t dy_batch_stride, const void* W, int64_t ldw, void* dX,
+                   int64_t ldx, int64_t dx_batch_stride, int batch, int M, int N, int K, int epilogue, const void* aux,
+                   int64_t ld_aux, int64_t aux_batch_stride, b2f_stream_t stream) {
+  return b2f::gemm_dgrad(dY, ldy, dy_batch_stride, W, ldw, dX, ldx, dx_batch_stride, batch, M, N, K, epilogue, aux,
+                         ld_aux, aux_batch_stride, ST);
+}
+int b2f_gemm_wgrad(const void* dY, int64_t ldy, int64_t dy_batch_stride, const void* X, int64_t ldx,
+                   int64_t x_batch_stride, float* dW, int64_t ldw, int batch, int rows, int M, int N, int accumulate,
+                   b2f_stream_t stream) {
+  return b2f::gemm_wgrad(dY, ldy, dy_batch_stride, X, ldx, x_batch_stride, dW, ldw, batch, rows, M, N, accumulate, ST);
+}
+int b2f_attention_fwd_lse(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                          int64_t ldo, int B, int H, int Hkv, int Sq, int Skv, int head_dim, float scale, int causal,
+                          float* lse, int64_t lse_stride, b2f_stream_t stream) {
+  return b2f::attention_fwd_lse(q, ldq, k, ldk, v, ldv, out, ldo, B, H, Hkv, Sq, Skv, head_dim, scale, causal, lse,
+                                lse_stride, ST);
+}
+int b2f_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                      const void* dout, int64_t lddo, const float* lse, const float* delta, int64_t S_pad, void* dq,
+                      int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int S, int head_dim,
+                      float scale, b2f_stream_t stream) {
+  return b2f::attention_bwd(q, ldq, k, ldk, v, ldv, dout, lddo, lse, delta, S_pad, dq, lddq, dk, lddk, dv, lddv, B, H, S,
+                            head_dim, scale, ST);
+}
+int b2f_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, float* lse, int B, int H,
+                   int S, int S_pad, b2f_stream_t stream) {
+  return b2f::attn_delta(o, ldo, dout, lddo, delta, lse, B, H, S, S_pad, ST);
+}
+int b2f_train_chunks(int rows) { return b2f::train_chunks(rows); }
+int b2f_train_ln_chunks(int rows) { return b2f::train_ln_chunks(rows); }
+int b2f_gate_resid_fwd(const void* x, int64_t ldx, int64_t x_bs, const void* y, int64_t ldy, int64_t y_bs,
+                       const void* gate, const void* gate_b, int64_t gate_ld, void* out, int64_t ldo, int64_t o_bs,
+                       int batch, int rows, int D, int split_row, b2f_stream_t stream) {
+  return b2f::gate_resid_fwd(x, ldx, x_bs, y, ldy, y_bs, gate, gate_b, gate_ld, out, ldo, o_bs, batch, rows, D, split_row, ST);
+}
+int b2f_gate_bwd(const void* dout, int64_t ldd, int64_t d_bs, const void* y, int64_t ldy, int64_t y_bs, const void* gate,
+                 const void* gate_b, int64_t gate_ld, void* dy, int64_t ldo, int64_t o_bs, float* partial, int batch,
+                 int rows, int D, int split_row, int part_row0, b2f_stream_t stream) {
+  return b2f::gate_bwd(dout, ldd, d_bs, y, ldy, y_bs, gate, gate_b, gate_ld, dy, ldo, o_bs, partial, batch, rows, D,
+                       split_row, part_row0, ST);
+}
+int b2f_col_reduce(const float* partial, int nchunks, int D, float* out, int64_t out_ld, int batch, int accumulate,
+                   b2f_stream_t stream) {
+  return b2f::col_reduce(partial, nchunks, D, out, out_ld, batch, accumulate, ST);
+}
+int b2f_ln_modulate_bwd(const void* x, int64_t ldx, int64_t x_bs, const void* dy, int64_t ldy, int64_t dy_bs,
+                        const void* scale, const void* scale_b, int64_t mod_ld, const void* dres_in, int64_t ldr,
+                        int64_t r_bs, void* dres_out, int64_t ldo, int64_t o_bs, float* partial, int batch, int rows,
+                        int D, float eps, int split_row, int part_row0, b2f_stream_t stream) {
+  return b2f::ln_modulate_bwd(x, ldx, x_bs, dy, ldy, dy_bs, scale, scale_b, mod_ld, dres_in, ldr, r_bs, dres_out, ldo,
+                              o_bs, partial, batch, rows, D, eps, split_row, part_row0, ST);
+}
+int b2f_rmsnorm_rope_out(const void* xq, const void* xk, int64_t ldx, int64_t x_bs, void* oq, void* ok, int64_t ldo,
+                         int64_t o_bs, const void* wq_a, const void* wk_a, const void* wq_b, const void* wk_b,
+                         const float* cos, const float* sin, int batch, int S, int H, int n_a, float eps,
+                         b2f_stream_t stream) {
+  return b2f::rmsnorm_rope_out(xq, xk, ldx, x_bs, oq, ok, ldo, o_bs, wq_a, wk_a, wq_b, wk_b, cos, sin, batch, S, H, n_a,
+                               eps, ST);
+}
+int b2f_rmsnorm_rope_bwd(void* dq, void* dk, int64_t ld, int64_t bs, const void* xq, const void* xk, int64_t ldx,
+                         int64_t x_bs, const void* wq_a, const void* wk_a, const void* wq_b, const void* wk_b,
+                         const float* cos, const float* sin, float* partial, int batch, int S, int H, int n_a, float eps,
+                         b2f_stream_t stream) {
+  return b2f::rmsnorm_rope_bwd(dq, dk, ld, bs, xq, xk, ldx, x_bs, wq_a, wk_a, wq_b, wk_b, cos, sin, partial, batch, S, H,
+                               n_a, eps, ST);
+}
+int b2f_gelu_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int D, b2f_stream_t stream) {
+  return b2f::gelu_rows(x, ldx, y, ldy, rows, D, ST);
+}
+int b2f_outer_acc(const float* dmod, int64_t dmod_ld, const void* act, int64_t act_ld, float* dW, int64_t ldw, int B,
+                  int N, int K, int accumulate, b2f_stream_t stream) {
+  return b2f::outer_acc(dmod, dmod_ld, act, act_ld, dW, ldw, B, N, K, accumulate, ST);
+}
+int b2f_mse_loss(const void* pred, const float* target, const float* w, void* dpred, float* loss_out, float* ws,
+                 int64_t n, float grad_scale, b2f_stream_t stream) {
+  return b2f::mse_loss(pred, target, w, dpred, loss_out, ws, n, grad_scale, ST);
+}
+int b2f_grad_sumsq(const float* g, int64_t n, float* sumsq_out, float* ws, int accumulate, b2f_stream_t stream) {
+  return b2f::grad_sumsq(g, n, sumsq_out, ws, accumulate, ST);
+}
+int b2f_clip_coef(const float* sumsq, float max_norm, float pre_scale, float* coef, float* norm_out, b2f_stream_t stream) {
+  return b2f::clip_coef(sumsq, max_norm, pre_scale, coef, norm_out, ST);
+}
+int b2f_adamw_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* gscale, b2f_stream_t stream) {
+  return b2f::adamw_step(p32, m, v, g, p16, n, lr, beta1, beta2, eps, weight_decay, step, gscale, ST);
+}
+int b2f_cast_bf16_f32(const void* src, void* dst, int64_t n, int to_f32, b2f_stream_t stream) {
+  return b2f::cast_bf16_f32(src, dst, n, to_f32, ST);
+}
+#undef ST
 
 }  // extern "C"

@@ -55,7 +55,18 @@ struct GemmParams {
   int split_n, epi2;
   __nv_bfloat16* out2;
   long long ldc2, out2_bs;
+  // MODE 2 (wgrad): the contraction runs over kbatch x K rows (tokens of every batch item)
+  int kbatch, kb_per_batch;
 };
+
+// Operand layouts of the kernel templates below.
+//   MODE 0  forward:  out[M,N] = A[M,K] . W[N,K]^T          A, W K-major (contraction contiguous)
+//   MODE 1  dgrad:    out[M,N] = A[M,K] . Wt[K,N]            A K-major, B MN-major: dX = dY . W with W as stored [out,in]
+//   MODE 2  wgrad:    out[M,N] = sum_b At[b,K,M]^T . Bt[b,K,N]   both MN-major (tokens are the rows of both), fp32 output
+// An MN-major 64(k) x 64(mn) box is one 128B-swizzled 8 KB TMA box; a tile of `mn` columns is mn/64 boxes 8 KB apart
+// (descriptor LBO = 8192, SBO = 1024, 16 k-rows = 2048 bytes per UMMA k-step) — the layout the attention kernel
+// uses for V.
+constexpr int MN_BOX_BYTES = 64 * 64 * 2;
 
 template <int BN>
 struct GemmCfg {
@@ -85,6 +96,15 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return 0.5f * x * (1.0f + tanhf(inner));
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float dgelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float t = tanhf(k0 * (x + k1 * x * x * x));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * x * x);
+}
+__device__ __forceinline__ float dsilu_f(float x) {
+  const float s = 1.0f / (1.0f + __expf(-x));
+  return s * (1.0f + x * (1.0f - s));
+}
 
 // Epilogue for 32 accumulator columns of one output row: bias / activation / gate / residual with the
 // bf16 rounding points of the torch-eager chain, then 16-byte stores.
@@ -140,6 +160,31 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
         v[2 * j] = r2.x + bf16r(g2.x * bf16r(v[2 * j]));
         v[2 * j + 1] = r2.y + bf16r(g2.y * bf16r(v[2 * j + 1]));
       }
+    }
+    else if (epi == B2F_EPI_DGELU || epi == B2F_EPI_DSILU) {
+      // backward of the activation fused into the dgrad GEMM: out = bf16(acc) * act'(u), u = the saved
+      // pre-activation (read through the resid pointer)
+      const uint4 uq = *reinterpret_cast<const uint4*>(res_row + n);
+      const uint32_t uw[4] = {uq.x, uq.y, uq.z, uq.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 u2 = unpack_bf16x2(uw[j]);
+        const float d0 = epi == B2F_EPI_DGELU ? dgelu_tanh_f(u2.x) : dsilu_f(u2.x);
+        const float d1 = epi == B2F_EPI_DGELU ? dgelu_tanh_f(u2.y) : dsilu_f(u2.y);
+        v[2 * j] = bf16r(v[2 * j]) * d0;
+        v[2 * j + 1] = bf16r(v[2 * j + 1]) * d1;
+      }
+    } else if (epi == B2F_EPI_F32 || epi == B2F_EPI_F32_ACC) {
+      float* o = reinterpret_cast<float*>(out_row) + n;
+      float4 a0 = make_float4(v[0], v[1], v[2], v[3]), a1 = make_float4(v[4], v[5], v[6], v[7]);
+      if (epi == B2F_EPI_F32_ACC) {
+        const float4 p0 = *reinterpret_cast<const float4*>(o), p1 = *reinterpret_cast<const float4*>(o + 4);
+        a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
+        a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
+      }
+      *reinterpret_cast<float4*>(o) = a0;
+      *reinterpret_cast<float4*>(o + 4) = a1;
+      continue;
     }
     else if (epi == B2F_EPI_RESID) {
       const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n);
@@ -213,6 +258,13 @@ __device__ __forceinline__ void epilogue_head_norm_rope(const GemmParams& p, uin
   }
 }
 
+// row pointer of the output; fp32 outputs (wgrad) have their pitch in floats
+__device__ __forceinline__ __nv_bfloat16* out_row_ptr(const GemmParams& p, int bidx, long long row) {
+  if (p.epi == B2F_EPI_F32 || p.epi == B2F_EPI_F32_ACC)
+    return reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<float*>(p.out) + bidx * p.out_bs + row * p.ldc);
+  return p.out + bidx * p.out_bs + row * p.ldc;
+}
+
 // Epilogue of one output tile for the calling warp's 32 rows: TMEM -> registers -> fused math -> global.
 // `arrive_cta0`: the CTA-pair kernel hands the accumulator stage back on CTA 0's barrier.
 template <int BN>
@@ -278,7 +330,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   }
 }
 
-template <int BN>
+template <int BN, int MODE = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -320,7 +372,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = MODE == 2 ? p.kbatch * p.kb_per_batch : (p.K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -336,8 +388,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int bb = m_blk / p.m_blocks_per_batch;
           const int mb = m_blk - bb * p.m_blocks_per_batch;
-          tma_load_3d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, mb * BLOCK_M, bb);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+          if (MODE == 2) {
+            const int kbb = kb / p.kb_per_batch;
+            const int kr = (kb - kbb * p.kb_per_batch) * BLOCK_K;
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_3d(sa + i * MN_BOX_BYTES, &tmA, &full_bar[stage], m_blk * BLOCK_M + 64 * i, kr, kbb);
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_3d(sb + i * MN_BOX_BYTES, &tmB, &full_bar[stage], n_blk * BN + 64 * i, kr, kbb);
+          } else {
+            tma_load_3d(sa, &tmA, &full_bar[stage], kb * BLOCK_K, mb * BLOCK_M, bb);
+            if (MODE == 1) {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(sb + i * MN_BOX_BYTES, &tmB, &full_bar[stage], n_blk * BN + 64 * i, kb * BLOCK_K);
+            } else {
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+            }
+          }
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -347,8 +416,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // whole warp runs the loop (uniform-datapath address math); one elected lane issues the MMAs
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0);
-    const uint64_t d_base = make_sdesc_sw128(smem_u32(smem), 16, 1024);
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, MODE >= 1, MODE == 2);
+    // K-major operands advance 32 bytes per UMMA k-step inside the swizzle row; MN-major ones 16 rows = 2048 bytes
+    constexpr int A_KSTEP = MODE == 2 ? 2048 : UMMA_K * 2;
+    constexpr int B_KSTEP = MODE >= 1 ? 2048 : UMMA_K * 2;
+    const uint64_t da_base = make_sdesc_sw128(smem_u32(smem), MODE == 2 ? MN_BOX_BYTES : 16, 1024);
+    const uint64_t db_base = make_sdesc_sw128(smem_u32(smem) + Cfg::A_BYTES, MODE >= 1 ? MN_BOX_BYTES : 16, 1024);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -360,12 +433,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint64_t da = d_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
-        const uint64_t db = da + uint64_t(Cfg::A_BYTES >> 4);
+        const uint64_t da = da_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
+        const uint64_t db = db_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_ss(d_tmem, da + uint64_t((k * UMMA_K * 2) >> 4), db + uint64_t((k * UMMA_K * 2) >> 4), idesc,
+            umma_ss(d_tmem, da + uint64_t((k * A_KSTEP) >> 4), db + uint64_t((k * B_KSTEP) >> 4), idesc,
                     (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tmem_full[as]);
@@ -396,7 +469,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long row = (long long)(m_blk - bidx * p.m_blocks_per_batch) * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.M;
       const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
-      __nv_bfloat16* out_row = p.out + bidx * p.out_bs + row * p.ldc;
+      __nv_bfloat16* out_row = out_row_ptr(p, bidx, row);
       const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
       __nv_bfloat16* out_row2 = p.out2 ? p.out2 + bidx * p.out2_bs + row * p.ldc2 - p.split_n : nullptr;
       epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], false,
@@ -416,12 +489,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN>
+template <int BN, int MODE = 0>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_err(e, "gemm smem attribute");
@@ -433,10 +506,11 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cu
   p.panel_n = BN == 256 ? 16 : 32;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = num_tiles < device_info().num_sms ? num_tiles : device_info().num_sms;
+  const double kk = MODE == 2 ? (double)p.kbatch * p.K : (double)p.K;
   prof_begin(KC_GEMM, stream);
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * p.K,
-           2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N));
+  gemm_bf16_kernel<BN, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * kk,
+           2.0 * ((double)p.batch * p.M * kk + (double)p.N * kk + (double)p.batch * p.M * p.N));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("gemm_bf16_kernel");
   return B2F_OK;
@@ -469,8 +543,9 @@ struct Gemm2Cfg {
 // kernel runs at the L2->SM bandwidth cap: ncu shows ~11.6 TB/s of xbar2l1tex reads at 75 % tensor activity).
 // A stage may be overwritten only when BOTH pairs have consumed it, so every CTA's `empty` barrier takes one
 // multicast commit from each pair leader.
-template <int CL>
+template <int CL, int MODE = 0>
 __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p) {
+  static_assert(CL == 2 || MODE == 0, "the 4-CTA cluster variant exists for the forward layout only");
   using Cfg = Gemm2Cfg;
   constexpr int PAIRS = CL / 2;
   constexpr int BN = Cfg::BN;
@@ -518,7 +593,7 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
 
   // p.m_blocks_per_batch / num_m_blocks are in units of 256-row pair tiles here
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = MODE == 2 ? p.kbatch * p.kb_per_batch : (p.K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -538,7 +613,16 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
             mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           else
             mbar_arrive_cta0(&full_bar[stage]);
-          if (CL == 2) {
+          if (MODE == 2) {
+            // wgrad: this CTA's 128 output rows (columns of dY) and 128 output columns (columns of X), 64 tokens
+            const int kbb = kb / p.kb_per_batch;
+            const int kr = (kb - kbb * p.kb_per_batch) * BLOCK_K;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              tma_load_3d_2cta(sa + i * MN_BOX_BYTES, tmA, &full_bar[stage], m_blk * 256 + int(rank) * BLOCK_M + 64 * i, kr, kbb);
+              tma_load_3d_2cta(sb + i * MN_BOX_BYTES, tmB, &full_bar[stage], n_blk * BN + int(rank) * (BN / 2) + 64 * i, kr, kbb);
+            }
+          } else if (CL == 2) {
             tma_load_3d_2cta(sa, tmA, &full_bar[stage], kb * BLOCK_K, mb * 256 + int(rank) * BLOCK_M, bb);
           } else {
             // 64-row slice `pc` of this half's A rows, to the same smem offset of both CTAs holding this half
@@ -546,7 +630,15 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
                                 mb * 256 + int(rank) * BLOCK_M + pc * (BLOCK_M / 2), bb,
                                 uint16_t((1u << rank) | (1u << (2 + rank))));
           }
-          tma_load_2d_2cta(sb, tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN + int(rank) * (BN / 2));
+          if (MODE == 1) {
+            // dgrad: this CTA's 128 output columns of W^T (= columns of W as stored), 64 contraction rows
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              tma_load_2d_2cta(sb + i * MN_BOX_BYTES, tmB, &full_bar[stage], n_blk * BN + int(rank) * (BN / 2) + 64 * i,
+                               kb * BLOCK_K);
+          } else if (MODE == 0) {
+            tma_load_2d_2cta(sb, tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN + int(rank) * (BN / 2));
+          }
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -556,8 +648,11 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
     }
   } else if (warp == 1) {
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0);
-      const uint64_t d_base = make_sdesc_sw128(smem_u32(smem), 16, 1024);
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, MODE >= 1, MODE == 2);
+      constexpr int A_KSTEP = MODE == 2 ? 2048 : UMMA_K * 2;
+      constexpr int B_KSTEP = MODE >= 1 ? 2048 : UMMA_K * 2;
+      const uint64_t da_base = make_sdesc_sw128(smem_u32(smem), MODE == 2 ? MN_BOX_BYTES : 16, 1024);
+      const uint64_t db_base = make_sdesc_sw128(smem_u32(smem) + Cfg::A_BYTES, MODE >= 1 ? MN_BOX_BYTES : 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -569,12 +664,12 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = d_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
-          const uint64_t db = da + uint64_t(Cfg::A_BYTES >> 4);
+          const uint64_t da = da_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t db = db_base + uint64_t((stage * Cfg::STAGE_BYTES) >> 4);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_ss_2cta(d_tmem, da + uint64_t((k * UMMA_K * 2) >> 4), db + uint64_t((k * UMMA_K * 2) >> 4),
+              umma_ss_2cta(d_tmem, da + uint64_t((k * A_KSTEP) >> 4), db + uint64_t((k * B_KSTEP) >> 4),
                            idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_mc(&empty_bar[stage], uint16_t((1u << CL) - 1));
             if (kb == num_kb - 1) umma_commit_mc(&tmem_full[as], uint16_t(3u << (2 * pc)));
@@ -606,7 +701,7 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
       const long long row = (long long)(m_blk - bidx * p.m_blocks_per_batch) * 256 + row_in_tile;
       const bool row_ok = row < p.M;
       const __nv_bfloat16* gate_row = p.gate ? p.gate + (long long)bidx * p.gate_ld : nullptr;
-      __nv_bfloat16* out_row = p.out + bidx * p.out_bs + row * p.ldc;
+      __nv_bfloat16* out_row = out_row_ptr(p, bidx, row);
       const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
       __nv_bfloat16* out_row2 = p.out2 ? p.out2 + bidx * p.out2_bs + row * p.ldc2 - p.split_n : nullptr;
       epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], true,
@@ -632,6 +727,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   gemm_pair_body<2>(&tmA, &tmB, p);
 }
 
+// dgrad / wgrad operand layouts of the CTA-pair kernel (MODE 1 / 2, see GemmParams)
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_grad_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const GemmParams p) {
+  gemm_pair_body<2, MODE>(&tmA, &tmB, p);
+}
+
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_4cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const GemmParams p) {
@@ -646,10 +749,15 @@ static int pair_kernel_attrs_once() {
   if (e != cudaSuccess) return cuda_err(e, "gemm 2cta smem attribute");
   e = cudaFuncSetAttribute(gemm_bf16_4cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_err(e, "gemm 4cta smem attribute");
+  e = cudaFuncSetAttribute(gemm_grad_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_err(e, "gemm dgrad 2cta smem attribute");
+  e = cudaFuncSetAttribute(gemm_grad_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_err(e, "gemm wgrad 2cta smem attribute");
   rc = B2F_OK;
   return rc;
 }
 
+template <int MODE = 0>
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg;
   if (int rc = pair_kernel_attrs_once()) return rc;
@@ -660,10 +768,14 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int max_pairs = device_info().num_sms / 2;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  const double kk = MODE == 2 ? (double)p.kbatch * p.K : (double)p.K;
   prof_begin(KC_GEMM, stream);
-  gemm_bf16_2cta_kernel<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * p.K,
-           2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N));
+  if constexpr (MODE == 0)
+    gemm_bf16_2cta_kernel<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  else
+    gemm_grad_2cta_kernel<MODE><<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * kk,
+           2.0 * ((double)p.batch * p.M * kk + (double)p.N * kk + (double)p.batch * p.M * p.N));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("gemm_bf16_2cta_kernel");
   return B2F_OK;
@@ -736,7 +848,7 @@ static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* 
        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
        reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(gate)) & 15)
     return B2F_ERR_ALIGN;
-  if (epilogue < 0 || epilogue > B2F_EPI_QUICK_GELU) return B2F_ERR_INVALID;
+  if (epilogue < 0 || epilogue > B2F_EPI_QUICK_GELU) return B2F_ERR_INVALID;  // backward epilogues: gemm_dgrad / gemm_wgrad
   if (epilogue == B2F_EPI_QKV_NORM_ROPE) {
     if (!qx || !qx->nw_q || !qx->nw_k || !qx->cos || !qx->sin || qx->d_model <= 0) return B2F_ERR_INVALID;
     if (N != 3 * qx->d_model + qx->n_extra || (qx->d_model % 128) || (qx->n_extra & 7)) return B2F_ERR_UNSUPPORTED;
@@ -800,7 +912,7 @@ static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* 
     if (rc2 != B2F_OK) return rc2;
     rc2 = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, BLOCK_K);
     if (rc2 != B2F_OK) return rc2;
-    return quad ? launch_gemm_4cta(tmA, tmB, p, stream) : launch_gemm_2cta(tmA, tmB, p, stream);
+    return quad ? launch_gemm_4cta(tmA, tmB, p, stream) : launch_gemm_2cta<0>(tmA, tmB, p, stream);
   }
   int rc = make_tmap_3d_rows(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)lda,
                              batch > 1 ? (uint64_t)a_bs : (uint64_t)M * lda);
@@ -818,6 +930,83 @@ int gemm_bf16(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t l
   if (epilogue == B2F_EPI_QKV_NORM_ROPE) return B2F_ERR_INVALID;  // needs the extended entry point
   return gemm_bf16_impl(A, lda, a_bs, W, ldw, bias, out, ldc, out_bs, batch, M, N, K, epilogue, resid, ldr,
                         resid_bs, gate, gate_ld, nullptr, stream);
+}
+
+// dX[batch, M, N] = epi(dY[batch, M, K] . W[K, N]) with W exactly as nn.Linear stores it ([out = K, in = N]): the
+// backward-data GEMM of every linear layer on the training path (reference train_denoiser.py:1172,
+// accelerator.backward -> autograd of F.linear).  Epilogues: B2F_EPI_BIAS (plain store), B2F_EPI_DGELU /
+// B2F_EPI_DSILU (times act'(u), u = `resid` [batch, M, N]), B2F_EPI_RESID (accumulate into another gradient).
+int gemm_dgrad(const void* dY, int64_t ldy, int64_t dy_bs, const void* W, int64_t ldw, void* dX, int64_t ldx,
+               int64_t dx_bs, int batch, int M, int N, int K, int epilogue, const void* aux, int64_t ld_aux,
+               int64_t aux_bs, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0 || !dY || !W || !dX) return B2F_ERR_INVALID;
+  if ((K & 7) || (N & 7) || (ldy & 7) || (ldw & 7) || (ldx & 7) || (dy_bs & 7) || (dx_bs & 7)) return B2F_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dX) |
+       reinterpret_cast<uintptr_t>(aux)) & 15)
+    return B2F_ERR_ALIGN;
+  if (epilogue != B2F_EPI_BIAS && epilogue != B2F_EPI_DGELU && epilogue != B2F_EPI_DSILU && epilogue != B2F_EPI_RESID)
+    return B2F_ERR_INVALID;
+  if (epilogue != B2F_EPI_BIAS && (!aux || (ld_aux & 7) || (aux_bs & 7))) return B2F_ERR_INVALID;
+  GemmParams p{};
+  p.batch = batch;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.out = static_cast<__nv_bfloat16*>(dX);
+  p.ldc = ldx;
+  p.out_bs = dx_bs;
+  p.epi = epilogue;
+  p.resid = static_cast<const __nv_bfloat16*>(aux);
+  p.ldr = ld_aux;
+  p.resid_bs = aux_bs;
+  CUtensorMap tmA, tmB;
+  const long long pair_tiles = (long long)batch * ((M + 255) / 256) * ((N + 255) / 256);
+  const bool pair = N >= 256 && pair_tiles >= device_info().num_sms / 2;
+  int rc = make_tmap_3d_rows(&tmA, dY, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)ldy,
+                             batch > 1 ? (uint64_t)dy_bs : (uint64_t)M * ldy);
+  if (rc != B2F_OK) return rc;
+  rc = make_tmap_2d_bf16(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, 64, 64);   // 64 (k) x 64 (n) boxes
+  if (rc != B2F_OK) return rc;
+  if (pair) return launch_gemm_2cta<1>(tmA, tmB, p, stream);
+  const long long num_m = (long long)batch * ((M + BLOCK_M - 1) / BLOCK_M);
+  const bool use256 = num_m * ((N + 255) / 256) >= device_info().num_sms && N >= 256;
+  return use256 ? launch_gemm<256, 1>(tmA, tmB, p, stream) : launch_gemm<128, 1>(tmA, tmB, p, stream);
+}
+
+// dW[M, N] (+)= sum_b dY[b, :, M]^T . X[b, :, N]  (fp32 output, contraction over the `rows` tokens of every batch
+// item): the backward-weight GEMM of the trainable projections (reference train_denoiser.py:71-119 names them).
+// dY: [batch, rows, >= M] view, X: [batch, rows, >= N] view (token pitches ldy / ldx, batch pitches in elements).
+int gemm_wgrad(const void* dY, int64_t ldy, int64_t dy_bs, const void* X, int64_t ldx, int64_t x_bs, float* dW,
+               int64_t ldw, int batch, int rows, int M, int N, int accumulate, cudaStream_t stream) {
+  if (!device_info().ok) return B2F_ERR_NODEVICE;
+  if (batch <= 0 || rows <= 0 || M <= 0 || N <= 0 || !dY || !X || !dW) return B2F_ERR_INVALID;
+  if ((M & 7) || (N & 7) || (ldy & 7) || (ldx & 7) || (dy_bs & 7) || (x_bs & 7) || (ldw & 3)) return B2F_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(dW)) & 15)
+    return B2F_ERR_ALIGN;
+  GemmParams p{};
+  p.batch = 1;
+  p.M = M;
+  p.N = N;
+  p.K = rows;
+  p.kbatch = batch;
+  p.kb_per_batch = (rows + BLOCK_K - 1) / BLOCK_K;
+  p.out = reinterpret_cast<__nv_bfloat16*>(dW);
+  p.ldc = ldw;
+  p.out_bs = 0;
+  p.epi = accumulate ? B2F_EPI_F32_ACC : B2F_EPI_F32;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_3d_rows(&tmA, dY, (uint64_t)M, (uint64_t)rows, (uint64_t)batch, (uint64_t)ldy,
+                             batch > 1 ? (uint64_t)dy_bs : (uint64_t)rows * ldy, 64);
+  if (rc != B2F_OK) return rc;
+  rc = make_tmap_3d_rows(&tmB, X, (uint64_t)N, (uint64_t)rows, (uint64_t)batch, (uint64_t)ldx,
+                         batch > 1 ? (uint64_t)x_bs : (uint64_t)rows * ldx, 64);
+  if (rc != B2F_OK) return rc;
+  const long long pair_tiles = (long long)((M + 255) / 256) * ((N + 255) / 256);
+  if (N >= 256 && pair_tiles >= device_info().num_sms / 2) return launch_gemm_2cta<2>(tmA, tmB, p, stream);
+  const long long num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const bool use256 = num_m * ((N + 255) / 256) >= device_info().num_sms && N >= 256;
+  return use256 ? launch_gemm<256, 2>(tmA, tmB, p, stream) : launch_gemm<128, 2>(tmA, tmB, p, stream);
 }
 
 int gemm_qkv_norm_rope(const void* A, int64_t lda, int64_t a_bs, const void* W, int64_t ldw,

@@ -88,6 +88,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -136,8 +144,8 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 // Instruction descriptor, kind::f16, BF16 x BF16 -> F32.
 //  [4,6) c_format=1(F32)  [7,10) a_format=1(BF16)  [10,13) b_format=1(BF16)
 //  [15] a_major (0=K)  [16] b_major (0=K, 1=MN)  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(b_mn_major) << 16) |
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_mn_major, int a_mn_major = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
@@ -178,6 +186,24 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
       "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),          \
       "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]),          \
       "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)                                               \
+      : "memory")
+
+#define B2F_TMEM_LD_X16(taddr, r)                                                                   \
+  asm volatile(                                                                                     \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                     \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                             \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),        \
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),    \
+        "=r"(r[14]), "=r"(r[15])                                                                    \
+      : "r"(taddr)                                                                                  \
+      : "memory")
+#define B2F_TMEM_ST_X16(taddr, r)                                                                   \
+  asm volatile(                                                                                     \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "                                              \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"                                    \
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),     \
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),            \
+      "r"(r[15]), "r"(taddr)                                                                        \
       : "memory")
 
 #define B2F_TMEM_LD_X8(taddr, r)                                                                    \

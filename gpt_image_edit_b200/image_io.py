@@ -41,3 +41,73 @@ def resize_u8(image_u8: np.ndarray, height: int, width: int) -> np.ndarray:
     from PIL import Image
 
     return np.asarray(Image.fromarray(image_u8).resize((width, height), Image.BICUBIC))
+
+
+# ------------------------------------------------------------------------------------------------
+# `qwen_vl_utils.process_vision_info` (un-vendored dependency of the reference, requirements.txt:34, unpinned;
+# algorithm as published in qwen-vl-utils 0.0.8-0.0.11 `vision_process.py`), images only.  Reference call sites:
+# univa/serve/cli.py:189, univa/eval/gedit/step1_gen_samples.py:143.
+IMAGE_FACTOR = 28
+MIN_PIXELS = 4 * 28 * 28
+MAX_PIXELS = 16384 * 28 * 28
+MAX_RATIO = 200
+
+
+def smart_resize(height: int, width: int, factor: int = IMAGE_FACTOR, min_pixels: int = MIN_PIXELS,
+                 max_pixels: int = MAX_PIXELS):
+    """(h, w): both multiples of `factor`, area within [min_pixels, max_pixels], aspect ratio kept as closely as the
+    grid allows (the rule `AutoProcessor(min_pixels=max_pixels=448*448)` applies, reference cli.py:51-55)."""
+    import math
+
+    if max(height, width) / min(height, width) > MAX_RATIO:
+        raise ValueError(f"absolute aspect ratio must be smaller than {MAX_RATIO}, got {max(height, width) / min(height, width)}")
+    h_bar = max(factor, round(height / factor) * factor)
+    w_bar = max(factor, round(width / factor) * factor)
+    if h_bar * w_bar > max_pixels:
+        beta = math.sqrt((height * width) / max_pixels)
+        h_bar = max(factor, math.floor(height / beta / factor) * factor)
+        w_bar = max(factor, math.floor(width / beta / factor) * factor)
+    elif h_bar * w_bar < min_pixels:
+        beta = math.sqrt(min_pixels / (height * width))
+        h_bar = math.ceil(height * beta / factor) * factor
+        w_bar = math.ceil(width * beta / factor) * factor
+    return h_bar, w_bar
+
+
+def fetch_image(ele: dict, size_factor: int = IMAGE_FACTOR):
+    """One {"type": "image", "image": path | PIL.Image, [min_pixels, max_pixels | resized_height, resized_width]}
+    content item -> RGB PIL image resized as qwen_vl_utils.fetch_image does (PIL's default bicubic)."""
+    from PIL import Image
+
+    image = ele.get("image", ele.get("image_url"))
+    if isinstance(image, Image.Image):
+        obj = image
+    elif isinstance(image, str) and image.startswith("file://"):
+        obj = Image.open(image[7:])
+    elif isinstance(image, str) and image.startswith(("http://", "https://", "data:image")):
+        raise ValueError("remote / inline images are not supported offline: pass a local path")
+    else:
+        obj = Image.open(image)
+    obj = obj.convert("RGB")
+    if "resized_height" in ele and "resized_width" in ele:
+        rh, rw = smart_resize(ele["resized_height"], ele["resized_width"], factor=size_factor)
+    else:
+        w, h = obj.size
+        rh, rw = smart_resize(h, w, factor=size_factor, min_pixels=ele.get("min_pixels", MIN_PIXELS),
+                              max_pixels=ele.get("max_pixels", MAX_PIXELS))
+    return obj.resize((rw, rh))
+
+
+def process_vision_info(conversation: list):
+    """(image_inputs | None, video_inputs = None) for a list of chat messages, in message order."""
+    images = []
+    for message in conversation:
+        content = message.get("content")
+        if not isinstance(content, list):
+            continue
+        for ele in content:
+            if "image" in ele or "image_url" in ele or ele.get("type") in ("image", "image_url"):
+                images.append(fetch_image(ele))
+            elif "video" in ele or ele.get("type") == "video":
+                raise ValueError("video inputs are not supported (the reference's serving path is image-only)")
+    return (images or None), None

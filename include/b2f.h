@@ -75,6 +75,11 @@ int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* fl
 #define B2F_EPI_QKV_NORM_ROPE 6 /* only through b2f_gemm_qkv_norm_rope */
 #define B2F_EPI_GELU_ERF 5 /* out = bf16(gelu_erf(bf16(acc + bias)))  (Qwen2.5-VL patch merger, nn.GELU()) */
 #define B2F_EPI_QUICK_GELU 7 /* out = bf16(x * bf16(sigmoid(bf16(1.702 x)))), x = bf16(acc + bias)  (CLIP-L MLP) */
+/* backward epilogues (b2f_gemm_dgrad / b2f_gemm_wgrad only) */
+#define B2F_EPI_DGELU 8   /* out = bf16(bf16(acc) * gelu_tanh'(u)),  u = saved pre-activation */
+#define B2F_EPI_DSILU 9   /* out = bf16(bf16(acc) * silu'(u)) */
+#define B2F_EPI_F32 10    /* fp32 store (weight gradients) */
+#define B2F_EPI_F32_ACC 11 /* fp32 accumulate: out += acc (gradient accumulation steps) */
 
 int b2f_gemm_bf16(const void* A, int64_t lda, int64_t a_batch_stride, const void* W, int64_t ldw,
                   const void* bias, void* out, int64_t ldc, int64_t out_batch_stride, int batch,
@@ -298,6 +303,91 @@ int b2f_softmax_rows(void* s, int64_t ld, int rows, int L, float scale, b2f_stre
 /* out[c, r] = in[r, c] for an [R, Cc] bf16 matrix. */
 int b2f_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int Cc,
                        b2f_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage-2 training step (reference train_denoiser.py:829-1181; trainable set :71-119; AdamW :596-602;
+ * clip_grad_norm_ :1174-1177; ZeRO-2 sharding scripts/accelerate_configs/zero2.json).  The reference reaches all of
+ * this through torch.autograd over diffusers' eager modules; here every backward op is its own kernel.
+ * Activations and activation gradients are bf16, weight gradients and token reductions fp32.
+ */
+/* Backward-data GEMM of nn.Linear: dX[batch, M, N] = epi(dY[batch, M, K] · W[K, N]) with W as stored ([out = K, in = N],
+ * read as an MN-major tcgen05 operand: no transposed copy).  epilogue: B2F_EPI_BIAS (store), B2F_EPI_DGELU /
+ * B2F_EPI_DSILU (times act'(aux), aux = saved pre-activation [batch, M, N]), B2F_EPI_RESID (dX = aux + result). */
+int b2f_gemm_dgrad(const void* dY, int64_t ldy, int64_t dy_batch_stride, const void* W, int64_t ldw, void* dX,
+                   int64_t ldx, int64_t dx_batch_stride, int batch, int M, int N, int K, int epilogue, const void* aux,
+                   int64_t ld_aux, int64_t aux_batch_stride, b2f_stream_t stream);
+/* Backward-weight GEMM: dW[M, N] (+)= sum_b dY[b, :rows, :M]^T · X[b, :rows, :N], fp32 output (pitch ldw floats); both
+ * operands are token-major activations read as MN-major tcgen05 operands. */
+int b2f_gemm_wgrad(const void* dY, int64_t ldy, int64_t dy_batch_stride, const void* X, int64_t ldx,
+                   int64_t x_batch_stride, float* dW, int64_t ldw, int batch, int rows, int M, int N, int accumulate,
+                   b2f_stream_t stream);
+/* b2f_attention_fwd that also writes lse2[b, h, q] = log2(sum_k exp2(scale*log2(e) * q.k)) at
+ * lse + (b*H + h)*lse_stride + q (lse_stride >= Sq; use a multiple of 128 for the backward). */
+int b2f_attention_fwd_lse(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                          int64_t ldo, int B, int H, int Hkv, int Sq, int Skv, int head_dim, float scale, int causal,
+                          float* lse, int64_t lse_stride, b2f_stream_t stream);
+/* delta[b, h, s] = sum_c dO * O for s < S; delta = 0 and lse = +inf for S <= s < S_pad (padding the backward relies on).
+ * delta / lse: fp32 [B, H, S_pad]. */
+int b2f_attn_delta(const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta, float* lse, int B, int H,
+                   int S, int S_pad, b2f_stream_t stream);
+/* Attention backward (non-causal, H == Hkv, head_dim 128): dq, dk, dv from q, k, v, dout, lse2 and delta.  Two
+ * tcgen05 kernels (dK/dV with the scores held transposed in TMEM; dQ), no atomics: bit-reproducible.  All tensors
+ * token-major [B, S, H*128] views.  S_pad: pitch of the lse / delta rows, a multiple of 128. */
+int b2f_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                      const void* dout, int64_t lddo, const float* lse, const float* delta, int64_t S_pad, void* dq,
+                      int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int S, int head_dim,
+                      float scale, b2f_stream_t stream);
+/* Row chunking of the column-reduction kernels below: partial buffers hold one fp32 row per chunk. */
+int b2f_train_chunks(int rows);
+int b2f_train_ln_chunks(int rows);
+/* out = bf16(x + bf16(gate[b] * y)) over [batch, rows, D] views (the GATE_RESID epilogue unfused: training keeps y). */
+int b2f_gate_resid_fwd(const void* x, int64_t ldx, int64_t x_bs, const void* y, int64_t ldy, int64_t y_bs,
+                       const void* gate, const void* gate_b, int64_t gate_ld, void* out, int64_t ldo, int64_t o_bs,
+                       int batch, int rows, int D, int split_row, b2f_stream_t stream);
+/* dy = bf16(gate[b] * dout) (dy / gate may be NULL) and per-chunk column sums of dout*y (y NULL: of dout) over rows
+ * >= part_row0 into partial[batch, b2f_train_chunks(rows), D] (NULL: none).  Bias, gate gradients. */
+int b2f_gate_bwd(const void* dout, int64_t ldd, int64_t d_bs, const void* y, int64_t ldy, int64_t y_bs, const void* gate,
+                 const void* gate_b, int64_t gate_ld, void* dy, int64_t ldo, int64_t o_bs, float* partial, int batch,
+                 int rows, int D, int split_row, int part_row0, b2f_stream_t stream);
+/* out[b, c] (+)= sum_k partial[b, k, c] in a fixed order. */
+int b2f_col_reduce(const float* partial, int nchunks, int D, float* out, int64_t out_ld, int batch, int accumulate,
+                   b2f_stream_t stream);
+/* Backward of b2f_ln_modulate: dres_out = bf16(dres_in + bf16(dx)); per-chunk column sums (dscale | dshift) over rows
+ * >= part_row0 into partial[batch, b2f_train_ln_chunks(rows), 2*D] (NULL: none).  dres_in may be NULL or alias dres_out. */
+int b2f_ln_modulate_bwd(const void* x, int64_t ldx, int64_t x_bs, const void* dy, int64_t ldy, int64_t dy_bs,
+                        const void* scale, const void* scale_b, int64_t mod_ld, const void* dres_in, int64_t ldr,
+                        int64_t r_bs, void* dres_out, int64_t ldo, int64_t o_bs, float* partial, int batch, int rows,
+                        int D, float eps, int split_row, int part_row0, b2f_stream_t stream);
+/* b2f_rmsnorm_rope out of place (training keeps the pre-norm projections), and its backward: in place on the Q / K
+ * column blocks of the gradient buffer; partial[(batch*S + 7)/8, 512] receives per-block RMSNorm-weight gradient rows
+ * [wq_a | wk_a | wq_b | wk_b] (NULL: none). */
+int b2f_rmsnorm_rope_out(const void* xq, const void* xk, int64_t ldx, int64_t x_bs, void* oq, void* ok, int64_t ldo,
+                         int64_t o_bs, const void* wq_a, const void* wk_a, const void* wq_b, const void* wk_b,
+                         const float* cos, const float* sin, int batch, int S, int H, int n_a, float eps,
+                         b2f_stream_t stream);
+int b2f_rmsnorm_rope_bwd(void* dq, void* dk, int64_t ld, int64_t bs, const void* xq, const void* xk, int64_t ldx,
+                         int64_t x_bs, const void* wq_a, const void* wk_a, const void* wq_b, const void* wk_b,
+                         const float* cos, const float* sin, float* partial, int batch, int S, int H, int n_a, float eps,
+                         b2f_stream_t stream);
+/* y = gelu_tanh(x) over a [rows, D] view. */
+int b2f_gelu_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int D, b2f_stream_t stream);
+/* dW[n, k] (+)= sum_b dmod[b, n] * act[b, k]: weight gradient of an AdaLN linear (dmod fp32, act bf16, dW fp32). */
+int b2f_outer_acc(const float* dmod, int64_t dmod_ld, const void* act, int64_t act_ld, float* dW, int64_t ldw, int B,
+                  int N, int K, int accumulate, b2f_stream_t stream);
+/* Flow-matching loss (train_denoiser.py:1105-1167): *loss_out = mean(w * (pred - target)^2); dpred = bf16(2 w (pred -
+ * target) * grad_scale / n).  pred bf16, target / w fp32 (w NULL: 1), ws: 1024 floats of scratch. */
+int b2f_mse_loss(const void* pred, const float* target, const float* w, void* dpred, float* loss_out, float* ws,
+                 int64_t n, float grad_scale, b2f_stream_t stream);
+/* *sumsq_out (+)= sum(g^2) over a flat fp32 gradient shard (ws: 1024 floats); coef = min(1, max_norm / (pre_scale *
+ * sqrt(sumsq) + 1e-6)) * pre_scale — accelerate's clip_grad_norm_ folded into the gradient scale AdamW applies. */
+int b2f_grad_sumsq(const float* g, int64_t n, float* sumsq_out, float* ws, int accumulate, b2f_stream_t stream);
+int b2f_clip_coef(const float* sumsq, float max_norm, float pre_scale, float* coef, float* norm_out, b2f_stream_t stream);
+/* torch.optim.AdamW on flat fp32 shards (master weights p32, moments m / v), gradient scaled by *gscale (device scalar,
+ * NULL: 1), bf16 copy of the new weights written to p16 (NULL: none).  step counts from 1. */
+int b2f_adamw_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* gscale, b2f_stream_t stream);
+/* bf16 <-> fp32 copies of flat arrays (master-weight initialisation, gradient buckets). */
+int b2f_cast_bf16_f32(const void* src, void* dst, int64_t n, int to_f32, b2f_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * FLUX VAE (diffusers AutoencoderKL) as one object.  Replaces `pipe.vae.encode(x)` /
