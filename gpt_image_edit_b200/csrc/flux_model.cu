@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "flux_ctx.h"
 #include "host_common.h"
 
 namespace b2f {
@@ -44,36 +45,6 @@ int rmsnorm_rope(void* q, void* k, int64_t ld, int64_t batch_stride, const void*
 int temb_sinusoid(const float* t, void* out, int rows, cudaStream_t stream);
 int temb_combine(const void* t, const void* g, const void* txt, void* temb, void* silu_temb,
                  int64_t n, cudaStream_t stream);
-
-typedef uint16_t bf16_t;
-
-struct Lin {
-  const bf16_t* w = nullptr;
-  const bf16_t* b = nullptr;
-};
-struct DoubleW {
-  Lin qkv, add_qkv, to_out, to_add_out, ff1, ff2, ffc1, ffc2;
-  const bf16_t *norm_q = nullptr, *norm_k = nullptr, *norm_added_q = nullptr, *norm_added_k = nullptr;
-};
-struct SingleW {
-  Lin qkv_mlp, proj_out;
-  const bf16_t *norm_q = nullptr, *norm_k = nullptr;
-};
-
-struct FluxCtx {
-  b2f_flux_cfg cfg;
-  int d = 0;
-  std::map<std::string, std::pair<const void*, int64_t>> bound;
-  Lin x_embedder, context_embedder, proj_out, adaln;
-  Lin t1, t2, g1, g2, p1, p2;
-  std::vector<DoubleW> dbl;
-  std::vector<SingleW> sgl;
-  const float* rope_cos = nullptr;
-  const float* rope_sin = nullptr;
-  int rope_S = 0;
-  bool finalized = false;
-  int64_t mod_width = 0;
-};
 
 static int64_t mod_width_of(const b2f_flux_cfg& c) {
   const int64_t d = (int64_t)c.num_heads * c.head_dim;

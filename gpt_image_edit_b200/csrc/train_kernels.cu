@@ -275,21 +275,26 @@ struct NormRopeBwdParams {
 };
 
 __global__ void __launch_bounds__(256) rmsnorm_rope_bwd_kernel(const NormRopeBwdParams p) {
-  __shared__ float acc_sm[512];
-  for (int i = threadIdx.x; i < 512; i += 256) acc_sm[i] = 0.f;
-  __syncthreads();
+  // per-warp weight-gradient rows, summed in a fixed order afterwards (no atomics: bit-reproducible)
+  __shared__ float acc_sm[8][256];
+  __shared__ int set_sm[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * 8 + warp;
   const int is_k = lane >> 4;
   const int l16 = lane & 15;
+  float dw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dw[j] = 0.f;
+  int my_set = -1;   // -1: no token, 0: weight set a (text rows), 1: set b
   if (tok < (long long)p.batch * p.S) {
     const int b = int(tok / p.S);
     const int s = int(tok - (long long)b * p.S);
     __nv_bfloat16* gbase = (is_k ? p.dk : p.dq) + b * p.batch_stride + s * p.ld + l16 * 8;
     const __nv_bfloat16* xbase = (is_k ? p.xk : p.xq) + b * p.x_batch_stride + s * p.ldx + l16 * 8;
     const bool set_a = s < p.n_a;
+    my_set = set_a ? 0 : 1;
     const __nv_bfloat16* wptr = is_k ? (set_a ? p.wk_a : p.wk_b) : (set_a ? p.wq_a : p.wq_b);
-    float w[8], cs[8], sn[8], dw[8];
+    float w[8], cs[8], sn[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(wptr + l16 * 8)), w);
     {
       const float4* c4 = reinterpret_cast<const float4*>(p.cos + (long long)s * 128 + l16 * 8);
@@ -300,8 +305,6 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_bwd_kernel(const NormRopeBwd
       sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w;
       sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dw[j] = 0.f;
 #pragma unroll 2
     for (int h = 0; h < p.H; ++h) {
       float x[8], d[8], dy[8], o[8];
@@ -331,13 +334,21 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_bwd_kernel(const NormRopeBwd
       for (int j = 0; j < 8; ++j) o[j] = r * (dy[j] * w[j] - x[j] * k2);
       *reinterpret_cast<uint4*>(gbase + h * 128) = pack8(o);
     }
-    float* dst = acc_sm + (set_a ? 0 : 256) + is_k * 128 + l16 * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(dst + j, dw[j]);
   }
+  if (!p.partial) return;
+  float* dst = &acc_sm[warp][is_k * 128 + l16 * 8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[j] = dw[j];
+  if (lane == 0) set_sm[warp] = my_set;
   __syncthreads();
-  if (p.partial)
-    for (int i = threadIdx.x; i < 512; i += 256) p.partial[(long long)blockIdx.x * 512 + i] = acc_sm[i];
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int set = i >> 8, c = i & 255;
+    float sum = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi)
+      if (set_sm[wi] == set) sum += acc_sm[wi][c];
+    p.partial[(long long)blockIdx.x * 512 + i] = sum;
+  }
 }
 
 // out-of-place forward used by the training step (keeps the pre-norm projections for the kernel above)

@@ -203,8 +203,9 @@ class B200FluxTransformer2DModel(torch.nn.Module):
             self._ws[tag] = buf
         return buf
 
-    def _temb_mod(self, t1000: torch.Tensor, g1000: torch.Tensor | None, pooled: torch.Tensor):
-        """rows of (timestep*1000, guidance*1000) fp32 + pooled bf16 -> (temb, mod) via the C ABI."""
+    def _temb_mod(self, t1000: torch.Tensor, g1000: torch.Tensor | None, pooled: torch.Tensor, want_silu: bool = False):
+        """rows of (timestep*1000, guidance*1000) fp32 + pooled bf16 -> (temb, mod) via the C ABI
+        (want_silu: also silu(temb), the input of every AdaLN linear — the training step needs it)."""
         rows = t1000.numel()
         d = self.inner_dim
         temb = torch.empty((rows, d), device=self.device, dtype=torch.bfloat16)
@@ -215,6 +216,8 @@ class B200FluxTransformer2DModel(torch.nn.Module):
         check(_lib.lib.b2f_flux_temb(self._h, ptr(t1000), ptr(g1000), ptr(pooled), pooled.stride(0), rows,
                                      ptr(temb), ptr(stemb), ptr(ws), nws, stream_ptr()), "b2f_flux_temb")
         check(_lib.lib.b2f_flux_modulation(self._h, ptr(stemb), rows, ptr(mod), stream_ptr()), "b2f_flux_modulation")
+        if want_silu:
+            return temb, mod, stemb
         return temb, mod
 
     @staticmethod
@@ -239,6 +242,21 @@ class B200FluxTransformer2DModel(torch.nn.Module):
         self._schedule = SimpleNamespace(n=n, B=B, mod=mod.view(n, B, self.mod_width))
         return self._schedule
 
+    def _set_rope(self, txt_ids, img_ids, S_txt: int, S_img: int):
+        """FluxPosEmbed tables for [txt; img] ids, handed to the engine (rebuilt only when the ids change)."""
+        if txt_ids.dim() == 3:
+            txt_ids = txt_ids[0]
+        if img_ids.dim() == 3:
+            img_ids = img_ids[0]
+        key = (txt_ids.data_ptr(), img_ids.data_ptr(), S_txt, S_img, txt_ids._version, img_ids._version)
+        if self._rope is None or self._rope[0] != key:
+            from . import ops
+            ids = torch.cat((txt_ids.float(), img_ids.float()), dim=0).contiguous()
+            cos, sin = ops.rope_tables(ids, tuple(self.config.axes_dims_rope))
+            self._rope = (key, cos, sin, (txt_ids, img_ids))
+        _, cos, sin, _keep = self._rope
+        check(_lib.lib.b2f_flux_set_rope(self._h, ptr(cos), ptr(sin), S_txt + S_img), "b2f_flux_set_rope")
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None,
@@ -253,19 +271,7 @@ class B200FluxTransformer2DModel(torch.nn.Module):
         S = S_txt + S_img
         hs = hidden_states.to(torch.bfloat16).contiguous()
         enc = encoder_hidden_states.to(torch.bfloat16).contiguous()
-        if txt_ids.dim() == 3:
-            txt_ids = txt_ids[0]
-        if img_ids.dim() == 3:
-            img_ids = img_ids[0]
-        # RoPE tables are a pure function of the ids; rebuild only when the ids object changes
-        key = (txt_ids.data_ptr(), img_ids.data_ptr(), S_txt, S_img, txt_ids._version, img_ids._version)
-        if self._rope is None or self._rope[0] != key:
-            from . import ops
-            ids = torch.cat((txt_ids.float(), img_ids.float()), dim=0).contiguous()
-            cos, sin = ops.rope_tables(ids, tuple(cfg.axes_dims_rope))
-            self._rope = (key, cos, sin, (txt_ids, img_ids))
-        _, cos, sin, _keep = self._rope
-        check(_lib.lib.b2f_flux_set_rope(self._h, ptr(cos), ptr(sin), S), "b2f_flux_set_rope")
+        self._set_rope(txt_ids, img_ids, S_txt, S_img)
 
         step = jak.get("_b2f_schedule_step")
         if step is not None and self._schedule is not None and self._schedule.B == B:

@@ -1,0 +1,359 @@
+"""Stage-2 training engine over libb2f (reference train_denoiser.py:829-1181, scripts/accelerate_configs/zero2.json).
+
+What the reference assembles from accelerate + DeepSpeed ZeRO-2 + torch.autograd, written out for this engine:
+
+  FluxTrainGraph       forward with per-block checkpoints / backward with per-block recompute of the FLUX denoiser
+                       (`b2f_flux_train_forward` / `b2f_flux_train_backward`) plus MLP2's forward / backward
+                       (two tcgen05 GEMMs each way), gradients in fp32
+  trainable_params()   the reference's trainable set (train_denoiser.py:71-119, 519-548) mapped onto this repo's
+                       fused weight storage
+  ShardedAdamW         ZeRO-2: gradients live in per-block buckets; each bucket is reduce-scattered (NCCL, fp32)
+                       as soon as its block's backward has been enqueued — on a side stream, overlapping the
+                       backward of the next block —, every rank keeps fp32 master weights and Adam moments for
+                       its 1/world slice only, clips by the global norm, updates its slice and all-gathers the new
+                       bf16 weights (zero2.json: stage 2, reduce_scatter true, overlap_comm true)
+
+All arithmetic is libb2f (`train_ops`); torch provides storage, streams and the process group.  The `math`
+argument exists so that the CPU `gloo` tests can substitute the oracle's torch implementations for the CUDA
+kernels when they check the sharding logic; the product never passes it.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------------ trainable set
+def get_trainable_params(layers_to_train=None, num_transformer_blocks: int = 19, only_img_branch: bool = True):
+    """Component-name list of the reference (train_denoiser.py:71-112), same strings in the same order."""
+    layers_to_train = list(range(57)) if layers_to_train is None else layers_to_train
+    components = []
+    transformer_components = ["attn.norm_q", "attn.norm_k", "attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out", "norm1.linear"]
+    single_transformer_components = ["attn.norm_q", "attn.norm_k", "attn.to_q", "attn.to_k", "attn.to_v", "norm.linear"]
+    if not only_img_branch:
+        transformer_components.extend(["norm1_context.linear", "attn.norm_added_q", "attn.norm_added_k", "ff.net", "ff_context.net"])
+        single_transformer_components.extend(["proj_mlp", "proj_out"])
+    for layer in layers_to_train:
+        if layer < num_transformer_blocks:
+            prefix = f"denoise_tower.denoiser.transformer_blocks.{layer}"
+            base = transformer_components
+        else:
+            prefix = f"denoise_tower.denoiser.single_transformer_blocks.{layer - num_transformer_blocks}"
+            base = single_transformer_components
+        components.extend([f"{prefix}.{comp}" for comp in base])
+    return components
+
+
+def check_param_is_in_components(name: str, components) -> bool:      # train_denoiser.py:118-119
+    return any(component in name for component in components)
+
+
+@dataclass
+class Param:
+    name: str            # diffusers-style name(s) this tensor answers to (for the log / checkpoint)
+    storage: torch.Tensor  # contiguous bf16 view into the model's weight storage
+    bind_key: str | None   # b2f_flux_bind_grad key (None: MLP2, handled in Python)
+    bucket: int
+    grad: torch.Tensor | None = None    # fp32 view into the bucket's flat gradient
+    offset: int = 0
+
+
+def trainable_params(model, layers_to_train=None, only_img_branch: bool = True, with_tune_mlp2: bool = True):
+    """[Param] for a UnivaQwen2p5VLForConditionalGeneration: bucket i = FLUX block i, last bucket = MLP2."""
+    if not only_img_branch:
+        raise _lib.B2FError("only_tune_image_branch=False (FF / text-stream weights) is not built: every stage yaml of the "
+                            "reference trains the image branch only")
+    den = model.denoise_tower.denoiser
+    cfg = den.config
+    d = den.inner_dim
+    nd, ns = cfg.num_layers, cfg.num_single_layers
+    layers = list(range(nd + ns)) if layers_to_train is None else [l for l in layers_to_train if l < nd + ns]
+    st = den._store
+    adaln_w, adaln_b = st["adaln.weight"], st["adaln.bias"]
+    out = []
+    for l in layers:
+        if l < nd:
+            p = f"transformer_blocks.{l}."
+            r0 = l * 12 * d
+            out += [Param(p + "attn.to_q|to_k|to_v.weight", st[p + "attn.qkv.weight"], p + "attn.qkv.weight", l),
+                    Param(p + "attn.to_q|to_k|to_v.bias", st[p + "attn.qkv.bias"], p + "attn.qkv.bias", l),
+                    Param(p + "attn.to_out.0.weight", st[p + "attn.to_out.0.weight"], p + "attn.to_out.0.weight", l),
+                    Param(p + "attn.to_out.0.bias", st[p + "attn.to_out.0.bias"], p + "attn.to_out.0.bias", l),
+                    Param(p + "attn.norm_q.weight", st[p + "attn.norm_q.weight"], p + "attn.norm_q.weight", l),
+                    Param(p + "attn.norm_k.weight", st[p + "attn.norm_k.weight"], p + "attn.norm_k.weight", l),
+                    Param(p + "norm1.linear.weight", adaln_w[r0:r0 + 6 * d], p + "norm1.linear.weight", l),
+                    Param(p + "norm1.linear.bias", adaln_b[r0:r0 + 6 * d], p + "norm1.linear.bias", l)]
+        else:
+            j = l - nd
+            p = f"single_transformer_blocks.{j}."
+            r0 = nd * 12 * d + j * 3 * d
+            out += [Param(p + "attn.to_q|to_k|to_v.weight", st[p + "qkv_mlp.weight"][:3 * d], p + "attn.qkv.weight", l),
+                    Param(p + "attn.to_q|to_k|to_v.bias", st[p + "qkv_mlp.bias"][:3 * d], p + "attn.qkv.bias", l),
+                    Param(p + "attn.norm_q.weight", st[p + "attn.norm_q.weight"], p + "attn.norm_q.weight", l),
+                    Param(p + "attn.norm_k.weight", st[p + "attn.norm_k.weight"], p + "attn.norm_k.weight", l),
+                    Param(p + "norm.linear.weight", adaln_w[r0:r0 + 3 * d], p + "norm.linear.weight", l),
+                    Param(p + "norm.linear.bias", adaln_b[r0:r0 + 3 * d], p + "norm.linear.bias", l)]
+    if with_tune_mlp2:
+        proj = model.denoise_tower.denoise_projector
+        b = nd + ns
+        out += [Param("denoise_projector.0.weight", proj.w0, None, b), Param("denoise_projector.0.bias", proj.b0, None, b),
+                Param("denoise_projector.2.weight", proj.w2, None, b), Param("denoise_projector.2.bias", proj.b2, None, b)]
+    for q in out:
+        if not q.storage.is_contiguous():
+            raise _lib.B2FError(f"{q.name}: trainable storage must be contiguous")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ ZeRO-2 AdamW
+class _B2FMath:
+    """The CUDA kernels (train_ops).  CPU tests substitute oracle.train_oracle.TorchMath."""
+
+    @staticmethod
+    def cast_to_f32(src):
+        from . import train_ops as T
+        return T.cast(src.contiguous(), torch.float32)
+
+    @staticmethod
+    def sumsq(g, out, accumulate):
+        from . import train_ops as T
+        T.grad_sumsq(g, out=out, accumulate=accumulate)
+
+    @staticmethod
+    def clip_coef(sumsq, max_norm, pre_scale):
+        from . import train_ops as T
+        return T.clip_coef(sumsq, max_norm, pre_scale)
+
+    @staticmethod
+    def adamw(p32, m, v, g, p16, **kw):
+        from . import train_ops as T
+        T.adamw_step_(p32, m, v, g, p16=p16, **kw)
+
+
+@dataclass
+class _Bucket:
+    params: list
+    size: int            # padded to a multiple of world * 64 elements
+    flat_grad: torch.Tensor = None     # fp32 [size]: this rank's (local) gradients of the bucket
+    shard_grad: torch.Tensor = None    # fp32 [size / world]: the reduced slice this rank owns
+    p32: torch.Tensor = None
+    m: torch.Tensor = None
+    v: torch.Tensor = None
+    flat_p16: torch.Tensor = None      # bf16 [size]: updated weights, all-gathered
+    reduced: torch.cuda.Event | None = None
+
+
+class ShardedAdamW:
+    """AdamW with ZeRO-2 partitioning over `group` (world 1: plain AdamW with fp32 master weights)."""
+
+    def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=1.0,
+                 group=None, math=None, comm_stream=None):
+        self.math = math or _B2FMath
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.lr, self.betas, self.eps, self.wd, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.step_count = 0
+        self.comm_stream = comm_stream
+        nb = max(p.bucket for p in params) + 1
+        self.buckets: list[_Bucket] = []
+        for b in range(nb):
+            ps = [p for p in params if p.bucket == b]
+            if not ps:
+                self.buckets.append(None)
+                continue
+            dev = ps[0].storage.device
+            off = 0
+            for p in ps:
+                p.offset = off
+                off += (p.storage.numel() + 63) // 64 * 64      # 256-byte aligned fp32 views for the TMA-free kernels
+            quantum = self.world * 64
+            size = (off + quantum - 1) // quantum * quantum
+            bk = _Bucket(ps, size)
+            bk.flat_grad = torch.zeros(size, device=dev, dtype=torch.float32)
+            for p in ps:
+                p.grad = bk.flat_grad[p.offset:p.offset + p.storage.numel()].view(p.storage.shape)
+            n = size // self.world
+            bk.shard_grad = bk.flat_grad if self.world == 1 else torch.zeros(n, device=dev, dtype=torch.float32)
+            # fp32 master copy of this rank's slice (DeepSpeed bf16 optimizer: fp32 partitions of the bf16 weights)
+            flat16 = torch.zeros(size, device=dev, dtype=torch.bfloat16)
+            for p in ps:
+                flat16[p.offset:p.offset + p.storage.numel()].copy_(p.storage.reshape(-1))
+            bk.flat_p16 = flat16
+            lo = self.rank * n
+            bk.p32 = self.math.cast_to_f32(flat16[lo:lo + n])
+            bk.m = torch.zeros_like(bk.p32)
+            bk.v = torch.zeros_like(bk.p32)
+            self.buckets.append(bk)
+        dev = params[0].storage.device
+        self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.last_grad_norm = None
+
+    # -- gradient reduction -------------------------------------------------------------------
+    def reduce_bucket(self, b: int):
+        """reduce-scatter bucket b's local gradients (sum over ranks) into this rank's slice.  Enqueued on the comm
+        stream after everything already enqueued on the current stream (the block's backward)."""
+        bk = self.buckets[b]
+        if bk is None or self.world == 1:
+            return
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.reduce_scatter_tensor(bk.shard_grad, bk.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+                bk.reduced = torch.cuda.Event()
+                bk.reduced.record(self.comm_stream)
+        else:
+            dist.reduce_scatter_tensor(bk.shard_grad, bk.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_all(self):
+        for b in range(len(self.buckets)):
+            self.reduce_bucket(b)
+
+    # -- the update ---------------------------------------------------------------------------
+    def step(self, lr: float | None = None):
+        """clip_grad_norm_(max_grad_norm) + AdamW on this rank's slices + all-gather of the new bf16 weights.
+        Gradients are averaged over ranks (DDP / ZeRO semantics): the 1/world factor is folded into the clip scale."""
+        lr = self.lr if lr is None else lr
+        self.step_count += 1
+        live = [bk for bk in self.buckets if bk is not None]
+        if self.comm_stream is not None and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for i, bk in enumerate(live):
+            self.math.sumsq(bk.shard_grad, self._sumsq, accumulate=i > 0)
+        if self.world > 1:
+            dist.all_reduce(self._sumsq, op=dist.ReduceOp.SUM, group=self.group)
+        coef, norm = self.math.clip_coef(self._sumsq, self.max_grad_norm, 1.0 / self.world)
+        self.last_grad_norm = norm
+        for bk in live:
+            n = bk.size // self.world
+            lo = self.rank * n
+            self.math.adamw(bk.p32, bk.m, bk.v, bk.shard_grad, bk.flat_p16[lo:lo + n], lr=lr, betas=self.betas, eps=self.eps,
+                            weight_decay=self.wd, step=self.step_count, gscale=coef)
+            if self.world > 1:
+                dist.all_gather_into_tensor(bk.flat_p16, bk.flat_p16[lo:lo + n].clone(), group=self.group)
+            for p in bk.params:        # scatter the flat bucket back into the model's (fused) weight storage
+                p.storage.copy_(bk.flat_p16[p.offset:p.offset + p.storage.numel()].view(p.storage.shape))
+        return norm
+
+    def zero_grad(self):
+        for bk in self.buckets:
+            if bk is not None:
+                bk.flat_grad.zero_()
+
+    def state_dict(self):
+        return {"step": self.step_count, "rank": self.rank, "world": self.world,
+                "buckets": [None if bk is None else {"p32": bk.p32, "m": bk.m, "v": bk.v} for bk in self.buckets]}
+
+    def load_state_dict(self, sd):
+        if sd["world"] != self.world:
+            raise _lib.B2FError(f"optimizer state was partitioned over {sd['world']} ranks, this run has {self.world}")
+        self.step_count = sd["step"]
+        for bk, s in zip(self.buckets, sd["buckets"]):
+            if bk is not None:
+                bk.p32.copy_(s["p32"]); bk.m.copy_(s["m"]); bk.v.copy_(s["v"])
+
+
+# ------------------------------------------------------------------------------------------------ forward / backward
+class FluxTrainGraph:
+    """One training forward/backward of MLP2 -> FLUX denoiser with the gradients of `params` accumulated into their
+    fp32 buffers.  Reference: lvlm_model(..., output_type="denoise_model_pred") + accelerator.backward(loss),
+    train_denoiser.py:1073-1093, 1172."""
+
+    def __init__(self, model, params, on_block_done=None):
+        self.model = model
+        self.den = model.denoise_tower.denoiser
+        self.proj = getattr(model.denoise_tower, "denoise_projector", None)
+        self.params = params
+        self.on_block_done = on_block_done          # callback(bucket) after a block's gradients are complete
+        self._bound = False
+        self._mlp2 = {p.name: p for p in params if p.bind_key is None}
+        self.n_blocks = self.den.config.num_layers + self.den.config.num_single_layers
+        self._trained_blocks = sorted({p.bucket for p in params if p.bind_key is not None})
+
+    def _bind(self):
+        for p in self.params:
+            if p.bind_key is not None:
+                check(_lib.lib.b2f_flux_bind_grad(self.den._h, p.bind_key.encode(), ptr(p.grad), p.grad.numel()),
+                      f"bind grad {p.bind_key}")
+        self._bound = True
+
+    def forward(self, vlm_hidden, hidden_states, timestep, guidance, pooled, img_ids, n_out_rows, prefix_embeds=None):
+        """vlm_hidden [B, L, 3584] (Qwen2.5-VL prefill output, frozen) -> MLP2 -> [vlm ‖ prefix] -> denoiser.
+        Returns model_pred [B, n_out_rows, 64] bf16 (the target tokens)."""
+        from . import ops
+        den = self.den
+        if not self._bound:
+            self._bind()
+        x = vlm_hidden.to(torch.bfloat16).contiguous()
+        self._x = x
+        self._pre = ops.linear(x, self.proj.w0, self.proj.b0)                     # kept for silu'
+        self._act = torch.empty_like(self._pre)
+        check(_lib.lib.b2f_silu(ptr(self._pre), ptr(self._act), self._pre.numel(), stream_ptr()), "b2f_silu")
+        enc_vlm = ops.linear(self._act, self.proj.w2, self.proj.b2)
+        self._L = enc_vlm.shape[1]
+        enc = enc_vlm if prefix_embeds is None else torch.cat([enc_vlm, prefix_embeds.to(torch.bfloat16)], dim=1)
+        enc = enc.contiguous()
+        B, S_img, _ = hidden_states.shape
+        S_txt = enc.shape[1]
+        txt_ids = torch.zeros(S_txt, 3, device=enc.device, dtype=torch.bfloat16)
+        den._set_rope(txt_ids, img_ids, S_txt, S_img)
+        t = den._times1000(timestep.reshape(-1).expand(B))
+        g = den._times1000(guidance.reshape(-1).expand(B)) if den.config.guidance_embeds else None
+        _, mod, stemb = den._temb_mod(t, g, pooled.to(torch.bfloat16).contiguous(), want_silu=True)
+        hs = hidden_states.to(torch.bfloat16).contiguous()
+        out = torch.empty((B, n_out_rows, den.config.out_channels), device=enc.device, dtype=torch.bfloat16)
+        nws = int(_lib.lib.b2f_flux_train_workspace_bytes(den._h, B, S_img, S_txt))
+        ws = den._workspace(nws, "train")
+        check(_lib.lib.b2f_flux_train_forward(den._h, ptr(hs), ptr(enc), ptr(mod), mod.stride(0), ptr(out), B, S_img, S_txt,
+                                              n_out_rows, ptr(ws), nws, stream_ptr()), "b2f_flux_train_forward")
+        self._ctx = dict(B=B, S_img=S_img, S_txt=S_txt, n_out=n_out_rows, mod=mod, stemb=stemb, ws=ws, nws=nws, hs=hs, enc=enc)
+        return out
+
+    def backward(self, dpred, accumulate: bool = False):
+        from . import train_ops as T
+        den, c = self.den, self._ctx
+        d_enc = torch.empty_like(c["enc"])
+        dpred = dpred.contiguous()
+
+        def run(first, last):
+            check(_lib.lib.b2f_flux_train_backward(den._h, ptr(dpred), ptr(c["mod"]), c["mod"].stride(0), ptr(c["stemb"]),
+                                                   c["stemb"].stride(0), ptr(d_enc), c["B"], c["S_img"], c["S_txt"],
+                                                   c["n_out"], int(accumulate), ptr(c["ws"]), c["nws"], first, last,
+                                                   stream_ptr()), "b2f_flux_train_backward")
+
+        if self.on_block_done is None:
+            run(0, -1)
+        else:
+            # block by block: each block's gradient bucket is reduced while the next block's backward runs
+            for blk in range(self.n_blocks - 1, -1, -1):
+                run(blk, blk + 1)
+                self.on_block_done(blk)
+        # MLP2: enc_vlm = silu(x W0^T + b0) W2^T + b2
+        if self._mlp2:
+            d_vlm = d_enc[:, :self._L]
+            m = self._mlp2
+            T.linear_wgrad(d_vlm, self._act, out=m["denoise_projector.2.weight"].grad, accumulate=accumulate)
+            self._bias_grad(d_vlm, m["denoise_projector.2.bias"].grad, accumulate)
+            dpre = T.linear_dgrad(d_vlm, self.proj.w2, epilogue=T.EPI_DSILU, aux=self._pre)
+            T.linear_wgrad(dpre, self._x, out=m["denoise_projector.0.weight"].grad, accumulate=accumulate)
+            self._bias_grad(dpre, m["denoise_projector.0.bias"].grad, accumulate)
+            if self.on_block_done is not None:
+                self.on_block_done(self.n_blocks)
+        return d_enc
+
+    @staticmethod
+    def _bias_grad(dy, dst, accumulate):
+        from . import train_ops as T
+        _, col = T.gate_bwd(dy, want_dy=False)                    # [B, D] per-batch column sums
+        _lib.check(_lib.lib.b2f_col_reduce(ptr(col), col.shape[0], col.shape[1], ptr(dst), col.shape[1], 1, int(accumulate),
+                                           stream_ptr()), "b2f_col_reduce")
+
+
+def flow_matching_loss(pred, target, weight=None, grad_scale: float = 1.0):
+    """(loss, dpred): mean(weight * (pred - target)^2) and its gradient (train_denoiser.py:1105-1167)."""
+    from . import train_ops as T
+    return T.mse_loss(pred.contiguous(), target.contiguous(), weight=weight, grad_scale=grad_scale)

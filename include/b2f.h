@@ -389,6 +389,37 @@ int b2f_adamw_step(float* p32, float* m, float* v, const float* g, void* p16, in
 /* bf16 <-> fp32 copies of flat arrays (master-weight initialisation, gradient buckets). */
 int b2f_cast_bf16_f32(const void* src, void* dst, int64_t n, int to_f32, b2f_stream_t stream);
 
+/* Training step of the FLUX object (reference train_denoiser.py:829-1181 with enable_gradient_checkpointing, :484-486).
+ * b2f_flux_bind_grad binds an fp32 gradient buffer (borrowed) to a trainable tensor; a tensor without a bound
+ * gradient is frozen and its weight-gradient GEMM is skipped.  Names (element counts as the weights):
+ *   transformer_blocks.{i}.attn.qkv.{weight,bias}            (to_q, to_k, to_v of the image stream, fused)
+ *   transformer_blocks.{i}.attn.to_out.0.{weight,bias}
+ *   transformer_blocks.{i}.attn.norm_q.weight / norm_k.weight
+ *   transformer_blocks.{i}.norm1.linear.{weight,bias}         ([6d, d]: the block's rows of the fused adaln tensor)
+ *   single_transformer_blocks.{j}.attn.qkv.{weight,bias}     ([3d, d]: rows [0, 3d) of qkv_mlp)
+ *   single_transformer_blocks.{j}.attn.norm_q.weight / norm_k.weight
+ *   single_transformer_blocks.{j}.norm.linear.{weight,bias}   ([3d, d])
+ * — exactly get_trainable_params(only_img_branch=True), train_denoiser.py:71-119.  dptr == NULL unbinds. */
+int b2f_flux_bind_grad(b2f_flux* ctx, const char* key, float* dptr, int64_t numel);
+size_t b2f_flux_train_workspace_bytes(const b2f_flux* ctx, int B, int S_img, int S_txt);
+/* Forward that keeps the input of every block (activation checkpoints) in ws; same arguments and results as
+ * b2f_flux_forward over all blocks. */
+int b2f_flux_train_forward(b2f_flux* ctx, const void* hidden, const void* enc, const void* mod, int64_t mod_ld,
+                           void* out, int B, int S_img, int S_txt, int n_out_rows, void* ws, size_t ws_bytes,
+                           b2f_stream_t stream);
+/* Backward over blocks [first_block, last_block) in reverse order, re-running each block from its checkpoint
+ * (pass (0, -1) for the whole model; partial ranges let the caller overlap a block's gradient reduction with the
+ * next block's backward: the residual-stream gradient persists in ws).  The tail (proj_out, norm_out) runs iff
+ * last_block covers the last block and consumes dout [B, n_out_rows, out_channels] bf16; the head runs iff
+ * first_block == 0 and writes d_enc [B, S_txt, joint_dim] bf16 (gradient of encoder_hidden_states, NULL: skip).
+ * silu_temb: [B, d] bf16 as written by b2f_flux_temb (input of every AdaLN linear).  accumulate != 0 adds to the
+ * bound gradient buffers (gradient accumulation steps) instead of overwriting them. */
+int b2f_flux_train_backward(b2f_flux* ctx, const void* dout, const void* mod, int64_t mod_ld, const void* silu_temb,
+                            int64_t silu_ld, void* d_enc, int B, int S_img, int S_txt, int n_out_rows, int accumulate,
+                            void* ws, size_t ws_bytes, int first_block, int last_block, b2f_stream_t stream);
+/* Test access: copy of the running residual-stream gradient dh[B, S_txt+S_img, d] bf16. */
+int b2f_flux_train_debug_dh(b2f_flux* ctx, void* dst, int B, int S_img, int S_txt, void* ws, b2f_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * FLUX VAE (diffusers AutoencoderKL) as one object.  Replaces `pipe.vae.encode(x)` /
  * `pipe.vae.decode(z)` — reference univa/utils/flux_pipeline.py:609, :1129; train_denoiser.py:887.
