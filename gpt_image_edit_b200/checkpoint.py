@@ -113,18 +113,42 @@ def load_flux_transformer(directory, device="cuda", prefix: str = ""):
     return m
 
 
-def load_univa_checkpoint(model_path, device="cuda"):
-    """-> (UnivaQwen2p5VLForConditionalGeneration, task_head, None) from a Univa checkpoint directory."""
+PROCESSOR_FILES = ("tokenizer.json", "tokenizer_config.json", "vocab.json", "preprocessor_config.json", "processor_config.json")
+
+
+def load_processor(model_path, min_pixels=448 * 448, max_pixels=448 * 448):
+    """`AutoProcessor.from_pretrained(model_path, min_pixels=, max_pixels=)` (reference cli.py:51-55): tokenizer, chat
+    template and Qwen2-VL image processor from the files next to the checkpoint.  Raises when they are missing — without
+    them the instruction text cannot reach the VLM."""
+    root = Path(model_path)
+    if not any((root / f).exists() for f in PROCESSOR_FILES):
+        raise FileNotFoundError(f"{root}: no tokenizer / processor files ({', '.join(PROCESSOR_FILES)}); the chat template and "
+                                "tokenizer of the Univa checkpoint are required (reference cli.py:51-55)")
+    from transformers import AutoProcessor
+
+    return AutoProcessor.from_pretrained(str(root), min_pixels=min_pixels, max_pixels=max_pixels)
+
+
+def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_pixels=448 * 448):
+    """-> (UnivaQwen2p5VLForConditionalGeneration, task_head, processor) from a Univa checkpoint directory
+    (reference cli.py:30-56)."""
     from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig, UnivaQwen2p5VLForConditionalGeneration
     from univa.serve.cli import TaskHead
 
     root = Path(model_path)
+    processor = load_processor(root, min_pixels, max_pixels)
     raw = json.loads((root / "config.json").read_text()) if (root / "config.json").exists() else {}
     cfg = UnivaQwen2p5VLConfig(denoise_tower=raw.get("denoise_tower"), text_config=raw.get("text_config"),
                                vision_config=raw.get("vision_config"))
     model = UnivaQwen2p5VLForConditionalGeneration(cfg, device=device)
     sd = load_state_dict_from_dir(root)
-    model.lvlm.load_state_dict({k: v for k, v in sd.items() if k.startswith(("visual.", "model."))})
+    lvlm_sd = {k: v for k, v in sd.items() if k.startswith(("visual.", "model.", "lm_head."))}
+    if "lm_head.weight" not in lvlm_sd and raw.get("tie_word_embeddings", False) and "model.embed_tokens.weight" in lvlm_sd:
+        lvlm_sd["lm_head.weight"] = lvlm_sd["model.embed_tokens.weight"]
+    res = model.lvlm.load_state_dict(lvlm_sd)
+    missing = list(getattr(res, "missing_keys", []) or [])
+    if missing:      # e.g. lm_head.weight: the text-reply branch would emit argmax = 0 at every step
+        raise KeyError(f"{root}: the checkpoint lacks tensors of the Qwen2.5-VL tower: {missing[:4]}")
     model.denoise_tower.denoiser.load_state_dict({k[len("denoise_tower.denoiser."):]: v for k, v in sd.items()
                                                   if k.startswith("denoise_tower.denoiser.")})
     model.denoise_tower.denoise_projector.load_state_dict({k[len("denoise_tower.denoise_projector."):]: v for k, v in sd.items()
@@ -135,4 +159,4 @@ def load_univa_checkpoint(model_path, device="cuda"):
         t = torch.load(th, map_location="cpu")
         head.w0.copy_(t["0.weight"]); head.b0.copy_(t["0.bias"])
         head.w3[:2].copy_(t["3.weight"]); head.b3[:2].copy_(t["3.bias"])
-    return model, head, None
+    return model, head, processor

@@ -208,7 +208,8 @@ class FluxKontextPipeline:
             noise = torch.randn(shape, generator=generator, device=device, dtype=dtype)
             latents = self._pack_latents(noise, batch_size, num_channels_latents, height, width)
         else:
-            latents = latents.to(device=device, dtype=dtype)
+            # a private copy: the Euler kernel updates the latents in place, the caller's tensor must not change
+            latents = latents.to(device=device, dtype=dtype).clone()
         return latents, image_latents, latent_ids, image_ids
 
     # ------------------------------------------------------------------ sampling (reference :732-1138)
@@ -221,6 +222,7 @@ class FluxKontextPipeline:
                  output_type: str = "pil", return_dict: bool = True, joint_attention_kwargs=None,
                  callback_on_step_end: Optional[Callable] = None, callback_on_step_end_tensor_inputs=("latents",),
                  max_sequence_length: int = 512, max_area: int = 1024 ** 2, _auto_resize: bool = True):
+        self._interrupt = False                    # reference :922 resets the flag at the start of every call
         if prompt is not None and prompt_embeds is not None:
             raise ValueError("Cannot forward both `prompt` and `prompt_embeds`. Please make sure to only forward one of the two.")
         if prompt_embeds is not None and pooled_prompt_embeds is None:

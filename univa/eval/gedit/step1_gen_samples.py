@@ -50,10 +50,19 @@ def run_model_and_return_samples(args: EvalConfig, state: dict, prompt_text: str
     img = np.asarray(Image.open(image1).convert("RGB"))
     gen_h, gen_w = generation_size(img.shape[0], img.shape[1], args.height, args.width)
     dev = state["device"]
-    pix, grid = qwen_pixel_values(resize_u8(img, 448, 448))
-    input_ids = cli.synthetic_chat_tokens(pix.shape[0] // 4).to(dev)       # chat template needs tokenizer files
-    lvlm = state["model"](input_ids, pixel_values=pix.to(dev), attention_mask=torch.ones_like(input_ids),
-                          image_grid_thw=grid, output_type="denoise_embeds")
+    if state.get("processor") is not None:
+        # the reference's prompt path (:119-151): a fixed 448x448 view for the VLM, chat template, system turn dropped
+        content = [{"type": "image", "image": image1, "resized_height": 448, "resized_width": 448}]
+        if prompt_text:
+            content.append({"type": "text", "text": prompt_text})
+        inputs = cli.prepare_inputs(state["processor"], [{"role": "user", "content": content}], dev)
+        lvlm = state["model"](inputs.input_ids, pixel_values=inputs["pixel_values"], attention_mask=inputs.attention_mask,
+                              image_grid_thw=inputs["image_grid_thw"], output_type="denoise_embeds")
+    else:       # --synthetic only: no tokenizer files offline (cli.load_main_model_and_processor raises otherwise)
+        pix, grid = qwen_pixel_values(resize_u8(img, 448, 448))
+        input_ids = cli.synthetic_chat_tokens(pix.shape[0] // 4).to(dev)
+        lvlm = state["model"](input_ids, pixel_values=pix.to(dev), attention_mask=torch.ones_like(input_ids),
+                              image_grid_thw=grid, output_type="denoise_embeds")
     t5, pooled = encode_prompt(state["text_encoders"], state["tokenizers"], prompt_text if args.joint_with_t5 else "", 256, dev, 1)
     embeds = t5 if args.only_use_t5 else (torch.cat([lvlm, t5], dim=1) if args.joint_with_t5 else lvlm)
     return state["pipe"](image=image_to_condition_tensor(img).to(dev), prompt_embeds=embeds, pooled_prompt_embeds=pooled,
@@ -72,10 +81,10 @@ def main(args: EvalConfig):
     args.local_rank, args.world_size = rank, world
     torch.manual_seed(D.rank_seed(args.seed, rank))                           # set_seed(seed, rank, device_specific=True)
     np.random.seed(D.rank_seed(args.seed, rank))
-    model, _, _ = cli.load_main_model_and_processor(args.pretrained_lvlm_name_or_path, device, args.synthetic, args.small)
+    model, _, processor = cli.load_main_model_and_processor(args.pretrained_lvlm_name_or_path, device, args.synthetic, args.small)
     pipe, tokenizers, text_encoders = cli.load_pipe(model.denoise_tower.denoiser, args.pretrained_denoiser_name_or_path, device,
                                                     args.synthetic, args.small)
-    state = dict(model=model, pipe=pipe, tokenizers=tokenizers, text_encoders=text_encoders, device=device)
+    state = dict(model=model, pipe=pipe, tokenizers=tokenizers, text_encoders=text_encoders, device=device, processor=processor)
     os.makedirs(args.output_dir, exist_ok=True)
     todo = D.shard(load_items(args.gedit_prompt_path, args.output_dir), rank, world)     # inference_list[rank::world] (:239)
     done = 0

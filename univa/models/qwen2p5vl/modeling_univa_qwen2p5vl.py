@@ -121,9 +121,13 @@ class UnivaQwen2p5VLForConditionalGeneration(torch.nn.Module):
 
     @contextmanager
     def forward_denoiser_context(self):                          # reference :604-621
-        prev = self.forward_denoiser
+        """Pass-through mode: the model answers as its denoiser (`model.config` becomes the denoiser's config, so a
+        pipeline built with `transformer=model` inside the context reads `.config.in_channels` etc.); yields the model."""
+        prev, prev_cfg = self.forward_denoiser, self.config
         self.forward_denoiser = True
+        self.config = self.denoise_tower.denoiser.config
         try:
-            yield
+            yield self
         finally:
             self.forward_denoiser = prev
+            self.config = prev_cfg

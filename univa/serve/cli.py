@@ -3,11 +3,18 @@ over the libb2f engine: same flags (`--model_path --flux_path --height --width -
 --guidance_scale --no_joint_with_t5 --ocr_enhancer --no_auto_hw`), same turn structure
 (VLM prefill -> task head -> MLP2 -> [T5 ‖ CLIP] -> FluxKontextPipeline -> PNG).
 
+The prompt path is the reference's (cli.py:131-198): a running `conversation` of chat messages and
+`history_image_paths`, `processor.apply_chat_template(..., add_generation_prompt=True)` with the system turn
+dropped, `process_vision_info` (448x448-pixel budget per image, aspect ratio kept), `processor(text=, images=)`;
+the processor (tokenizer + image processor + chat template) is loaded from `--model_path` and its absence is an
+error.  Text replies are decoded with `processor.batch_decode` (cli.py:261-263).
+
 Differences, all forced by this environment and all explicit:
   * `--synthetic` builds every model with seeded random weights at the real architecture sizes (no
-    checkpoints or tokenizer files exist offline); token ids then follow SURVEY.md §8d's canonical
+    checkpoints or tokenizer files exist offline); ONLY then do token ids follow SURVEY.md §8d's canonical
     layout instead of the chat template.  Without `--synthetic` the loaders in
-    gpt_image_edit_b200.checkpoint read the reference's checkpoint directories (safetensors).
+    gpt_image_edit_b200.checkpoint read the reference's checkpoint directories (safetensors) and the
+    processor files next to them.
   * one VLM prefill per turn instead of the reference's two identical ones (cli.py:200 and :211):
     `hidden_states[-1]` of the first equals the pre-MLP2 tensor of the second.
   * with `--synthetic` the T5-XXL / CLIP-L encoders carry seeded random weights and the prompt is
@@ -24,7 +31,8 @@ import numpy as np
 import torch
 
 from gpt_image_edit_b200 import ops
-from gpt_image_edit_b200.image_io import image_to_condition_tensor, qwen_pixel_values, resize_u8
+from gpt_image_edit_b200._lib import B2FError
+from gpt_image_edit_b200.image_io import image_to_condition_tensor, process_vision_info, qwen_pixel_values, resize_u8
 from gpt_image_edit_b200.pipeline import FluxKontextPipeline
 from gpt_image_edit_b200.scheduler import FlowMatchEulerDiscreteScheduler
 from gpt_image_edit_b200.text_encoders import (B200CLIPTextModel, B200T5Encoder, CLIPTextConfig, SyntheticTokenizer,
@@ -34,6 +42,7 @@ from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig
 from univa.utils.anyres_util import dynamic_resize
 
 seed = 42
+generate_image_temp = "./generate_image_{}.png"          # reference cli.py:27
 ASSISTANT_TOKEN_ID = 77091          # reference cli.py:202
 IM_START, IM_END, VISION_START, VISION_END, IMAGE_PAD = 151644, 151645, 151652, 151653, 151655
 
@@ -51,10 +60,12 @@ class TaskHead(torch.nn.Module):
         return ops.linear(ops.linear(x.to(torch.bfloat16), self.w0, self.b0, epilogue=ops.EPI_SILU), self.w3, self.b3)[:, :2]
 
 
-def load_main_model_and_processor(model_path, device, synthetic=False, small=False):
+def load_main_model_and_processor(model_path, device, synthetic=False, small=False, min_pixels=448 * 448,
+                                  max_pixels=448 * 448):
+    """-> (model, task_head, processor)  (reference cli.py:30-56).  processor is None only with --synthetic."""
     if not synthetic:
         from gpt_image_edit_b200.checkpoint import load_univa_checkpoint
-        return load_univa_checkpoint(model_path, device)
+        return load_univa_checkpoint(model_path, device, min_pixels=min_pixels, max_pixels=max_pixels)
     kw = {}
     if small:  # plumbing runs: a few layers at full width
         kw = dict(text_config=dict(num_hidden_layers=2), vision_config=dict(depth=2, fullatt_block_indexes=(1,)),
@@ -108,39 +119,130 @@ def synthetic_chat_tokens(n_image_tokens: int, n_text: int = 24, vocab: int = 15
     return torch.tensor([ids])
 
 
-@torch.no_grad()
-def run_turn(args, model, task_head, pipe, image_u8: np.ndarray | None, text: str, device, tokenizers=None,
-             text_encoders=None):
-    shapes = [(image_u8.shape[1], image_u8.shape[0])] if image_u8 is not None else []
-    new_h, new_w = (args.height, args.width) if args.no_auto_hw or not shapes else \
-        update_size(shapes, "any_11ratio", anchor_pixels=args.height * args.width)
-    pixel_values = grid = None
-    n_img_tok = 0
-    if image_u8 is not None:
-        pixel_values, grid = qwen_pixel_values(resize_u8(image_u8, 448, 448))          # min_pixels = max_pixels = 448^2
-        n_img_tok = pixel_values.shape[0] // 4
-    input_ids = synthetic_chat_tokens(n_img_tok).to(device)
-    hidden = model.prefill_hidden(input_ids, pixel_values=None if pixel_values is None else pixel_values.to(device),
-                                  attention_mask=torch.ones_like(input_ids), image_grid_thw=grid)
-    assistant_vec = hidden[input_ids == ASSISTANT_TOKEN_ID][-1:]
-    task = task_head(assistant_vec)[0].float()
-    if getattr(args, "force_text_reply", False):
-        task = torch.tensor([1.0, 0.0])
-    if not (task[0] < task[1]):
-        # understanding branch (reference cli.py:256-267): greedy KV-cache decode, reply = the newly generated ids
-        generated = model.generate(input_ids=input_ids, pixel_values=None if pixel_values is None else pixel_values.to(device),
-                                   attention_mask=torch.ones_like(input_ids), image_grid_thw=grid,
-                                   max_new_tokens=args.max_new_tokens)
-        return generated[0, input_ids.shape[1]:].tolist()
-    lvlm_embeds = model.denoise_tower.denoise_projector(hidden)                          # MLP2 -> [1, L, 4096]
-    # [T5 ‖ CLIP] on the libb2f encoders; an empty T5 prompt under --no_joint_with_t5 (reference cli.py:221-234)
-    t5_embeds, pooled = encode_prompt(text_encoders, tokenizers, text if not args.no_joint_with_t5 else "", 256, device, 1)
-    prompt_embeds = lvlm_embeds if args.no_joint_with_t5 else torch.cat([lvlm_embeds, t5_embeds], dim=1)
-    cond = None if image_u8 is None else image_to_condition_tensor(image_u8).to(device)
-    return pipe(image=cond, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled, height=new_h, width=new_w,
-                num_inference_steps=args.num_inference_steps, guidance_scale=args.guidance_scale,
-                generator=torch.Generator(device=device).manual_seed(seed),
-                **({"max_area": args.max_area, "_auto_resize": False} if args.max_area else {})).images[0]
+def prepare_inputs(processor, conversation, device):
+    """Chat messages -> model inputs, as the reference does it (cli.py:183-198; gedit/step1_gen_samples.py:136-151):
+    chat template with the generation prompt, the default system turn dropped, images fetched and resized by
+    `process_vision_info`, then the processor call that expands `<|image_pad|>` and builds pixel_values."""
+    chat_text = processor.apply_chat_template(conversation, tokenize=False, add_generation_prompt=True)
+    chat_text = "<|im_end|>\n".join(chat_text.split("<|im_end|>\n")[1:])   # drop system
+    image_inputs, video_inputs = process_vision_info(conversation)
+    inputs = processor(text=[chat_text], images=image_inputs, videos=video_inputs, padding=True, return_tensors="pt")
+    return inputs.to(device)
+
+
+def prepare_condition_images(image_paths, device):
+    """[-1, 1] float32 [N, 3, H, W] of the history images (reference cli.py:99-116)."""
+    from PIL import Image
+
+    if not image_paths:
+        return None
+    imgs = [image_to_condition_tensor(np.asarray(Image.open(p).convert("RGB")))[0] for p in image_paths]
+    return torch.stack(imgs).to(device, dtype=torch.float32)
+
+
+class ChatSession:
+    """State of the reference's REPL (cli.py:131-137): `conversation`, `history_image_paths`, output counter."""
+
+    def __init__(self, args, model, task_head, pipe, processor, tokenizers, text_encoders, device):
+        self.args, self.model, self.task_head, self.pipe, self.processor = args, model, task_head, pipe, processor
+        self.tokenizers, self.text_encoders, self.device = tokenizers, text_encoders, device
+        self.conversation: list = []
+        self.history_image_paths: list = []
+        self.cur_genimg_i = 0
+        if processor is None and not getattr(args, "synthetic", False):
+            raise B2FError("no processor (tokenizer / chat template / image processor files) was found under --model_path; "
+                           "the instruction cannot reach the VLM without it.  Pass --synthetic for the offline plumbing run")
+
+    # ------------------------------------------------------------------ prompt construction (cli.py:151-197)
+    def add_user_turn(self, txt: str, urls: list):
+        """Append the user's message (text, then one image item per url with the 448x448-pixel budget) to the
+        conversation and the urls to the image history; -> (height, width) of the generation."""
+        args = self.args
+        from PIL import Image
+
+        content = []
+        if txt:
+            if getattr(args, "ocr_enhancer", False) and urls:
+                raise B2FError("--ocr_enhancer needs the paddleocr service of the reference (univa/utils/get_ocr.py): out of scope")
+            content.append({"type": "text", "text": txt})
+        new_h, new_w = args.height, args.width
+        if urls:
+            for url in urls:
+                content.append({"type": "image", "image": url, "min_pixels": 448 * 448, "max_pixels": 448 * 448})
+                self.history_image_paths.append(url)
+            # the reference calls update_size whenever the turn has images; its --no_auto_hw flag is parsed but unused
+            shapes = [Image.open(u).size for u in urls[:2]]
+            new_h, new_w = update_size(shapes, "any_11ratio", anchor_pixels=args.height * args.width)
+        self.conversation.append({"role": "user", "content": content})
+        return new_h, new_w
+
+    def model_inputs(self):
+        """(input_ids, attention_mask, pixel_values | None, image_grid_thw | None) for the whole conversation."""
+        dev = self.device
+        if self.processor is not None:
+            inputs = prepare_inputs(self.processor, self.conversation, dev)
+            has_img = "pixel_values" in inputs
+            return (inputs["input_ids"], inputs["attention_mask"], inputs["pixel_values"] if has_img else None,
+                    inputs["image_grid_thw"] if has_img else None)
+        # --synthetic: canonical token layout (SURVEY.md section 8d), one 448x448 view of the latest image
+        from PIL import Image
+
+        pixel_values = grid = None
+        n_img_tok = 0
+        if self.history_image_paths:
+            img = np.asarray(Image.open(self.history_image_paths[-1]).convert("RGB"))
+            pixel_values, grid = qwen_pixel_values(resize_u8(img, 448, 448))
+            pixel_values = pixel_values.to(dev)
+            n_img_tok = pixel_values.shape[0] // 4
+        input_ids = synthetic_chat_tokens(n_img_tok).to(dev)
+        return input_ids, torch.ones_like(input_ids), pixel_values, grid
+
+    # ------------------------------------------------------------------ one turn (cli.py:139-267)
+    @torch.no_grad()
+    def turn(self, txt: str, urls: list, output_path: str | None = None):
+        """-> ("image", path) or ("text", reply)"""
+        args, dev = self.args, self.device
+        new_h, new_w = self.add_user_turn(txt, urls)
+        input_ids, attention_mask, pixel_values, grid = self.model_inputs()
+
+        hidden = self.model.prefill_hidden(input_ids, pixel_values=pixel_values, attention_mask=attention_mask,
+                                           image_grid_thw=grid)
+        assistant_vec = hidden[input_ids == ASSISTANT_TOKEN_ID][-1:]
+        if assistant_vec.shape[0] == 0:
+            raise B2FError(f"token id {ASSISTANT_TOKEN_ID} ('assistant') does not occur in the prompt: the tokenizer under "
+                           "--model_path is not the Qwen2.5-VL tokenizer the task head was trained with")
+        task = self.task_head(assistant_vec)[0].float()
+        if getattr(args, "force_text_reply", False):
+            task = torch.tensor([1.0, 0.0])
+        if not (task[0] < task[1]):
+            # understanding branch (cli.py:256-267): greedy KV-cache decode, reply = the newly generated ids
+            generated = self.model.generate(input_ids=input_ids, pixel_values=pixel_values, attention_mask=attention_mask,
+                                            image_grid_thw=grid, max_new_tokens=args.max_new_tokens)
+            reply = reply_text(generated[0, input_ids.shape[1]:].tolist(), self.processor)
+            self.conversation.append({"role": "assistant", "content": [{"type": "text", "text": reply}]})
+            return "text", reply
+        lvlm_embeds = self.model.denoise_tower.denoise_projector(hidden)                 # MLP2 -> [1, L, 4096]
+        assert lvlm_embeds.shape[0] == 1
+        # [T5 ‖ CLIP] on the libb2f encoders; an empty T5 prompt under --no_joint_with_t5 (cli.py:221-234)
+        t5_embeds, pooled = encode_prompt(self.text_encoders, self.tokenizers, txt if not args.no_joint_with_t5 else "", 256,
+                                          dev, 1)
+        prompt_embeds = lvlm_embeds if args.no_joint_with_t5 else torch.cat([lvlm_embeds, t5_embeds], dim=1)
+        if len(self.history_image_paths) > 1:
+            # the reference stacks every history image into `image=` (cli.py:237) and its prepare_latents then fails on the
+            # batch mismatch (flux_pipeline.py:676-690 keep N latents for batch 1): one context image per session
+            raise B2FError("more than one image in the session history: the reference pipeline accepts a single context image "
+                           "per edit (start a new session to edit a generated image)")
+        cond = prepare_condition_images(self.history_image_paths, dev)
+        image = self.pipe(image=cond, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled, height=new_h, width=new_w,
+                          num_inference_steps=args.num_inference_steps, guidance_scale=args.guidance_scale,
+                          generator=torch.Generator(device=dev).manual_seed(seed),
+                          **({"max_area": args.max_area, "_auto_resize": False} if args.max_area else {})).images[0]
+        img_url = output_path or generate_image_temp.format(self.cur_genimg_i)
+        self.cur_genimg_i += 1
+        image.save(img_url)
+        self.conversation.append({"role": "assistant", "content": [{"type": "image", "image": img_url}]})
+        self.history_image_paths.append(img_url)
+        return "image", img_url
 
 
 def reply_text(token_ids, processor=None):
@@ -154,23 +256,15 @@ def main(args):
     if not torch.cuda.is_available():
         raise SystemExit("univa.serve.cli runs on a B200 through libb2f; there is no CPU path")
     device = torch.device("cuda")
-    model, task_head, _ = load_main_model_and_processor(args.model_path, device, args.synthetic, args.small)
+    model, task_head, processor = load_main_model_and_processor(args.model_path, device, args.synthetic, args.small)
     pipe, tokenizers, text_encoders = load_pipe(model.denoise_tower.denoiser, args.flux_path, device, args.synthetic, args.small)
-    from PIL import Image
+    session = ChatSession(args, model, task_head, pipe, processor, tokenizers, text_encoders, device)
 
-    def load(path):
-        return None if not path else np.asarray(Image.open(path).convert("RGB"))
-
-    if args.prompt is not None or args.image is not None:
-        img = run_turn(args, model, task_head, pipe, load(args.image), args.prompt or "", device, tokenizers, text_encoders)
-        if isinstance(img, list):
-            print(f"Assistant: {reply_text(img)}")
-            return
-        img.save(args.output)
-        print(f"Assistant: generate image at {args.output}")
+    if args.prompt is not None or args.image is not None:       # one non-interactive turn
+        kind, out = session.turn(args.prompt or "", [args.image] if args.image else [], output_path=args.output)
+        print(f"Assistant: generate image at {out}" if kind == "image" else f"Assistant: {out}")
         return
     print("Interactive UniWorld-V1 Chat (Exit if input is empty)")
-    k = 0
     while True:
         txt = input("Text prompt (or press Enter to skip): ").strip()
         img_input = input("Image URLs (comma-separated, or press Enter to skip): ").strip()
@@ -178,16 +272,8 @@ def main(args):
             print("Exit.")
             break
         urls = [u.strip() for u in img_input.split(",") if u.strip()]
-        if len(urls) > 1:
-            print("only one context image per edit is supported (as in the reference pipeline, SURVEY.md §3.1)")
-        out = run_turn(args, model, task_head, pipe, load(urls[0]) if urls else None, txt, device, tokenizers, text_encoders)
-        if isinstance(out, list):
-            print(f"Assistant: {reply_text(out)}\n")
-            continue
-        path = os.path.join(os.getcwd(), f"output_{k}.png")
-        out.save(path)
-        k += 1
-        print(f"Assistant: generate image at {path}\n")
+        kind, out = session.turn(txt, urls)
+        print(f"Assistant: generate image at {out}\n" if kind == "image" else f"Assistant: {out}\n")
 
 
 def build_parser():
