@@ -357,3 +357,183 @@ def flow_matching_loss(pred, target, weight=None, grad_scale: float = 1.0):
     """(loss, dpred): mean(weight * (pred - target)^2) and its gradient (train_denoiser.py:1105-1167)."""
     from . import train_ops as T
     return T.mse_loss(pred.contiguous(), target.contiguous(), weight=weight, grad_scale=grad_scale)
+
+
+# ------------------------------------------------------------------------------------------------ one optimisation step
+def compute_density_for_timestep_sampling(weighting_scheme, batch_size, logit_mean=0.0, logit_std=1.0, mode_scale=1.29,
+                                          generator=None, device="cpu"):
+    """diffusers.training_utils.compute_density_for_timestep_sampling (SD3 paper, section 3.1): u in (0, 1)."""
+    import math
+    if weighting_scheme == "logit_normal":
+        u = torch.normal(mean=logit_mean, std=logit_std, size=(batch_size,), generator=generator, device=device)
+        return torch.sigmoid(u)
+    u = torch.rand(size=(batch_size,), generator=generator, device=device)
+    if weighting_scheme == "mode":
+        u = 1 - u - mode_scale * (torch.cos(math.pi * u / 2) ** 2 - 1 + u)
+    return u
+
+
+def compute_loss_weighting_for_sd3(weighting_scheme, sigmas):
+    """diffusers.training_utils.compute_loss_weighting_for_sd3."""
+    import math
+    if weighting_scheme == "sigma_sqrt":
+        return (sigmas ** -2.0).float()
+    if weighting_scheme == "cosmap":
+        return 2 / (math.pi * (1 - 2 * sigmas + 2 * sigmas ** 2))
+    return torch.ones_like(sigmas)
+
+
+class Stage2Trainer:
+    """`train_denoiser.py`'s loop body (:829-1181) on this engine: VAE-encode target and context, flow-matching noising,
+    Qwen2.5-VL prefill (frozen) -> MLP2 -> FLUX with block checkpoints, loss, backward, ZeRO-2 AdamW step.
+
+    `tc` / `mc` are the reference's TrainingConfig / ModelConfig (univa/training/configuration_denoise.py)."""
+
+    def __init__(self, model, vae, pipe, tc, mc, empty_pooled, group=None, overlap_comm: bool = True):
+        from .scheduler import FlowMatchEulerDiscreteScheduler
+        self.model, self.vae, self.pipe, self.tc, self.mc = model, vae, pipe, tc, mc
+        self.empty_pooled = empty_pooled                      # [1, 768] CLIP pooled embedding of "" (:795-805)
+        den = model.denoise_tower.denoiser
+        if mc.only_tune_mlp2:
+            params = [p for p in trainable_params(model, layers_to_train=[], with_tune_mlp2=True)]
+        else:
+            params = trainable_params(model, layers_to_train=mc.flux_train_layer_idx, only_img_branch=mc.only_tune_image_branch,
+                                      with_tune_mlp2=mc.with_tune_mlp2)
+        if tc.optimizer.lower() != "adamw":
+            raise _lib.B2FError(f"optimizer={tc.optimizer!r}: only AdamW is built (the stage yamls of the reference use adamw)")
+        if tc.gradient_checkpointing:
+            den.enable_gradient_checkpointing()               # always on in this engine: the backward recomputes each block
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        comm = torch.cuda.Stream() if (overlap_comm and world > 1) else None
+        self.opt = ShardedAdamW(params, lr=tc.learning_rate, betas=(tc.adam_beta1, tc.adam_beta2), eps=tc.adam_epsilon,
+                                weight_decay=tc.adam_weight_decay, max_grad_norm=tc.max_grad_norm, group=group, comm_stream=comm)
+        self.params = params
+        self._micro = 0
+        self.graph = FluxTrainGraph(model, params, on_block_done=self._block_done if world > 1 else None)
+        self.sched = FlowMatchEulerDiscreteScheduler()         # noise_scheduler_copy (:437-440)
+        self.global_step = 0
+        self.gen = None
+
+    def _block_done(self, bucket):
+        # reduce a block's gradients as soon as they are complete, but only on the last micro-batch of an accumulation window
+        if (self._micro + 1) % self.tc.gradient_accumulation_steps == 0:
+            self.opt.reduce_bucket(bucket)
+
+    def lr_at(self, step: int) -> float:
+        """diffusers get_scheduler("constant" | "constant_with_warmup" | "linear" | "cosine") (:604-611)."""
+        import math
+        tc = self.tc
+        base, warm, total = tc.learning_rate, tc.lr_warmup_steps, max(tc.max_train_steps or 1, 1)
+        name = tc.lr_scheduler
+        if name == "constant":
+            return base
+        w = min(1.0, (step + 1) / warm) if warm > 0 else 1.0
+        if name == "constant_with_warmup" or step < warm:
+            return base * w
+        prog = (step - warm) / max(1, total - warm)
+        if name == "linear":
+            return base * max(0.0, 1.0 - prog)
+        if name == "cosine":
+            return base * max(0.0, 0.5 * (1.0 + math.cos(math.pi * tc.lr_num_cycles * 2.0 * prog)))
+        raise _lib.B2FError(f"lr_scheduler={name!r} is not built")
+
+    @torch.no_grad()
+    def _vae_latents(self, image, generator=None):
+        # :887-898 — latent_dist.sample(), then (z - shift) * scale
+        z = self.vae.encode(image.to(self.vae.dtype)).latent_dist.sample(generator=generator)
+        return (z.float() - self.vae.config.shift_factor) * self.vae.config.scaling_factor
+
+    def sample_sigmas(self, bsz, latent_hw, device):
+        """(sigmas [B], timesteps [B]) as :939-993."""
+        import math
+        tc = self.tc
+        if tc.discrete_timestep:
+            u = compute_density_for_timestep_sampling(tc.weighting_scheme, bsz, tc.logit_mean, tc.logit_std, tc.mode_scale,
+                                                      generator=self.gen, device=device)
+            n = self.sched.config["num_train_timesteps"]
+            idx = (u * n).long().clamp_(max=n - 1)
+            sig = torch.linspace(1.0, 1.0 / n, n, device=device)      # FlowMatchEulerDiscreteScheduler's training table
+            if not self.sched.config.get("use_dynamic_shifting", True):   # FLUX: dynamic shifting, table left unshifted
+                shift = self.sched.config.get("shift", 1.0)
+                sig = shift * sig / (1 + (shift - 1) * sig)
+            sigmas = sig[idx]
+            return sigmas, sigmas * n
+        sigmas = torch.sigmoid(torch.randn((bsz,), device=device, dtype=torch.float32, generator=self.gen))
+        from .pipeline import calculate_shift
+        c = self.sched.config
+        mu = calculate_shift((latent_hw[0] * latent_hw[1]) // 4, c["base_image_seq_len"], c["max_image_seq_len"], c["base_shift"],
+                             c["max_shift"])
+        s = math.exp(mu)
+        sigmas = (sigmas * s) / (1 + (s - 1) * sigmas)
+        return sigmas, sigmas * 1000.0
+
+    def step(self, batch) -> dict:
+        """One micro-batch (and, at the end of an accumulation window, one optimizer step).  batch keys as the reference's
+        dataloader: generated_image [B,3,H,W], ref_pixel_values [B,(n,)3,H,W] | None, input_ids, attention_mask,
+        pixel_values, image_grid_thw, weights [B,1,h,w] | None."""
+        tc, mc = self.tc, self.mc
+        dev = self.model.device
+        pipe = self.pipe
+        gen_img = batch["generated_image"].to(dev)
+        cond = batch.get("ref_pixel_values")
+        if cond is not None:
+            if cond.ndim == 5:
+                cond = cond.view(-1, *cond.shape[2:])
+            cond = cond.to(dev, dtype=torch.float32)
+        model_input = self._vae_latents(gen_img, self.gen)                                   # [B,16,h,w] fp32
+        B, C, h, w = model_input.shape
+        noise = torch.randn(model_input.shape, device=dev, dtype=model_input.dtype, generator=self.gen)
+        sigmas, timesteps = self.sample_sigmas(B, (h, w), dev)
+        s4 = sigmas.view(B, 1, 1, 1)
+        noisy = (1.0 - s4) * model_input + s4 * noise                                       # :995
+        vsf = pipe.vae_scale_factor
+        if cond is not None:
+            latents, image_latents, ids_t, ids_c = pipe.prepare_latents(cond, B, C, h * vsf, w * vsf, torch.bfloat16, dev,
+                                                                        None, noisy)
+            packed_t = pipe._pack_latents(latents, B, C, h, w)
+            packed = torch.cat([packed_t, image_latents], dim=1)
+            img_ids = torch.cat([ids_t, ids_c], dim=0)
+        else:
+            packed = pipe._pack_latents(noisy.to(torch.bfloat16), B, C, h, w)
+            img_ids = pipe._prepare_latent_image_ids(B, h // 2, w // 2, dev, torch.bfloat16)
+        S_tgt = (h // 2) * (w // 2)
+        guidance = torch.full((B,), float(mc.guidance_scale), device=dev)
+        if mc.vlm_residual_image_factor:
+            raise _lib.B2FError("vlm_residual_image_factor > 0 is not built (0.0 in every stage yaml)")
+        with torch.no_grad():
+            hidden = self.model.prefill_hidden(batch["input_ids"].to(dev), pixel_values=None if batch.get("pixel_values") is None
+                                               else batch["pixel_values"].to(dev), attention_mask=batch["attention_mask"].to(dev),
+                                               image_grid_thw=batch.get("image_grid_thw"))
+        prefix = batch.get("t5_prompt_embeds")                                              # None when drop_t5_rate = 1
+        n_out = S_tgt if (mc.joint_ref_feature and cond is not None) or cond is None else packed.shape[1]
+        pred = self.graph.forward(hidden, packed, (timesteps / 1000).to(torch.bfloat16), guidance,
+                                  self.empty_pooled.expand(B, -1), img_ids, n_out, prefix_embeds=prefix)
+        if pred.shape[1] != S_tgt:
+            raise _lib.B2FError("joint_ref_feature=false with a context image compares context tokens with the target "
+                                "(the reference would fail in _unpack_latents); set joint_ref_feature: true")
+        target = pipe._pack_latents(noise - model_input, B, C, h, w).float().contiguous()   # packing is a permutation
+        weighting = sigmas.view(B, 1, 1, 1) if tc.sigmas_as_weight else \
+            compute_loss_weighting_for_sd3(tc.weighting_scheme, sigmas).view(B, 1, 1, 1)
+        wts = None
+        am = batch.get("weights")
+        if tc.mask_weight_type is not None and am is not None:
+            am = am.to(dev).float()
+            if am.shape[-2:] != (h, w):
+                am = torch.nn.functional.interpolate(am, size=(h, w), mode="nearest")
+            weighting = weighting.float() * am
+        if weighting.numel() > 1 and not bool((weighting == 1).all()):
+            wts = pipe._pack_latents(weighting.expand(B, C, h, w).contiguous(), B, C, h, w).float().contiguous()
+        ga = tc.gradient_accumulation_steps
+        loss, dpred = flow_matching_loss(pred, target, weight=wts, grad_scale=1.0 / ga)
+        self.graph.backward(dpred, accumulate=(self._micro % ga) != 0)
+        self._micro += 1
+        out = {"loss": loss, "sigmas": sigmas, "stepped": False}
+        if self._micro % ga == 0:
+            if self.graph.on_block_done is None:
+                self.opt.reduce_all()
+            lr = self.lr_at(self.global_step)
+            out["grad_norm"] = self.opt.step(lr)
+            out["lr"] = lr
+            out["stepped"] = True
+            self.global_step += 1
+        return out

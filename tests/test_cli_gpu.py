@@ -45,6 +45,49 @@ def test_cli_text_reply_branch(tmp_path, capsys):
     assert 1 <= len(toks) <= 6 and all(0 <= int(t) < 152064 for t in toks)
 
 
+def test_cli_turn_through_a_processor_the_instruction_reaches_the_vlm(tmp_path, monkeypatch):
+    """Non-synthetic prompt path on the GPU: chat template + tokenizer + image processor (a toy Qwen2.5-VL processor
+    directory) feed the prefill; two different instructions give different VLM embeddings and the turn writes a PNG."""
+    import sys
+    from pathlib import Path
+    from types import SimpleNamespace
+
+    from PIL import Image
+
+    sys.path.insert(0, str(Path(__file__).parent))
+    from toy_processor import build_toy_processor
+
+    from gpt_image_edit_b200.checkpoint import load_processor
+    from univa.serve import cli
+
+    build_toy_processor(tmp_path / "proc")
+    processor = load_processor(tmp_path / "proc")
+    tid = processor.tokenizer.convert_tokens_to_ids
+    dev = torch.device("cuda")
+    model, head, _ = cli.load_main_model_and_processor("", dev, synthetic=True, small=True, image_token_id=tid("<|image_pad|>"),
+                                                       vision_start_token_id=tid("<|vision_start|>"))
+    pipe, toks, encs = cli.load_pipe(model.denoise_tower.denoiser, "", dev, synthetic=True, small=True)
+    monkeypatch.setattr(cli, "ASSISTANT_TOKEN_ID", tid("<|im_start|>"))   # the toy vocabulary has no 77091
+    rng = np.random.default_rng(3)
+    src = tmp_path / "src.png"
+    Image.fromarray(rng.integers(0, 256, size=(300, 420, 3), dtype=np.uint8)).save(src)
+    args = cli.build_parser().parse_args(["--height", "256", "--width", "256", "--num_inference_steps", "2",
+                                          "--max_area", str(256 * 256)])
+    embeds = []
+    for text in ("make the sky purple", "remove the tree on the left"):
+        sess = cli.ChatSession(args, model, head, pipe, processor, toks, encs, dev)
+        sess.add_user_turn(text, [str(src)])
+        ids, mask, pix, grid = sess.model_inputs()
+        assert grid.tolist() == [[1, 26, 36]] and int((ids == tid("<|image_pad|>")).sum()) == 26 * 36 // 4
+        embeds.append(model(ids, pixel_values=pix, attention_mask=mask, image_grid_thw=grid, output_type="denoise_embeds"))
+    assert embeds[0].shape[1] != embeds[1].shape[1] or not torch.equal(embeds[0], embeds[1])
+    sess = cli.ChatSession(args, model, head, pipe, processor, toks, encs, dev)
+    kind, out = sess.turn("make the sky purple", [str(src)], output_path=str(tmp_path / "out.png"))
+    assert kind == "image" and Image.open(out).size[0] % 16 == 0
+    assert sess.conversation[-1] == {"role": "assistant", "content": [{"type": "image", "image": out}]}
+    assert sess.history_image_paths == [str(src), out]
+
+
 def test_checkpoint_roundtrip_through_safetensors(tmp_path):
     from gpt_image_edit_b200 import checkpoint as ck
     from gpt_image_edit_b200.flux_transformer import B200FluxTransformer2DModel, FluxTransformerConfig

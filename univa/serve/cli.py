@@ -61,7 +61,7 @@ class TaskHead(torch.nn.Module):
 
 
 def load_main_model_and_processor(model_path, device, synthetic=False, small=False, min_pixels=448 * 448,
-                                  max_pixels=448 * 448):
+                                  max_pixels=448 * 448, **config_overrides):
     """-> (model, task_head, processor)  (reference cli.py:30-56).  processor is None only with --synthetic."""
     if not synthetic:
         from gpt_image_edit_b200.checkpoint import load_univa_checkpoint
@@ -70,6 +70,7 @@ def load_main_model_and_processor(model_path, device, synthetic=False, small=Fal
     if small:  # plumbing runs: a few layers at full width
         kw = dict(text_config=dict(num_hidden_layers=2), vision_config=dict(depth=2, fullatt_block_indexes=(1,)),
                   denoise_tower=dict(denoiser_config=dict(num_layers=1, num_single_layers=1)))
+    kw.update(config_overrides)     # e.g. the special-token ids of a non-Qwen tokenizer (tests)
     cfg = UnivaQwen2p5VLConfig(**kw)
     model = UnivaQwen2p5VLForConditionalGeneration(cfg, device=device)
     model.lvlm.randomize_(seed=10)
