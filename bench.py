@@ -43,30 +43,33 @@ def flops_per_forward(S_img: int, S_txt: int, n_double=N_DOUBLE, n_single=N_SING
     return lin + attn + emb + ada
 
 
-def ncu_traffic():
-    """DRAM bytes (read + write) of the dominant-kernel launch captured with `ncu --set full`
-    (profiles/r01_ncu_full_v2_summary.json, produced by scripts/ncu_summary.py); None if absent."""
-    f = ROOT / "profiles" / "r01_ncu_full_v2_summary.json"
-    if not f.exists():
-        return None
-    best = None
-    for rec in json.loads(f.read_text())["launches"]:
-        if "gemm" not in rec.get("kernel", ""):
-            continue
+def ncu_traffic(kernel_class: str):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the dominant kernel class, from the newest
+    committed `ncu --set full` summary under profiles/ that holds a launch of that class (scripts/ncu_summary.py output);
+    None when no capture of that class is committed — the figure is never borrowed from another kernel."""
+    want = "attn" if kernel_class == "attention" else "gemm"
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for f in sorted((ROOT / "profiles").glob("r*_ncu_full*summary.json"), reverse=True):
         try:
-            rd, wr = rec["dram__bytes_read.sum"].split(), rec["dram__bytes_write.sum"].split()
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            tot = float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]]
-            dur = float(rec["gpu__time_duration.sum"].split()[0])
+            launches = json.loads(f.read_text())["launches"]
         except Exception:
             continue
-        if best is None or dur > best[1]:
-            best = (tot, dur, rec.get("kernel", ""), rec.get("what", ""))
-    if best is None:
-        return None
-    return {"dram_bytes_per_launch": best[0], "launch_us_under_ncu": best[1], "kernel": best[2],
-            "note": "longest captured GEMM launch: " + best[3] + " (algorithmic A+W+out = 561 MB; writes still resident in the "
-                    "126 MB L2 at kernel end are not counted by dram__bytes_write)"}
+        best = None
+        for rec in launches:
+            if want not in rec.get("kernel", ""):
+                continue
+            try:
+                rd, wr = rec["dram__bytes_read.sum"].split(), rec["dram__bytes_write.sum"].split()
+                tot = float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]]
+                dur = float(rec["gpu__time_duration.sum"].split()[0])
+            except Exception:
+                continue
+            if best is None or dur > best[1]:
+                best = (tot, dur, rec.get("kernel", ""), rec.get("what", ""))
+        if best is not None:
+            return {"dram_bytes_per_launch": best[0], "launch_us_under_ncu": best[1], "kernel": best[2], "launch": best[3],
+                    "source": f"profiles/{f.name} (longest captured launch of the class)"}
+    return None
 
 
 def peaks():
@@ -164,10 +167,91 @@ def cpu_reference_sample(height: int, width: int, steps_28: int, threads: int | 
         fo.single_block(sd, 0, cfg, h, temb, cos, sin)
         t_s = time.perf_counter() - t0
     sec_per_image = steps_28 * (N_DOUBLE * t_d + N_SINGLE * t_s)
-    return dict(value=1.0 / sec_per_image, unit="images/s", cores=threads, kind="port",
+    return dict(value=1.0 / sec_per_image, unit="images/s", cores=os.cpu_count() or 1, threads=threads, kind="port",
                 sample=f"oracle fp32: 1 double ({t_d:.2f}s) + 1 single ({t_s:.2f}s) block at S={S_TXT + S_img}, d={D_MODEL}; "
                        f"extrapolated x{N_DOUBLE}/x{N_SINGLE} blocks x{steps_28} steps (VAE/conditioning excluded)",
+                excluded=["vae_encode", "vae_decode", "qwen2.5-vl prefill", "mlp2", "t5-xxl", "clip-l"],
                 sec_per_image_extrapolated=sec_per_image)
+
+
+def cpu_vae_seconds(height: int, width: int, threads: int) -> dict:
+    """Oracle FLUX VAE (fp32) encode + decode of one image on host cores, measured once (the CPU
+    figure states what it includes)."""
+    from oracle import vae_oracle as vo
+
+    torch.set_num_threads(threads)
+    cfg = vo.VaeConfig()
+    sd = vo.make_synthetic_state_dict(cfg, seed=1, dtype=torch.float32)
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(1, 3, height, width, generator=g) * 2 - 1
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        z = vo.encode_mode(sd, cfg, img)
+        t_e = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        vo.decode(sd, cfg, z)
+        t_d = time.perf_counter() - t0
+    return {"vae_encode_s": t_e, "vae_decode_s": t_d}
+
+
+def cpu_config1_seconds(threads: int) -> dict:
+    """BASELINE.json configs[0] / BASELINE.md section 4(i): one 256x256 edit, 4 Euler steps, fp32, host cores, through
+    the oracle's pipeline loop with the full 19 + 38 block depth.  To bound host memory the 57 blocks share the weights of
+    one double and one single block (same shapes, same FLOPs: 47.6 GB of distinct fp32 weights would not change the
+    arithmetic cost); VAE encode/decode included, conditioning supplied as embeddings."""
+    from oracle import flux_oracle as fo
+
+    torch.set_num_threads(threads)
+    cfg1 = fo.FluxConfig(num_layers=1, num_single_layers=1)
+    sd = fo.make_synthetic_state_dict(cfg1, seed=0, dtype=torch.float32)
+    S_img = 2 * 16 * 16
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, S_img // 2, 64, generator=g)
+    ctx = torch.randn(1, S_img // 2, 64, generator=g)
+    enc = torch.randn(1, S_TXT, 4096, generator=g)
+    pooled = torch.randn(1, 768, generator=g)
+    ids = torch.zeros(S_TXT + S_img, 3)
+    cos, sin = fo.rope_tables(ids)
+    sig = np.linspace(1.0, 0.0, 5)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(4):
+            hs = torch.cat([lat, ctx], 1)
+            x = fo._lin(sd, "x_embedder", hs)
+            c = fo._lin(sd, "context_embedder", enc)
+            temb = fo.time_text_embed(sd, cfg1, torch.full((1,), float(sig[i]) * 1000), torch.full((1,), 3500.0), pooled)
+            for _ in range(N_DOUBLE):
+                c, x = fo.double_block(sd, 0, cfg1, x, c, temb, cos, sin)
+            h = torch.cat([c, x], 1)
+            for _ in range(N_SINGLE):
+                h = fo.single_block(sd, 0, cfg1, h, temb, cos, sin)
+            x = h[:, S_TXT:]
+            e = fo._lin(sd, "norm_out.linear", torch.nn.functional.silu(temb))
+            sc, sh = torch.chunk(e, 2, dim=1)
+            v = fo._lin(sd, "proj_out", fo.layer_norm(x) * (1 + sc)[:, None] + sh[:, None])[:, :S_img // 2]
+            lat = lat + float(sig[i + 1] - sig[i]) * v
+    t_loop = time.perf_counter() - t0
+    vae = cpu_vae_seconds(256, 256, threads)
+    total = t_loop + vae["vae_encode_s"] + vae["vae_decode_s"]
+    return {"config": "single 256x256 edit, 4 Euler steps, fp32 CPU (BASELINE.json configs[0])", "seconds_per_edit": total,
+            "denoise_loop_s": t_loop, **vae, "threads": threads, "cores": os.cpu_count() or 1,
+            "note": "oracle restatement; 57 blocks at full width sharing one double + one single block's weights (memory bound of "
+                    "the host), S = 544 + 512; Qwen2.5-VL / T5 / CLIP conditioning supplied as embeddings"}
+
+
+def reference_config(args):
+    """`config` of the CPU arm: the same workload as the GPU arm, described for what THIS arm runs."""
+    S_img = 2 * (args.height // 16) * (args.width // 16)
+    return {"workload": f"C{args.height}: FLUX.1-Kontext-dev MMDiT 19+38 blocks d=3072, {args.height}x{args.width}, "
+                        f"{args.num_inference_steps} Euler steps, S_txt={S_TXT}, S_img={S_img}, guidance 3.5",
+            "batch_per_gpu": 1, "global_batch": 1,
+            "parallelism": "host threads of one process (torch intra-op), no GPU",
+            "implementation": "oracle/flux_oracle.py: fp32 PyTorch restatement of the reference's diffusers path (the reference "
+                              "itself cannot be installed offline, DESIGN.md section 3)",
+            "timed": "one double-stream + one single-stream block at the full shapes per step of this arm, extrapolated to 19 / 38 "
+                     "blocks and 28 Euler steps",
+            "conditioning": "EXCLUDED from this arm (Qwen2.5-VL prefill, MLP2, T5-XXL, CLIP-L); the GPU arm includes them",
+            "vae": "EXCLUDED from `value`; measured once, see cpu_baseline.vae (the GPU arm includes encode + decode)"}
 
 
 def run_reference_arm(args):
@@ -186,13 +270,17 @@ def run_reference_arm(args):
             break
     sec = float(np.mean(times)) if times else last["sec_per_image_extrapolated"]
     val = 1.0 / sec
-    cb = {k: last[k] for k in ("unit", "cores", "kind", "sample")}
+    cb = {k: last[k] for k in ("unit", "cores", "threads", "kind", "sample", "excluded")}
     cb["value"] = val
+    if not args.no_cpu_extras:
+        cb["vae"] = cpu_vae_seconds(args.height, args.width, last["threads"])
+        cb["sec_per_image_with_vae"] = sec + cb["vae"]["vae_encode_s"] + cb["vae"]["vae_decode_s"]
+        cb["config1"] = cpu_config1_seconds(last["threads"])
     print(json.dumps({
         "impl": "reference", "metric": "edited images/sec @1024px 28-step", "value": val, "unit": "images/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1), "cpu_baseline": cb,
+        "config": reference_config(args), "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -209,6 +297,130 @@ def workload_config(args, world):
                              "L=288) + MLP2, T5-XXL encoder (256 tokens), CLIP-L text encoder (77 tokens)")}
 
 
+# ---------------------------------------------------------------------------------------------- training arm
+def run_train_arm(args):
+    """BASELINE.json configs[3]: `train_denoiser.py` stage-2 at 512x512, bf16, ZeRO-2 over the ranks, synthetic
+    (src, instr, tgt) triples.  One "step" = one optimizer step (batch_per_gpu samples per rank): VAE-encode target and
+    context, frozen Qwen2.5-VL-7B prefill, MLP2, FLUX forward with block checkpoints, loss, backward with per-block
+    recompute, gradient reduce-scatter, clipping, AdamW, bf16 all-gather — all inside the timed region."""
+    import torch.distributed as dist
+
+    import train_denoiser as td
+    from gpt_image_edit_b200 import _lib
+    from gpt_image_edit_b200 import distributed as D
+    from gpt_image_edit_b200.training import Stage2Trainer
+    from univa.training.configuration_denoise import load_config
+    from univa.training.synthetic_data import SyntheticEditDataset, collate
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(os.environ.get("TMPDIR", "/tmp"), "nccl_debug.%h.%p.log"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    D.init_from_env("nccl", dev)
+    conf = load_config(ROOT / "scripts" / "denoiser" / "flux_qwen2p5vl_7b_vlm_stage2_512_synthetic.yaml")
+    conf.dataset_config.batch_size = args.batch_per_gpu
+    if args.layers:      # debug only
+        conf.model_config.small = True
+    H = W = 512
+    model, vae, pipe, empty = td.build_models(conf, dev)
+    D.broadcast_weights(list(model.denoise_tower.denoiser._store.values()) +
+                        list(model.denoise_tower.denoise_projector.state_dict().values()))
+    trainer = Stage2Trainer(model, vae, pipe, conf.training_config, conf.model_config, empty)
+    trainer.gen = torch.Generator(device=dev).manual_seed(conf.training_config.seed + rank)
+    data = SyntheticEditDataset(H, W, seed=conf.training_config.seed + rank)
+    B = args.batch_per_gpu
+    n_distinct = 4
+    host = []
+    for i in range(n_distinct):
+        b = collate([data[i * B + j] for j in range(B)])
+        host.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()})
+    on_dev = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values() if torch.is_tensor(v))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, from_host):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s.record()
+        loss = None
+        for i in range(n):
+            b = host[i % n_distinct] if from_host else on_dev[i % n_distinct]
+            if from_host:
+                b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()}
+            out = trainer.step(b)
+            if from_host:
+                loss = out["loss"].item()            # the step's result read back to the host
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e)
+        if from_host:
+            ms = max(ms, (time.perf_counter() - t0) * 1e3)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), loss
+
+    for i in range(args.warmup):
+        trainer.step(on_dev[i % n_distinct])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.prof_enable(True)
+    n0 = _lib.launch_count()
+    ms_total, _ = timed(args.steps, False)
+    launches = _lib.launch_count() - n0
+    prof = _lib.prof_collect()
+    _lib.prof_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, last_loss = timed(args.steps, True)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+    dom = max(("gemm", "attention"), key=lambda k: prof[k]["ms"])
+    pd = prof[dom]
+    achieved = pd["flops"] / (pd["ms"] / 1e3) / 1e12 if pd["ms"] > 0 else 0.0
+    total_flops = sum(v["flops"] for v in prof.values()) / args.steps
+    n_train = sum(p.storage.numel() for p in trainer.params)
+    line = {
+        "metric": "stage-2 training samples/sec @512px (train_denoiser.py, ZeRO-2)", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "train512: train_denoiser.py stage-2, 512x512 target + 512x512 context, S = 288 + 1024 + 1024, "
+                               "Qwen2.5-VL-7B (frozen) + MLP2 + FLUX.1-Kontext-dev 19+38 blocks, recompute per block",
+                   "batch_per_gpu": B, "global_batch": B * world, "trainable_parameters": n_train,
+                   "parallelism": f"ZeRO-2 x{world}: fp32 gradient reduce-scatter per block overlapped with the backward, "
+                                  "fp32 master weights + Adam moments partitioned, bf16 all-gather",
+                   "l2": "inputs larger than L2 (weights stream every forward and backward)",
+                   "optimizer": "AdamW, clip 1.0, lr 1e-6 (scripts/denoiser/flux_qwen2p5vl_7b_vlm_stage2_512_synthetic.yaml)"},
+        "model_tflops_per_gpu": total_flops / (ms_step / 1e3) / 1e12,
+        "model_frac_of_sustained_peak": total_flops / (ms_step / 1e3) / 1e12 / pk["tensor_sustained"],
+        "e2e": {"value": world * B / (ms_e2e / args.steps / 1e3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 4, "last_loss": last_loss},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tensor_sustained"], "peak_source": pk["source"] + ", sustained figure",
+                     "launches": pd["launches"], "share_of_step": pd["ms"] / ms_total, "traffic": None,
+                     "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                     "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
+                                     "gbps": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["flops"] == 0 else None}
+                                 for k, v in prof.items() if v["launches"]}},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -222,12 +434,18 @@ def main():
     ap.add_argument("--num-inference-steps", type=int, default=28)
     ap.add_argument("--layers", type=str, default=None, help="debug: 'D,S' block counts (invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-extras", action="store_true", help="reference arm: skip the one-off VAE and 256x256/4-step "
+                    "(BASELINE.json configs[0]) CPU timings")
+    ap.add_argument("--workload", default="edit", choices=["edit", "train512"], help="edit: the headline metric; train512: "
+                    "BASELINE.json configs[3], stage-2 training samples/s at 512x512 (ZeRO-2 over the ranks)")
     ap.add_argument("--no-conditioning", action="store_true", help="feed synthetic prompt_embeds instead of running the "
                     "Qwen2.5-VL prefill + MLP2 inside the timed region")
     args = ap.parse_args()
 
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "train512":
+        return run_train_arm(args)
 
     import torch.distributed as dist
 
@@ -399,7 +617,7 @@ def main():
             "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_sustained"],
             "frac_of_burst_peak": achieved / pk["tensor_burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
             "avg_launch_ms": pd["ms"] / max(pd["launches"], 1), "launches": pd["launches"],
-            "algorithmic_tflop_per_launch": pd["flops"] / max(pd["launches"], 1) / 1e12, "traffic": ncu_traffic(),
+            "algorithmic_tflop_per_launch": pd["flops"] / max(pd["launches"], 1) / 1e12, "traffic": ncu_traffic(dom),
             "share_of_step": pd["ms"] / ms_total,
             "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                             "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,

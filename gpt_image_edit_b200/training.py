@@ -525,6 +525,11 @@ class Stage2Trainer:
             wts = pipe._pack_latents(weighting.expand(B, C, h, w).contiguous(), B, C, h, w).float().contiguous()
         ga = tc.gradient_accumulation_steps
         loss, dpred = flow_matching_loss(pred, target, weight=wts, grad_scale=1.0 / ga)
+        if getattr(self, "trace", None) is not None:          # test / debug hook: checksums of the step's intermediates
+            cs = lambda t: float(t.double().sum())
+            self.trace.append(dict(sigmas=sigmas.tolist(), model_input=cs(model_input), noise=cs(noise), packed=cs(packed),
+                                   hidden=cs(hidden), pred=cs(pred), target=cs(target), loss=float(loss),
+                                   wts=None if wts is None else cs(wts)))
         self.graph.backward(dpred, accumulate=(self._micro % ga) != 0)
         self._micro += 1
         out = {"loss": loss, "sigmas": sigmas, "stepped": False}

@@ -101,6 +101,49 @@ def titan_from_diffusers(cfg: fo.FluxConfig, sd: dict):
     return m.eval()
 
 
+def titan_forward_with_guidance(m, cfg: fo.FluxConfig, sd: dict, inp: dict):
+    """torchtitan's FluxModel has no guidance embedder (it implements FLUX.1-schnell's graph); FLUX.1-dev / Kontext add
+    `vec += guidance_in(timestep_embedding(guidance, 256))` with `guidance_in` an MLPEmbedder like `time_in` (BFL
+    model.py).  This bolts that term onto torchtitan's own modules — its MLPEmbedder class and its
+    timestep_embedding — and otherwise replays FluxModel.forward verbatim, so the oracle's guidance MLP and the place it
+    enters the graph are checked by an implementation this repo did not write."""
+    from torchtitan.experiments.flux.model.layers import MLPEmbedder, timestep_embedding
+
+    g_in = MLPEmbedder(in_dim=256, hidden_dim=cfg.inner_dim).double()
+    g_in.load_state_dict({"in_layer.weight": sd["time_text_embed.guidance_embedder.linear_1.weight"].double(),
+                          "in_layer.bias": sd["time_text_embed.guidance_embedder.linear_1.bias"].double(),
+                          "out_layer.weight": sd["time_text_embed.guidance_embedder.linear_2.weight"].double(),
+                          "out_layer.bias": sd["time_text_embed.guidance_embedder.linear_2.bias"].double()})
+    img, txt = m.img_in(inp["hidden_states"]), m.txt_in(inp["encoder_hidden_states"])
+    vec = m.time_in(timestep_embedding(inp["timestep"], 256))
+    vec = vec + g_in(timestep_embedding(inp["guidance"], 256))
+    vec = vec + m.vector_in(inp["pooled_projections"])
+    ids = torch.cat((inp["txt_ids"][None].double(), inp["img_ids"][None].double()), dim=1)
+    ids = ids.expand(img.shape[0], -1, -1)
+    pe = m.pe_embedder(ids)
+    for block in m.double_blocks:
+        img, txt = block(img=img, txt=txt, vec=vec, pe=pe)
+    img = torch.cat((txt, img), 1)
+    for block in m.single_blocks:
+        img = block(img, vec=vec, pe=pe)
+    img = img[:, txt.shape[1]:, ...]
+    return m.final_layer(img, vec)
+
+
+def titan_guidance_golden():
+    """flux_toy_titan_guidance.pt: torchtitan + the bolted-on guidance embedder, float64, guidance 3.5 and 1.0."""
+    cfg = fo.FluxConfig(**TOY)                      # guidance_embeds=True
+    sd = fo.make_synthetic_state_dict(cfg, seed=13, dtype=torch.float64)
+    inp = toy_inputs(cfg, B=2, seed=5)
+    inp["guidance"] = torch.tensor([3.5, 1.0], dtype=torch.float64)
+    m = titan_from_diffusers(cfg, {k: v for k, v in sd.items() if "guidance_embedder" not in k})
+    with torch.no_grad():
+        out = titan_forward_with_guidance(m, cfg, sd, inp)
+    torch.save(dict(cfg=TOY, seed=13, inputs={k: v.float() for k, v in inp.items()}, output=out.float()),
+               HERE / "flux_toy_titan_guidance.pt")
+    print("titan+guidance output", out.shape, out.abs().mean().item())
+
+
 VAE_TOY = dict(block_out_channels=(32, 64, 128, 128))
 
 
@@ -178,6 +221,7 @@ def vae_golden():
 def main():
     vae_golden()
     rope_index_golden()
+    titan_guidance_golden()
     cfg = fo.FluxConfig(**TOY, guidance_embeds=False)
     sd = fo.make_synthetic_state_dict(cfg, seed=11, dtype=torch.float64)
     inp = toy_inputs(cfg)

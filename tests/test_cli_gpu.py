@@ -68,6 +68,7 @@ def test_cli_turn_through_a_processor_the_instruction_reaches_the_vlm(tmp_path, 
                                                        vision_start_token_id=tid("<|vision_start|>"))
     pipe, toks, encs = cli.load_pipe(model.denoise_tower.denoiser, "", dev, synthetic=True, small=True)
     monkeypatch.setattr(cli, "ASSISTANT_TOKEN_ID", tid("<|im_start|>"))   # the toy vocabulary has no 77091
+    head.w3.zero_()                                                       # logits = bias = (0, 1): the turn generates
     rng = np.random.default_rng(3)
     src = tmp_path / "src.png"
     Image.fromarray(rng.integers(0, 256, size=(300, 420, 3), dtype=np.uint8)).save(src)

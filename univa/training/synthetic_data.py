@@ -28,21 +28,25 @@ class SyntheticEditDataset(torch.utils.data.Dataset):
     def __getitem__(self, i: int) -> dict:
         from univa.serve.cli import synthetic_chat_tokens
         g = torch.Generator().manual_seed(self.seed * 1_000_003 + i)
-        src = torch.rand(3, self.h, self.w, generator=g) * 2 - 1
+        # everything is derived from uint8 pixels with integer arithmetic, so a sample is bit-identical whatever the
+        # host's thread count (a float resize rounds differently under OMP_NUM_THREADS=1, which torchrun sets)
+        src_u8 = torch.randint(0, 256, (3, self.h, self.w), generator=g, dtype=torch.uint8)
+        src = src_u8.float() / 127.5 - 1.0
         # the target is the source with a rectangular region re-drawn: a real edit changes part of the picture
         tgt = src.clone()
         bh, bw = max(16, self.h // 4), max(16, self.w // 4)
         y0 = int(torch.randint(0, self.h - bh + 1, (1,), generator=g))
         x0 = int(torch.randint(0, self.w - bw + 1, (1,), generator=g))
-        tgt[:, y0:y0 + bh, x0:x0 + bw] = torch.rand(3, bh, bw, generator=g) * 2 - 1
+        tgt[:, y0:y0 + bh, x0:x0 + bw] = torch.randint(0, 256, (3, bh, bw), generator=g, dtype=torch.uint8).float() / 127.5 - 1.0
         lh, lw = self.h // 8, self.w // 8
         weights = torch.ones(1, lh, lw)
         ratio = (self.h * self.w) / (bh * bw)
         weights[:, y0 // 8:(y0 + bh) // 8, x0 // 8:(x0 + bw) // 8] = math.log2(ratio) + 1.0
-        # 448x448 view of the source for the VLM: 32x32 patches of 14 -> 1024 rows of 1176, 256 image tokens
-        view = torch.nn.functional.interpolate(src[None], size=(448, 448), mode="bilinear", align_corners=False)[0]
+        # 448x448 nearest-neighbour view of the source for the VLM: 32x32 patches of 14 -> 1024 rows of 1176, 256 image tokens
+        iy = (torch.arange(448) * self.h) // 448
+        ix = (torch.arange(448) * self.w) // 448
+        u8 = src_u8[:, iy][:, :, ix].permute(1, 2, 0).contiguous().numpy()
         from gpt_image_edit_b200.image_io import qwen_pixel_values
-        u8 = ((view.permute(1, 2, 0) + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).numpy()
         pix, grid = qwen_pixel_values(u8)
         ids = synthetic_chat_tokens(pix.shape[0] // 4, n_text=self.n_text, vocab=self.vocab, seed_=self.seed * 7919 + i)[0]
         return dict(generated_image=tgt, ref_pixel_values=src, input_ids=ids, attention_mask=torch.ones_like(ids),
