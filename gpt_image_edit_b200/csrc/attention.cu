@@ -458,6 +458,7 @@ attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tmem_relinquish_2cta();
   }
   tc_fence_before();
+  __syncthreads();      // CTA-scope barrier for the smem word tcgen05.alloc wrote (racecheck does not model barrier.cluster)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;

@@ -88,7 +88,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(x_full, 1);
     for (int i = 0; i < BWD_STAGES; ++i) {
       mbar_init(&y_full[i], 1);
-      mbar_init(&y_empty[i], 1);
+      // a stage is free when its MMAs have completed (one tcgen05.commit) AND the four row warps have finished reading
+      // the lse2 / delta vectors staged with it (MODE 0; they arrive in MODE 1 as well to keep one protocol)
+      mbar_init(&y_empty[i], 5);
     }
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
@@ -250,7 +252,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) {
+        mbar_arrive(&y_empty[stage]);     // this warp's generic-proxy reads of the stage's smem are done
+        mbar_arrive(p_ready);
+      }
       if (++stage == BWD_STAGES) {
         stage = 0;
         phase ^= 1;

@@ -527,15 +527,18 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cu
 //   Barriers: TMA bytes of both CTAs are counted on CTA 0's `full` barrier; tcgen05.commit
 //   multicasts "stage free" / "accumulator ready" to both CTAs; both CTAs' epilogue warps arrive on
 //   CTA 0's `tmem_empty`.
-struct Gemm2Cfg {
-  static constexpr int BN = 256;
+template <int BN_>
+struct Gemm2CfgT {
+  static constexpr int BN = BN_;       // 256, or 192: the narrower tile exists for shapes whose 256-wide tiling leaves the last
+                                       // wave mostly empty (M = 8192, N = 3072: 384 tiles = 5.19 waves of 74 pairs -> 6.92 at 192)
   static constexpr int STAGES = 6;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;       // 128 rows of A per CTA
   static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;      // 128 rows of W per CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 32 KB
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 512;   // two accumulator stages of BN fp32 columns (power-of-two allocation)
 };
+using Gemm2Cfg = Gemm2CfgT<256>;
 
 // CL = CTAs per cluster: 2 = one CTA pair; 4 = two CTA pairs side by side in N (a 256 x 512 super tile) that
 // SHARE their A rows: each CTA fetches a 64-row slice of its 128 A rows and TMA-multicasts it to the CTA of the
@@ -543,10 +546,11 @@ struct Gemm2Cfg {
 // kernel runs at the L2->SM bandwidth cap: ncu shows ~11.6 TB/s of xbar2l1tex reads at 75 % tensor activity).
 // A stage may be overwritten only when BOTH pairs have consumed it, so every CTA's `empty` barrier takes one
 // multicast commit from each pair leader.
-template <int CL, int MODE = 0>
+template <int CL, int MODE = 0, int BNP = 256>
 __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p) {
   static_assert(CL == 2 || MODE == 0, "the 4-CTA cluster variant exists for the forward layout only");
-  using Cfg = Gemm2Cfg;
+  static_assert(BNP == 256 || (CL == 2 && MODE == 0), "the 192-wide tile exists for the plain forward pair kernel only");
+  using Cfg = Gemm2CfgT<BNP>;
   constexpr int PAIRS = CL / 2;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -727,6 +731,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   gemm_pair_body<2>(&tmA, &tmB, p);
 }
 
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_2cta_n192_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const GemmParams p) {
+  gemm_pair_body<2, 0, 192>(&tmA, &tmB, p);
+}
+
 // dgrad / wgrad operand layouts of the CTA-pair kernel (MODE 1 / 2, see GemmParams)
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -749,6 +759,8 @@ static int pair_kernel_attrs_once() {
   if (e != cudaSuccess) return cuda_err(e, "gemm 2cta smem attribute");
   e = cudaFuncSetAttribute(gemm_bf16_4cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_err(e, "gemm 4cta smem attribute");
+  e = cudaFuncSetAttribute(gemm_bf16_2cta_n192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2CfgT<192>::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_err(e, "gemm 2cta n192 smem attribute");
   e = cudaFuncSetAttribute(gemm_grad_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_err(e, "gemm dgrad 2cta smem attribute");
   e = cudaFuncSetAttribute(gemm_grad_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
@@ -778,6 +790,25 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams 
            2.0 * ((double)p.batch * p.M * kk + (double)p.N * kk + (double)p.batch * p.M * p.N));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("gemm_bf16_2cta_kernel");
+  return B2F_OK;
+}
+
+int launch_gemm_2cta_n192(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t stream) {
+  using Cfg = Gemm2CfgT<192>;
+  if (int rc = pair_kernel_attrs_once()) return rc;
+  p.m_blocks_per_batch = (p.M + 255) / 256;
+  p.num_m_blocks = p.batch * p.m_blocks_per_batch;
+  p.num_n_blocks = (p.N + Cfg::BN - 1) / Cfg::BN;
+  p.panel_n = 16;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int max_pairs = device_info().num_sms / 2;
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  prof_begin(KC_GEMM, stream);
+  gemm_bf16_2cta_n192_kernel<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * p.K,
+           2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  B2F_CHECK_LAUNCH("gemm_bf16_2cta_n192_kernel");
   return B2F_OK;
 }
 
@@ -910,8 +941,16 @@ static int gemm_bf16_impl(const void* A, int64_t lda, int64_t a_bs, const void* 
     int rc2 = make_tmap_3d_rows(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)lda,
                                 batch > 1 ? (uint64_t)a_bs : (uint64_t)M * lda, quad ? 64 : 128);
     if (rc2 != B2F_OK) return rc2;
-    rc2 = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, 128, BLOCK_K);
+    // tile width: 192 instead of 256 when that packs the waves better (cost ~ waves x tile width); plain epilogues only
+    static const int allow_n192 = [] { const char* v = getenv("B2F_GEMM_N192"); return v ? atoi(v) : 1; }();
+    const long long m_tiles = (long long)batch * ((M + 255) / 256), n_pairs = device_info().num_sms / 2;
+    const long long waves256 = (m_tiles * ((N + 255) / 256) + n_pairs - 1) / n_pairs;
+    const long long waves192 = (m_tiles * ((N + 191) / 192) + n_pairs - 1) / n_pairs;
+    const bool n192 = allow_n192 && !quad && epilogue != B2F_EPI_QKV_NORM_ROPE && (N % 192) == 0 &&
+                      waves192 * 192 * 100 < waves256 * 256 * 95;
+    rc2 = make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, n192 ? 96 : 128, BLOCK_K);
     if (rc2 != B2F_OK) return rc2;
+    if (n192) return launch_gemm_2cta_n192(tmA, tmB, p, stream);
     return quad ? launch_gemm_4cta(tmA, tmB, p, stream) : launch_gemm_2cta<0>(tmA, tmB, p, stream);
   }
   int rc = make_tmap_3d_rows(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)batch, (uint64_t)lda,

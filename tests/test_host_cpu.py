@@ -232,7 +232,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     from pathlib import Path
 
     root = Path(__file__).resolve().parent.parent
-    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0",
+                        "--no-cpu-extras"],    # the one-off VAE / 256px-4-step CPU timings take minutes on a small host
                        capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
@@ -242,6 +243,48 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["config"]["workload"].startswith("C1024") and d["dtype"] == "f32"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "extrapolated" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= cb["threads"] >= 1 and cb["value"] == d["value"] and "extrapolated" in cb["sample"]
+    assert "qwen2.5-vl prefill" in cb["excluded"] and "libb2f" not in json.dumps(d["config"])     # the CPU arm describes itself
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert abs(d["ms_per_step"] - 1000.0 / d["value"]) / d["ms_per_step"] < 1e-6
+
+
+def test_bench_cpu_extras_functions():
+    """the one-off CPU timings of the reference arm (VAE encode + decode of the oracle) run and report seconds."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    v = b.cpu_vae_seconds(64, 64, 2)
+    assert v["vae_encode_s"] > 0 and v["vae_decode_s"] > 0
+
+
+def test_ctypes_signatures_match_the_header():
+    """every function include/b2f.h declares is bound in _lib._SIGNATURES with the same number and kinds of arguments
+    (pointer / int / int64 / float / double / size_t) — a mismatch corrupts the call silently."""
+    import ctypes as C
+    import re
+
+    from gpt_image_edit_b200 import _lib
+
+    text = re.sub(r"/\*.*?\*/", "", _lib.HEADER_PATH.read_text(), flags=re.S)
+    decls = re.findall(r"\b(?:int|void|size_t|int64_t|uint64_t|const char\*)\s+(b2f_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+
+    def kind(a):
+        a = a.strip()
+        if a in ("void", ""):
+            return None
+        if "*" in a or "b2f_stream_t" in a:
+            return "p"
+        for k, v in (("int64_t", "i64"), ("size_t", "sz"), ("float", "f"), ("double", "d"), ("int", "i")):
+            if k in a:
+                return v
+        return "?"
+    m = {C.c_void_p: "p", C.c_int64: "i64", C.c_int: "i", C.c_float: "f", C.c_double: "d", C.c_size_t: "sz", C.c_char_p: "p"}
+    assert len(decls) >= 70
+    for name, args in decls:
+        want = [k for k in (kind(a) for a in args.split(",")) if k]
+        have = [m.get(h, "p") for h in _lib._SIGNATURES[name][1]]
+        assert want == have, (name, want, have)
