@@ -75,6 +75,7 @@ _SIGNATURES = {
     "b2f_vae_workspace_bytes": (C.c_size_t, [_vp, _i32, _i32, _i32]),
     "b2f_vae_encode": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, C.c_size_t, _vp]),
     "b2f_vae_decode": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, C.c_size_t, _vp]),
+    "b2f_vae_decode_u8": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, C.c_size_t, _vp]),
     "b2f_flux_create": (_i32, [C.POINTER(_vp), _vp]),
     "b2f_flux_destroy": (None, [_vp]),
     "b2f_flux_bind_weight": (_i32, [_vp, C.c_char_p, _vp, _i64]),
@@ -118,6 +119,7 @@ _SIGNATURES = {
     "b2f_clip_coef": (_i32, [_vp, C.c_float, C.c_float, _vp, _vp, _vp]),
     "b2f_adamw_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i32, _vp, _vp]),
     "b2f_cast_bf16_f32": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "b2f_blend_bf16": (_i32, [_vp, _vp, C.c_float, C.c_float, _vp, _i64, _vp]),
     "b2f_flux_bind_grad": (_i32, [_vp, C.c_char_p, _vp, _i64]),
     "b2f_flux_train_workspace_bytes": (C.c_size_t, [_vp, _i32, _i32, _i32]),
     "b2f_flux_train_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, C.c_size_t, _vp]),

@@ -104,6 +104,7 @@ int clip_coef(const float* sumsq, float max_norm, float pre_scale, float* coef, 
 int adamw_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1, float beta2,
                float eps, float wd, int step, const float* gscale, cudaStream_t st);
 int cast_bf16_f32(const void* src, void* dst, int64_t n, int to_f32, cudaStream_t st);
+int blend_bf16(const void* a, const void* b, float wa, float wb, void* out, int64_t n, cudaStream_t st);
 }  // namespace b2f
 
 extern "C" {
@@ -362,6 +363,9 @@ int b2f_adamw_step(float* p32, float* m, float* v, const float* g, void* p16, in
 }
 int b2f_cast_bf16_f32(const void* src, void* dst, int64_t n, int to_f32, b2f_stream_t stream) {
   return b2f::cast_bf16_f32(src, dst, n, to_f32, ST);
+}
+int b2f_blend_bf16(const void* a, const void* b, float wa, float wb, void* out, int64_t n, b2f_stream_t stream) {
+  return b2f::blend_bf16(a, b, wa, wb, out, n, ST);
 }
 #undef ST
 

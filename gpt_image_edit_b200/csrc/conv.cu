@@ -37,6 +37,8 @@ struct ConvParams {
   __nv_bfloat16* out;
   const __nv_bfloat16* resid;  // same layout as out (NHWC), may be null
   int out_nchw;                // 1: write out[n, co, y, x] for co < Cout (small Cout heads)
+                               // 2: uint8 NHWC image out[n, y, x, co] = round(clamp(bf16(conv)/2 + 0.5, 0, 1) * 255):
+                               //    VaeImageProcessor.postprocess fused into decoder.conv_out (reference flux_pipeline.py:1130)
   int tiles_y, tiles_x, num_m_blocks, num_n_blocks;
 };
 
@@ -213,6 +215,19 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
               v[2 * j + 1] += b2.y;
             }
           }
+          if (p.out_nchw == 2) {
+            uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out) + (((long long)n_img * p.Ho + y) * p.Wo + x) * p.Cout;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int co = n + j;
+              if (co < p.Cout) {
+                const float img = bf16r(v[j]);                                   // the bf16 image the decoder returns
+                const float u = fminf(fmaxf(img / 2.0f + 0.5f, 0.0f), 1.0f);     // denormalise + clamp in fp32
+                o8[co] = (uint8_t)rintf(u * 255.0f);                             // numpy round (half to even)
+              }
+            }
+            continue;
+          }
           if (p.out_nchw) {
             // small heads (Cout <= 32): planar output, one scalar per (pixel, channel)
 #pragma unroll
@@ -290,10 +305,11 @@ int conv3x3(const void* in, const void* w, const void* bias, void* out, const vo
   if (Cin % 64 || Cout <= 0 || (stride != 1 && stride != 2)) return B2F_ERR_UNSUPPORTED;
   if (!out_nchw && (Cout & 7)) return B2F_ERR_UNSUPPORTED;
   if (out_nchw && resid) return B2F_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w) |
-       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
+  if (out_nchw < 0 || out_nchw > 2) return B2F_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(bias) |
        reinterpret_cast<uintptr_t>(resid)) & 15)
     return B2F_ERR_ALIGN;
+  if (out_nchw != 2 && (reinterpret_cast<uintptr_t>(out) & 15)) return B2F_ERR_ALIGN;
   ConvParams p{};
   p.N = N;
   p.stride = stride;

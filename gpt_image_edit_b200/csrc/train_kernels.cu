@@ -566,6 +566,23 @@ __global__ void __launch_bounds__(256) cast_kernel(const void* src, void* dst, l
   }
 }
 
+// out = bf16( bf16(a * wa) + bf16(b * wb) ): `old * (1 - f) + image_embeds * f` of the reference's
+// vlm_residual_image_factor branch (modeling_univa_qwen2p5vl.py:504-506) with torch's bf16 rounding points
+__global__ void __launch_bounds__(256) blend_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, float wa, float wb,
+                                                    __nv_bfloat16* out, long long n8) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n8) return;
+  float x[8], y[8];
+  unpack8(reinterpret_cast<const uint4*>(a)[i], x);
+  unpack8(reinterpret_cast<const uint4*>(b)[i], y);
+  // a Python scalar multiplying a bf16 CUDA tensor is first cast to the tensor's dtype (same rule the Euler step found for
+  // its 0-dim dt): the weights are rounded to bf16 before the multiply
+  const float wab = bf16r(wa), wbb = bf16r(wb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = bf16r(x[j] * wab) + bf16r(y[j] * wbb);
+  reinterpret_cast<uint4*>(out)[i] = pack8(x);
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -789,6 +806,15 @@ int adamw_step(float* p32, float* m, float* v, const float* g, void* p16, int64_
   adamw_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(a);
   prof_end(KC_OTHER, st, 0, 30.0 * n);
   B2F_TRAIN_LAUNCHED("adamw_kernel");
+}
+
+int blend_bf16(const void* a, const void* b, float wa, float wb, void* out, int64_t n, cudaStream_t st) {
+  if (!a || !b || !out || n <= 0 || (n & 7)) return B2F_ERR_INVALID;
+  if (!al16(a) || !al16(b) || !al16(out)) return B2F_ERR_ALIGN;
+  blend_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a),
+                                                             static_cast<const __nv_bfloat16*>(b), wa, wb,
+                                                             static_cast<__nv_bfloat16*>(out), n / 8);
+  B2F_TRAIN_LAUNCHED("blend_kernel");
 }
 
 int cast_bf16_f32(const void* src, void* dst, int64_t n, int to_f32, cudaStream_t st) {

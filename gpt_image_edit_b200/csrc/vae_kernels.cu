@@ -162,6 +162,25 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const T* in, __nv
   reinterpret_cast<uint4*>(out)[i] = pack8v(f);
 }
 
+// uint8 NHWC [N, H, W, C] image -> NHWC bf16 in [-1, 1], channels zero-padded to Cpad: the reference's host-side
+// `torch.tensor(np.array(img), float32) / 255.0`, `(x - 0.5) / 0.5` and `.to(bf16)` (univa/serve/cli.py:99-116,
+// flux_pipeline.py:674) in the kernel that feeds encoder.conv_in — same fp32 operations, one rounding.
+__global__ void __launch_bounds__(256) u8_nhwc_to_nhwc_pad_kernel(const uint8_t* in, __nv_bfloat16* out, long long npix,
+                                                                  int C, int Cpad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (pixel, octet)
+  const int oc = Cpad >> 3;
+  if (i >= npix * oc) return;
+  const int o = int(i % oc);
+  const long long pix = i / oc;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = o * 8 + j;
+    f[j] = c < C ? ((float)in[pix * C + c] / 255.0f - 0.5f) / 0.5f : 0.f;
+  }
+  reinterpret_cast<uint4*>(out)[i] = pack8v(f);
+}
+
 // ---------------------------------------------------------------- row softmax, in place, bf16
 // p = softmax(scale * s) per row of length L (L % 8 == 0), one block per row, fp32 math.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* s, long long ld, int L, float scale) {
@@ -268,7 +287,10 @@ int nchw_to_nhwc_pad(const void* in, int in_is_f32, void* out, int N, int C, int
   if (!in || !out || N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad < C || (Cpad & 7)) return B2F_ERR_INVALID;
   const long long total = (long long)N * H * W * (Cpad / 8);
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (in_is_f32)
+  if (in_is_f32 == 2)      // uint8 NHWC image
+    u8_nhwc_to_nhwc_pad_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(in), static_cast<__nv_bfloat16*>(out),
+                                                       (long long)N * H * W, C, Cpad);
+  else if (in_is_f32)
     nchw_to_nhwc_pad_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in),
                                                              static_cast<__nv_bfloat16*>(out), N, C, H, W, Cpad);
   else

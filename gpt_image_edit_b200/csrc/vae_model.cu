@@ -224,8 +224,8 @@ int b2f_vae_encode(b2f_vae* h, const void* image_nchw, int image_is_f32, int N, 
   return r.rc;
 }
 
-int b2f_vae_decode(b2f_vae* h, const void* z_nchw, int N, int h_lat, int w_lat, void* image_nchw,
-                   void* ws, size_t ws_bytes, b2f_stream_t stream_) {
+static int vae_decode_impl(b2f_vae* h, const void* z_nchw, int N, int h_lat, int w_lat, void* image_nchw, int out_mode,
+                           void* ws, size_t ws_bytes, b2f_stream_t stream_) {
   VaeCtx* c = reinterpret_cast<VaeCtx*>(h);
   if (!c || !z_nchw || !image_nchw || !ws || N <= 0 || h_lat <= 0 || w_lat <= 0) return B2F_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
@@ -252,8 +252,18 @@ int b2f_vae_decode(b2f_vae* h, const void* z_nchw, int N, int h_lat, int w_lat, 
     }
   }
   r.gn("decoder.conv_norm_out", r.X, r.A, (long long)hh * ww, ch, 1);
-  r.conv("decoder.conv_out", r.A, static_cast<bf16_t*>(image_nchw), nullptr, hh, ww, ch, g.out_channels, 1, 1);
+  r.conv("decoder.conv_out", r.A, static_cast<bf16_t*>(image_nchw), nullptr, hh, ww, ch, g.out_channels, 1, out_mode);
   return r.rc;
+}
+
+int b2f_vae_decode(b2f_vae* h, const void* z_nchw, int N, int h_lat, int w_lat, void* image_nchw,
+                   void* ws, size_t ws_bytes, b2f_stream_t stream_) {
+  return vae_decode_impl(h, z_nchw, N, h_lat, w_lat, image_nchw, 1, ws, ws_bytes, stream_);
+}
+
+int b2f_vae_decode_u8(b2f_vae* h, const void* z_nchw, int N, int h_lat, int w_lat, void* image_u8_nhwc,
+                      void* ws, size_t ws_bytes, b2f_stream_t stream_) {
+  return vae_decode_impl(h, z_nchw, N, h_lat, w_lat, image_u8_nhwc, 2, ws, ws_bytes, stream_);
 }
 
 }  // extern "C"

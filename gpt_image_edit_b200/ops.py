@@ -281,3 +281,15 @@ def linear_qkv_norm_rope(x, weight, bias, wq, wk, cos, sin, *, rope_row0: int = 
                                           0 if e3 is None else e3.stride(1), 0 if e3 is None else e3.stride(0),
                                           epi_extra, stream_ptr()), "b2f_gemm_qkv_norm_rope")
     return out
+
+
+def blend(a, b, wa: float, wb: float, *, out=None) -> torch.Tensor:
+    """out = a * wa + b * wb in torch's bf16 evaluation order (each product and the sum rounded to bf16)."""
+    _req(a, "a")
+    _req(b, "b")
+    if a.shape != b.shape or not a.is_contiguous() or not b.is_contiguous():
+        raise _lib.B2FError("blend: contiguous tensors of equal shape expected")
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.lib.b2f_blend_bf16(ptr(a), ptr(b), float(wa), float(wb), ptr(out), a.numel(), stream_ptr()), "b2f_blend_bf16")
+    return out

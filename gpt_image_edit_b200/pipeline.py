@@ -179,7 +179,7 @@ class FluxKontextPipeline:
         return x.reshape(batch_size, channels // 4, height, width)
 
     def _encode_vae_image(self, image, generator=None):
-        z = self.vae.encode(image.to(self.vae.dtype)).latent_dist.mode()
+        z = self.vae.encode(image if image.dtype == torch.uint8 else image.to(self.vae.dtype)).latent_dist.mode()
         return (z - self.vae.config.shift_factor) * self.vae.config.scaling_factor
 
     def prepare_latents(self, image, batch_size, num_channels_latents, height, width, dtype, device, generator=None,
@@ -192,8 +192,11 @@ class FluxKontextPipeline:
         shape = (batch_size, num_channels_latents, height, width)
         image_latents = image_ids = None
         if image is not None:
-            image = image.to(device=device, dtype=dtype)
-            image_latents = self._encode_vae_image(image, generator) if image.shape[1] != self.latent_channels else image
+            if image.dtype == torch.uint8:
+                image_latents = self._encode_vae_image(image.to(device), generator)
+            else:
+                image = image.to(device=device, dtype=dtype)
+                image_latents = self._encode_vae_image(image, generator) if image.shape[1] != self.latent_channels else image
             n = image_latents.shape[0]
             if batch_size > n and batch_size % n == 0:
                 image_latents = torch.cat([image_latents] * (batch_size // n), dim=0)
@@ -265,7 +268,15 @@ class FluxKontextPipeline:
         text_ids = torch.zeros(prompt_embeds.shape[1], 3, device=device, dtype=dtype)
         negative_text_ids = torch.zeros(negative_prompt_embeds.shape[1], 3, device=device, dtype=dtype) if do_true_cfg else None
 
-        if image is not None and not (isinstance(image, torch.Tensor) and image.size(1) == self.latent_channels):
+        if isinstance(image, torch.Tensor) and image.dtype == torch.uint8:
+            # uint8 pixels [N,H,W,3]: normalised inside the VAE's first kernel; only sizes the pipeline would not
+            # resize can take this path (anything else goes through the float preprocess like the reference)
+            ih, iw = int(image.shape[1]), int(image.shape[2])
+            if _auto_resize or ih % mult or iw % mult:
+                image = ((image.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+        if image is not None and image.dtype == torch.uint8:
+            pass
+        elif image is not None and not (isinstance(image, torch.Tensor) and image.size(1) == self.latent_channels):
             ih, iw = self.image_processor.get_default_height_width(image)
             if _auto_resize:
                 a = iw / ih
@@ -332,8 +343,17 @@ class FluxKontextPipeline:
         else:
             z = self._unpack_latents(latents, height, width, self.vae_scale_factor)
             z = (z / self.vae.config.scaling_factor) + self.vae.config.shift_factor
-            images = self.vae.decode(z.to(self.vae.dtype), return_dict=False)[0]
-            images = self.image_processor.postprocess(images, output_type=output_type)
+            if output_type in ("pil", "u8") and hasattr(self.vae, "decode_u8"):
+                # postprocess fused into the last conv: uint8 [N,H,W,3] straight from the decoder
+                u8 = self.vae.decode_u8(z.to(self.vae.dtype))
+                if output_type == "u8":
+                    images = u8
+                else:
+                    from PIL import Image
+                    images = [Image.fromarray(a) for a in u8.cpu().numpy()]
+            else:
+                images = self.vae.decode(z.to(self.vae.dtype), return_dict=False)[0]
+                images = self.image_processor.postprocess(images, output_type=output_type)
         if not return_dict:
             return (images,)
         return FluxPipelineOutput(images=images)

@@ -239,14 +239,22 @@ class B200AutoencoderKL(torch.nn.Module):
 
     @torch.no_grad()
     def encode(self, x: torch.Tensor, return_dict: bool = True):
-        if not x.is_cuda or x.dim() != 4 or x.dtype not in (torch.bfloat16, torch.float32):
-            raise _lib.B2FError("vae.encode: CUDA [N,3,H,W] bf16/fp32 tensor required")
+        """x: [N,3,H,W] bf16 / fp32 in [-1, 1], or uint8 pixels [N,H,W,3] (PIL / numpy layout): then the reference's
+        `(u/255 - 0.5)/0.5` normalisation (cli.py:99-116) runs inside the kernel that feeds encoder.conv_in."""
+        if not x.is_cuda or x.dim() != 4 or x.dtype not in (torch.bfloat16, torch.float32, torch.uint8):
+            raise _lib.B2FError("vae.encode: CUDA [N,3,H,W] bf16/fp32 tensor or uint8 [N,H,W,3] pixels required")
         x = x.contiguous()
-        N, _, H, W = x.shape
+        if x.dtype == torch.uint8:
+            N, H, W, C = x.shape
+            if C != self.config.in_channels:
+                raise _lib.B2FError(f"vae.encode: uint8 input must be [N,H,W,{self.config.in_channels}], got {tuple(x.shape)}")
+            kind = 2
+        else:
+            N, _, H, W = x.shape
+            kind = int(x.dtype == torch.float32)
         ws, n = self._workspace(N, H, W)
         mom = torch.empty((N, 2 * self.config.latent_channels, H // 8, W // 8), device=self._dev, dtype=torch.bfloat16)
-        check(_lib.lib.b2f_vae_encode(self._h, ptr(x), int(x.dtype == torch.float32), N, H, W, ptr(mom), ptr(ws), n,
-                                      stream_ptr()), "b2f_vae_encode")
+        check(_lib.lib.b2f_vae_encode(self._h, ptr(x), kind, N, H, W, ptr(mom), ptr(ws), n, stream_ptr()), "b2f_vae_encode")
         dist = DiagonalGaussianDistribution(mom)
         return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
 
@@ -260,3 +268,16 @@ class B200AutoencoderKL(torch.nn.Module):
         img = torch.empty((N, self.config.out_channels, 8 * h, 8 * w), device=self._dev, dtype=torch.bfloat16)
         check(_lib.lib.b2f_vae_decode(self._h, ptr(z), N, h, w, ptr(img), ptr(ws), n, stream_ptr()), "b2f_vae_decode")
         return SimpleNamespace(sample=img) if return_dict else (img,)
+
+    @torch.no_grad()
+    def decode_u8(self, z: torch.Tensor) -> torch.Tensor:
+        """z [N,C,h,w] -> uint8 pixels [N,8h,8w,3]: decode with VaeImageProcessor.postprocess (`(x/2+0.5).clamp(0,1)`,
+        `(. * 255).round()`, reference flux_pipeline.py:1130) fused into the epilogue of decoder.conv_out."""
+        if not z.is_cuda or z.dim() != 4:
+            raise _lib.B2FError("vae.decode_u8: CUDA [N,C,h,w] tensor required")
+        z = z.to(torch.bfloat16).contiguous()
+        N, _, h, w = z.shape
+        ws, n = self._workspace(N, 8 * h, 8 * w)
+        img = torch.empty((N, 8 * h, 8 * w, self.config.out_channels), device=self._dev, dtype=torch.uint8)
+        check(_lib.lib.b2f_vae_decode_u8(self._h, ptr(z), N, h, w, ptr(img), ptr(ws), n, stream_ptr()), "b2f_vae_decode_u8")
+        return img

@@ -284,6 +284,7 @@ int b2f_move_rows(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, co
  * NULL, out [N,Ho,Wo,Cout] (NHWC) or, with out_nchw, [N,Cout,Ho,Wo].  stride 1: padding 1.
  * stride 2: diffusers Downsample2D (pad right/bottom by one, no other padding), Ho = Hin/2.
  * resid (NHWC, same shape as out, may alias out): out = bf16(resid + bf16(conv + bias)).
+ * out_nchw: 0 NHWC bf16, 1 planar [N,Cout,Ho,Wo] bf16, 2 uint8 pixels [N,Ho,Wo,Cout] = round(clamp(x/2 + 0.5, 0, 1) * 255).
  */
 int b2f_conv3x3(const void* in, const void* w, const void* bias, void* out, const void* resid, int N,
                 int Hin, int Win, int Cin, int Cout, int stride, int out_nchw, b2f_stream_t stream);
@@ -386,6 +387,9 @@ int b2f_clip_coef(const float* sumsq, float max_norm, float pre_scale, float* co
  * NULL: 1), bf16 copy of the new weights written to p16 (NULL: none).  step counts from 1. */
 int b2f_adamw_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* gscale, b2f_stream_t stream);
+/* out = bf16(bf16(a * bf16(wa)) + bf16(b * bf16(wb))) over n contiguous bf16 elements (n % 8 == 0): the
+ * `old * (1 - f) + image_embeds * f` blend of vlm_residual_image_factor (modeling_univa_qwen2p5vl.py:504-506). */
+int b2f_blend_bf16(const void* a, const void* b, float wa, float wb, void* out, int64_t n, b2f_stream_t stream);
 /* bf16 <-> fp32 copies of flat arrays (master-weight initialisation, gradient buckets). */
 int b2f_cast_bf16_f32(const void* src, void* dst, int64_t n, int to_f32, b2f_stream_t stream);
 
@@ -442,13 +446,19 @@ int b2f_vae_create(b2f_vae** out, const b2f_vae_cfg* cfg);
 void b2f_vae_destroy(b2f_vae* ctx);
 int b2f_vae_bind_weight(b2f_vae* ctx, const char* key, const void* dptr, int64_t numel);
 size_t b2f_vae_workspace_bytes(const b2f_vae* ctx, int N, int H, int W);
-/* image [N,3,H,W] (bf16, or fp32 when image_is_f32) -> moments [N, 2*latent, H/8, W/8] bf16
- * (mean | logvar, un-clamped; `latent_dist.mode()` is the first half). */
+/* image -> moments [N, 2*latent, H/8, W/8] bf16 (mean | logvar, un-clamped; `latent_dist.mode()` is the first half).
+ * image_is_f32 selects the input format: 0 = bf16 [N,3,H,W], 1 = fp32 [N,3,H,W], 2 = uint8 [N,H,W,3] pixels (PIL / numpy
+ * layout): the reference's host-side normalisation `(u/255 - 0.5)/0.5` and `.to(bf16)` (univa/serve/cli.py:99-116) run inside
+ * the kernel that feeds encoder.conv_in, so a 1024x1024 context image crosses PCIe as 3 MB instead of 12 MB. */
 int b2f_vae_encode(b2f_vae* ctx, const void* image_nchw, int image_is_f32, int N, int H, int W,
                    void* moments_nchw, void* ws, size_t ws_bytes, b2f_stream_t stream);
-/* z [N,latent,h,w] bf16 -> image [N,3,8h,8w] bf16. */
+/* z [N,latent,h,w] bf16 -> image [N,3,8h,8w] bf16; b2f_vae_decode_u8 writes uint8 [N,8h,8w,3] pixels instead:
+ * VaeImageProcessor.postprocess (`(x/2 + 0.5).clamp(0,1)`, `(. * 255).round()`, reference flux_pipeline.py:1130) fused
+ * into the epilogue of decoder.conv_out. */
 int b2f_vae_decode(b2f_vae* ctx, const void* z_nchw, int N, int h_lat, int w_lat, void* image_nchw,
                    void* ws, size_t ws_bytes, b2f_stream_t stream);
+int b2f_vae_decode_u8(b2f_vae* ctx, const void* z_nchw, int N, int h_lat, int w_lat, void* image_u8_nhwc,
+                      void* ws, size_t ws_bytes, b2f_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 """GPU parity of the VAE kernels and of the composed encode/decode against the oracle restatement
 of diffusers AutoencoderKL (oracle/vae_oracle.py, pinned against torchtitan's independent AE)."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -139,3 +140,27 @@ def test_vae_is_bit_reproducible_run_to_run():
     assert torch.equal(z[0], z[1]) and torch.equal(z[0], z[2])
     d = [vae.decode(z[0], return_dict=False)[0] for _ in range(3)]
     assert torch.equal(d[0], d[1]) and torch.equal(d[0], d[2])
+
+
+def test_uint8_pixels_in_and_out_equal_the_host_side_chain():
+    """f3 (image I/O edges): uint8 [N,H,W,3] pixels go straight into encoder.conv_in's feeder kernel and come straight out
+    of decoder.conv_out's epilogue; both must be bit-identical to the reference's host-side chain — `/255`, `(x-0.5)/0.5`,
+    `.to(bf16)` on the way in (cli.py:99-116), `(x/2+0.5).clamp(0,1)`, `(*255).round().astype(uint8)` on the way out
+    (VaeImageProcessor.postprocess, flux_pipeline.py:1130)."""
+    from gpt_image_edit_b200.pipeline import VaeImageProcessor
+    from gpt_image_edit_b200.vae import B200AutoencoderKL, VaeConfig
+
+    vae = B200AutoencoderKL(VaeConfig(block_out_channels=(64, 128, 256, 256))).randomize_(seed=4)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    u8 = torch.randint(0, 256, (2, 96, 128, 3), device="cuda", generator=g, dtype=torch.uint8)
+    ref_in = ((u8.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+    m_u8 = vae.encode(u8).latent_dist.mean
+    m_f32 = vae.encode(ref_in).latent_dist.mean
+    m_bf16 = vae.encode(ref_in.bfloat16()).latent_dist.mean
+    assert torch.equal(m_u8, m_f32) and torch.equal(m_u8, m_bf16)
+    z = torch.randn(2, 16, 12, 16, device="cuda", generator=g).bfloat16()
+    img = vae.decode(z, return_dict=False)[0]
+    want = [np.asarray(p) for p in VaeImageProcessor.postprocess(img, "pil")]
+    got = vae.decode_u8(z)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (2, 96, 128, 3)
+    assert all(np.array_equal(w, g_.cpu().numpy()) for w, g_ in zip(want, got))

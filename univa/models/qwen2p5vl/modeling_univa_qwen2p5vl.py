@@ -99,9 +99,18 @@ class UnivaQwen2p5VLForConditionalGeneration(torch.nn.Module):
             raise ValueError(f"Unknown output_type: {output_type}.")
         outputs = None
         if not only_use_t5:
-            if vlm_residual_image_factor > 0.0:
-                raise B2FError("vlm_residual_image_factor > 0 is not implemented (default 0.0 in the reference)")
-            hidden = self.prefill_hidden(input_ids, pixel_values, attention_mask, image_grid_thw)
+            if vlm_residual_image_factor > 0.0 and pixel_values is not None:
+                # reference :504-506: the decoder's outputs at the image-token positions are blended with the ViT features
+                from gpt_image_edit_b200 import ops
+                hidden, image_embeds = self.lvlm(input_ids, pixel_values=pixel_values, attention_mask=attention_mask,
+                                                 image_grid_thw=image_grid_thw, return_image_embeds=True)
+                flat = hidden.view(-1, hidden.shape[-1])
+                where = (input_ids.to(flat.device).reshape(-1) == self.config.image_token_id).nonzero().squeeze(1).contiguous()
+                old = ops.gather_rows(flat, where)
+                f = float(vlm_residual_image_factor)
+                ops.scatter_rows_(flat, where, ops.blend(old, image_embeds.contiguous(), 1.0 - f, f))
+            else:
+                hidden = self.prefill_hidden(input_ids, pixel_values, attention_mask, image_grid_thw)
             outputs = self.denoise_tower.denoise_projector(hidden)
         if output_type == "denoise_embeds":
             return outputs
