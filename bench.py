@@ -436,6 +436,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cpu-extras", action="store_true", help="reference arm: skip the one-off VAE and 256x256/4-step "
                     "(BASELINE.json configs[0]) CPU timings")
+    ap.add_argument("--sweep", default="", help="comma list of SIZE[xBATCH] configurations measured in one process, e.g. "
+                    "512,768,1024,1024x4 (BASELINE.json configs[2] and [4]); writes gpurun_out/sweep_n{N}.json")
     ap.add_argument("--workload", default="edit", choices=["edit", "train512"], help="edit: the headline metric; train512: "
                     "BASELINE.json configs[3], stage-2 training samples/s at 512x512 (ZeRO-2 over the ranks)")
     ap.add_argument("--no-conditioning", action="store_true", help="feed synthetic prompt_embeds instead of running the "
@@ -510,138 +512,166 @@ def main():
         # L_qwen = 4 + 256 + 1 + 22 + 5 = 288 tokens, + 256 T5 tokens = S_txt 544
         cond = (qwen, mlp2, synthetic_chat_tokens(256, n_text=22), t5, clip, t5_ids, clip_ids)
 
-    B, H, W = args.batch_per_gpu, args.height, args.width
-    S_img = 2 * (H // 16) * (W // 16)
-    g = torch.Generator().manual_seed(1 + rank)
-    src = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()   # uint8 pixels, PIL / numpy layout:
-    # the (u/255 - 0.5)/0.5 normalisation of cli.py:99-116 runs inside the VAE's first kernel
-    g2 = torch.Generator().manual_seed(2 + rank)
-    if cond is not None and cond[2].shape[1] + 256 != S_TXT:
-        raise SystemExit(f"conditioning layout gives S_txt = {cond[2].shape[1] + 256}, expected {S_TXT}")
-    pe_h = torch.randn(B, S_TXT, 4096, generator=g2).bfloat16().pin_memory()   # only used with --no-conditioning
-    t5_ids_h = (cond[5].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
-    clip_ids_h = (cond[6].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
-    pix_h = torch.randn(B * 1024, 1176, generator=g2).bfloat16().pin_memory()      # 448x448 -> 1024 patches per image
-    ids_h = (cond[2].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
-    pp_h = torch.randn(B, 768, generator=g2).bfloat16().pin_memory()
-    noise_h = torch.stack([torch.randn(S_img // 2, 64, generator=torch.Generator().manual_seed(42 + rank * B + i))
-                           for i in range(B)]).bfloat16().pin_memory()
-    ctx_lat_h = torch.randn(B, 16, H // 8, W // 8, generator=g2).bfloat16().pin_memory()  # only used without a VAE
+    def run_config(args):
+        B, H, W = args.batch_per_gpu, args.height, args.width
+        S_img = 2 * (H // 16) * (W // 16)
+        g = torch.Generator().manual_seed(1 + rank)
+        src = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()   # uint8 pixels, PIL / numpy layout:
+        # the (u/255 - 0.5)/0.5 normalisation of cli.py:99-116 runs inside the VAE's first kernel
+        g2 = torch.Generator().manual_seed(2 + rank)
+        if cond is not None and cond[2].shape[1] + 256 != S_TXT:
+            raise SystemExit(f"conditioning layout gives S_txt = {cond[2].shape[1] + 256}, expected {S_TXT}")
+        pe_h = torch.randn(B, S_TXT, 4096, generator=g2).bfloat16().pin_memory()   # only used with --no-conditioning
+        t5_ids_h = (cond[5].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
+        clip_ids_h = (cond[6].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
+        pix_h = torch.randn(B * 1024, 1176, generator=g2).bfloat16().pin_memory()      # 448x448 -> 1024 patches per image
+        ids_h = (cond[2].repeat(B, 1) if cond is not None else torch.zeros(B, 1, dtype=torch.long)).pin_memory()
+        pp_h = torch.randn(B, 768, generator=g2).bfloat16().pin_memory()
+        noise_h = torch.stack([torch.randn(S_img // 2, 64, generator=torch.Generator().manual_seed(42 + rank * B + i))
+                               for i in range(B)]).bfloat16().pin_memory()
+        ctx_lat_h = torch.randn(B, 16, H // 8, W // 8, generator=g2).bfloat16().pin_memory()  # only used without a VAE
 
-    def one_edit(from_host: bool):
-        nb = lambda t: t.to(dev, non_blocking=True)
-        if from_host:
-            noise = nb(noise_h)
-            image = nb(src) if vae is not None else nb(ctx_lat_h)
-            if cond is not None:
-                pix, ids, t5_ids, clip_ids = nb(pix_h), nb(ids_h), nb(t5_ids_h), nb(clip_ids_h)
+        def one_edit(from_host: bool):
+            nb = lambda t: t.to(dev, non_blocking=True)
+            if from_host:
+                noise = nb(noise_h)
+                image = nb(src) if vae is not None else nb(ctx_lat_h)
+                if cond is not None:
+                    pix, ids, t5_ids, clip_ids = nb(pix_h), nb(ids_h), nb(t5_ids_h), nb(clip_ids_h)
+                else:
+                    pe, pp = nb(pe_h), nb(pp_h)
             else:
-                pe, pp = nb(pe_h), nb(pp_h)
-        else:
-            noise = dev_in["noise"].clone()
-            image = dev_in["image"]
-            pe, pp = dev_in["pe"], dev_in["pp"]
-            pix, ids, t5_ids, clip_ids = dev_in["pix"], dev_in["ids"], dev_in["t5_ids"], dev_in["clip_ids"]
-        if cond is not None:
-            # VLM prefill (ViT + 28-layer decoder) -> MLP2 -> [B, L, 4096]; T5-XXL hidden states and the CLIP-L pooled
-            # vector from the libb2f encoders; joined as cli.py:210-234 does
-            hidden = cond[0](ids, pixel_values=pix, image_grid_thw=[(1, 32, 32)] * B)
-            pe = torch.cat([cond[1](hidden), cond[3](t5_ids)[0]], dim=1)
-            pp = cond[4](clip_ids, output_hidden_states=False).pooler_output
-        out = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pp, height=H, width=W,
-                   num_inference_steps=args.num_inference_steps, guidance_scale=3.5, latents=noise,
-                   max_area=H * W, _auto_resize=False, output_type="u8" if vae is not None else "latent").images
-        if from_host:
-            return out.to("cpu", non_blocking=False)      # uint8 [B,H,W,3] pixels (postprocess fused into decoder.conv_out)
-        return out
+                noise = dev_in["noise"].clone()
+                image = dev_in["image"]
+                pe, pp = dev_in["pe"], dev_in["pp"]
+                pix, ids, t5_ids, clip_ids = dev_in["pix"], dev_in["ids"], dev_in["t5_ids"], dev_in["clip_ids"]
+            if cond is not None:
+                # VLM prefill (ViT + 28-layer decoder) -> MLP2 -> [B, L, 4096]; T5-XXL hidden states and the CLIP-L pooled
+                # vector from the libb2f encoders; joined as cli.py:210-234 does
+                hidden = cond[0](ids, pixel_values=pix, image_grid_thw=[(1, 32, 32)] * B)
+                pe = torch.cat([cond[1](hidden), cond[3](t5_ids)[0]], dim=1)
+                pp = cond[4](clip_ids, output_hidden_states=False).pooler_output
+            out = pipe(image=image, prompt_embeds=pe, pooled_prompt_embeds=pp, height=H, width=W,
+                       num_inference_steps=args.num_inference_steps, guidance_scale=3.5, latents=noise,
+                       max_area=H * W, _auto_resize=False, output_type="u8" if vae is not None else "latent").images
+            if from_host:
+                return out.to("cpu", non_blocking=False)      # uint8 [B,H,W,3] pixels (postprocess fused into decoder.conv_out)
+            return out
 
-    dev_in = dict(pe=pe_h.to(dev), pp=pp_h.to(dev), noise=noise_h.to(dev),
-                  image=(src if vae is not None else ctx_lat_h).to(dev), pix=pix_h.to(dev), ids=ids_h.to(dev),
-                  t5_ids=t5_ids_h.to(dev), clip_ids=clip_ids_h.to(dev))
+        dev_in = dict(pe=pe_h.to(dev), pp=pp_h.to(dev), noise=noise_h.to(dev),
+                      image=(src if vae is not None else ctx_lat_h).to(dev), pix=pix_h.to(dev), ids=ids_h.to(dev),
+                      t5_ids=t5_ids_h.to(dev), clip_ids=clip_ids_h.to(dev))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
 
-    def timed(n, from_host):
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        s.record()
-        for _ in range(n):
-            one_edit(from_host)
-        e.record()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        ms = s.elapsed_time(e)
-        if from_host:
-            ms = max(ms, wall * 1e3)  # the D2H read ends on the host
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        def timed(n, from_host):
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            s.record()
+            for _ in range(n):
+                one_edit(from_host)
+            e.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            ms = s.elapsed_time(e)
+            if from_host:
+                ms = max(ms, wall * 1e3)  # the D2H read ends on the host
+            t = torch.tensor([ms], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
 
-    for _ in range(args.warmup):
-        one_edit(False)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    _lib.prof_enable(True)
-    n0 = _lib.launch_count()
-    ms_total = timed(args.steps, False)
-    launches = _lib.launch_count() - n0
-    prof = _lib.prof_collect()
-    _lib.prof_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
-    one_edit(True)
-    ms_e2e = timed(args.steps, True)
+        for _ in range(args.warmup):
+            one_edit(False)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        _lib.prof_enable(True)
+        n0 = _lib.launch_count()
+        ms_total = timed(args.steps, False)
+        launches = _lib.launch_count() - n0
+        shapes = _lib.prof_shapes()
+        prof = _lib.prof_collect()
+        _lib.prof_enable(False)
+        clocks = sampler.stop() if rank == 0 else None
+        one_edit(True)
+        ms_e2e = timed(args.steps, True)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    pk = peaks()
-    ms_per_edit = ms_total / args.steps
-    value = world * B / (ms_per_edit / 1e3)
-    e2e = world * B / (ms_e2e / args.steps / 1e3)
-    f_fwd = flops_per_forward(S_img, S_TXT, nd, ns) * B
-    f_edit = f_fwd * args.num_inference_steps
-    gm = prof["gemm"]
-    dom = max(("gemm", "attention"), key=lambda k: prof[k]["ms"])
-    pd = prof[dom]
-    achieved = pd["flops"] / (pd["ms"] / 1e3) / 1e12 if pd["ms"] > 0 else 0.0
-    roof = {"bound": "tensor", "kernel": {"gemm": "gemm_bf16_kernel (tcgen05)", "attention": "attn_fwd_kernel (tcgen05)"}[dom],
-            "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_sustained"],
-            "frac_of_burst_peak": achieved / pk["tensor_burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
-            "avg_launch_ms": pd["ms"] / max(pd["launches"], 1), "launches": pd["launches"],
-            "algorithmic_tflop_per_launch": pd["flops"] / max(pd["launches"], 1) / 1e12, "traffic": ncu_traffic(dom),
-            "share_of_step": pd["ms"] / ms_total,
-            "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
-                            "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
-                            "gbps": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["flops"] == 0 else None}
-                        for k, v in prof.items() if v["launches"]}}
-    line = {
-        "metric": "edited images/sec @1024px 28-step", "value": value, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_edit, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": dict(workload_config(args, world), vae="hand-written (included)" if vae is not None else
-                       "EXCLUDED (context latents supplied, latent output)"),
-        "ms_per_denoise_step": ms_per_edit / args.num_inference_steps,
-        "model_tflops_per_gpu": f_edit / (ms_per_edit / 1e3) / 1e12,
-        "model_frac_of_sustained_peak": f_edit / (ms_per_edit / 1e3) / 1e12 / pk["tensor_sustained"],
-        "e2e": {"value": e2e, "unit": "images/s",
-                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in
-                                              (noise_h, src if vae is not None else ctx_lat_h) +
-                                              ((pix_h, ids_h, t5_ids_h, clip_ids_h) if cond is not None else (pe_h, pp_h)))),
-                "d2h_bytes_per_step": int(B * 3 * H * W if vae is not None else noise_h.numel() * 2)},
-        "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_sample(H, W, args.num_inference_steps)
-        cb.pop("sec_per_image_extrapolated", None)
-        line["cpu_baseline"] = cb
-    print(json.dumps(line))
+        if rank != 0:
+            return None
+        pk = peaks()
+        ms_per_edit = ms_total / args.steps
+        value = world * B / (ms_per_edit / 1e3)
+        e2e = world * B / (ms_e2e / args.steps / 1e3)
+        f_fwd = flops_per_forward(S_img, S_TXT, nd, ns) * B
+        f_edit = f_fwd * args.num_inference_steps
+        gm = prof["gemm"]
+        dom = max(("gemm", "attention"), key=lambda k: prof[k]["ms"])
+        pd = prof[dom]
+        achieved = pd["flops"] / (pd["ms"] / 1e3) / 1e12 if pd["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": {"gemm": "gemm_bf16_kernel (tcgen05)", "attention": "attn_fwd_kernel (tcgen05)"}[dom],
+                "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tensor_sustained"],
+                "frac_of_burst_peak": achieved / pk["tensor_burst"], "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                "avg_launch_ms": pd["ms"] / max(pd["launches"], 1), "launches": pd["launches"],
+                "algorithmic_tflop_per_launch": pd["flops"] / max(pd["launches"], 1) / 1e12, "traffic": ncu_traffic(dom),
+                "share_of_step": pd["ms"] / ms_total,
+                "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
+                                "gbps": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["flops"] == 0 else None}
+                            for k, v in prof.items() if v["launches"]}}
+        line = {
+            "metric": "edited images/sec @1024px 28-step", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_edit, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": dict(workload_config(args, world), vae="hand-written (included)" if vae is not None else
+                           "EXCLUDED (context latents supplied, latent output)"),
+            "ms_per_denoise_step": ms_per_edit / args.num_inference_steps,
+            "model_tflops_per_gpu": f_edit / (ms_per_edit / 1e3) / 1e12,
+            "model_frac_of_sustained_peak": f_edit / (ms_per_edit / 1e3) / 1e12 / pk["tensor_sustained"],
+            "e2e": {"value": e2e, "unit": "images/s",
+                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in
+                                                  (noise_h, src if vae is not None else ctx_lat_h) +
+                                                  ((pix_h, ids_h, t5_ids_h, clip_ids_h) if cond is not None else (pe_h, pp_h)))),
+                    "d2h_bytes_per_step": int(B * 3 * H * W if vae is not None else noise_h.numel() * 2)},
+            "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
+        }
+        # in-loop GEMM efficiency per shape (the ten largest time sinks)
+        roof["gemm_shapes"] = [{"shape": t, "launches": n, "ms": round(ms, 2), "tflops": round(tf, 1)}
+                               for t, n, ms, tf in sorted(shapes, key=lambda r: -r[2])[:14]]
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_sample(H, W, args.num_inference_steps)
+            cb.pop("sec_per_image_extrapolated", None)
+            line["cpu_baseline"] = cb
+        return line
+
+    if args.sweep:
+        # BASELINE.json configs[2] / [4] in ONE process per N (models built once): the resolution sweep at batch 1 per GPU and
+        # the 1024^2 run at batch 4 per GPU (global batch 32 at N = 8); one JSON object per configuration
+        import copy
+        out = []
+        for spec in args.sweep.split(","):
+            hw, _, b = spec.partition("x")
+            a2 = copy.copy(args)
+            a2.height = a2.width = int(hw)
+            a2.batch_per_gpu = int(b or 1)
+            a2.no_cpu_baseline = True
+            line = run_config(a2)
+            if rank == 0:
+                line["sweep"] = spec
+                out.append(line)
+                print(json.dumps({k: line[k] for k in ("sweep", "value", "ms_per_step", "ms_per_denoise_step", "n_gpus",
+                                                        "model_tflops_per_gpu", "model_frac_of_sustained_peak")}), flush=True)
+        if rank == 0:
+            (ROOT / "gpurun_out").mkdir(exist_ok=True)
+            (ROOT / "gpurun_out" / f"sweep_n{world}.json").write_text(json.dumps(out, indent=1))
+    else:
+        line = run_config(args)
+        if rank == 0:
+            print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

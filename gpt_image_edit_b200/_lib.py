@@ -51,6 +51,7 @@ _SIGNATURES = {
     "b2f_device_info": (_i32, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_size_t)]),
     "b2f_launch_count": (C.c_uint64, []),
     "b2f_prof_enable": (None, [_i32]),
+    "b2f_prof_shapes": (_i32, [C.c_char_p, _i32]),
     "b2f_prof_collect": (_i32, [_i32, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b2f_gemm_bf16": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
     "b2f_gemm_qkv_norm_rope": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, C.c_float, _i32, _vp, _i64, _i64, _i32, _vp]),
@@ -175,6 +176,18 @@ def prof_collect() -> dict:
         ms, n, fl, by = C.c_double(), _i64(), C.c_double(), C.c_double()
         check(lib.b2f_prof_collect(i, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)), "b2f_prof_collect")
         out[name] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+    return out
+
+
+def prof_shapes() -> list:
+    """[(tag, launches, ms, tflops)] per GEMM shape since the last call (call before prof_collect)."""
+    buf = C.create_string_buffer(1 << 20)
+    n = lib.b2f_prof_shapes(buf, len(buf))
+    check(min(n, 0), "b2f_prof_shapes")
+    out = []
+    for line in buf.value.decode().splitlines():
+        tag, cnt, ms, tf = line.split("\t")
+        out.append((tag, int(cnt), float(ms), float(tf)))
     return out
 
 

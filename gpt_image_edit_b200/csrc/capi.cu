@@ -45,6 +45,7 @@ int softmax_rows(void* s, int64_t ld, int rows, int L, float scale, cudaStream_t
 int transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int Cc,
                    cudaStream_t stream);
 int prof_collect(int kc, double* ms, int64_t* launches, double* flops, double* bytes);
+int prof_shapes(char* buf, int cap);
 int rope_tables(const float* ids, int S, const int* axes_dim, double theta, float* cos, float* sin,
                 cudaStream_t stream);
 int attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -145,6 +146,7 @@ int b2f_device_info(int* num_sms, int* cc_major, int* cc_minor, size_t* smem_opt
 uint64_t b2f_launch_count(void) { return b2f::g_launch_count.load(); }
 
 void b2f_prof_enable(int on) { b2f::prof_set(on != 0); }
+int b2f_prof_shapes(char* buf, int cap) { return b2f::prof_shapes(buf, cap); }
 int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* flops, double* bytes) {
   return b2f::prof_collect(kernel_class, ms, launches, flops, bytes);
 }

@@ -29,7 +29,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // TMA producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
 
 struct GemmParams {
   int batch, M, N, K;  // M rows per batch item
@@ -90,12 +91,17 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int t, int& m_b
   n_blk = panel * p.panel_n + (r - m_blk * w);
 }
 
+// gelu_tanh(x) = 0.5 x (1 + tanh(u)) = x * sigmoid(2u), u = k0 (x + k1 x^3): one ex2 and one fast division instead of the
+// branchy tanhf (which made the K = 3072 GEMMs with a GELU epilogue epilogue-bound: 1096 instead of 1257 TFLOP/s in the
+// denoising loop).  Relative error ~1e-6, far below the bf16 rounding of the result.
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  const float u = x * fmaf(x * x, k0 * k1, k0);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -2.8853900817779268f));   // exp(-2u)
+  return __fdividef(x, 1.0f + e);
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float dgelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   const float t = tanhf(k0 * (x + k1 * x * x * x));
@@ -130,7 +136,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
     }
     if (epi == B2F_EPI_GELU_TANH) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_f(bf16r(v[j]));
+      for (int j = 0; j < 8; j += 2) {
+        bf16r2(v[j], v[j + 1]);            // packed rounding (the scalar conversion runs on the slow XU pipe)
+        v[j] = gelu_tanh_f(v[j]);
+        v[j + 1] = gelu_tanh_f(v[j + 1]);
+      }
     } else if (epi == B2F_EPI_GELU_ERF) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -139,7 +149,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
       }
     } else if (epi == B2F_EPI_SILU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = silu_f(bf16r(v[j]));
+      for (int j = 0; j < 8; j += 2) {
+        bf16r2(v[j], v[j + 1]);
+        v[j] = silu_f(v[j]);
+        v[j + 1] = silu_f(v[j + 1]);
+      }
     } else if (epi == B2F_EPI_QUICK_GELU) {
       // transformers QuickGELUActivation in bf16 eager: x * sigmoid(1.702 * x), each op rounded
 #pragma unroll
@@ -157,8 +171,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
       for (int j = 0; j < 4; ++j) {
         const float2 g2 = unpack_bf16x2(gw[j]);
         const float2 r2 = unpack_bf16x2(rw[j]);
-        v[2 * j] = r2.x + bf16r(g2.x * bf16r(v[2 * j]));
-        v[2 * j + 1] = r2.y + bf16r(g2.y * bf16r(v[2 * j + 1]));
+        float y0 = v[2 * j], y1 = v[2 * j + 1];
+        bf16r2(y0, y1);
+        y0 *= g2.x;
+        y1 *= g2.y;
+        bf16r2(y0, y1);
+        v[2 * j] = r2.x + y0;
+        v[2 * j + 1] = r2.y + y1;
       }
     }
     else if (epi == B2F_EPI_DGELU || epi == B2F_EPI_DSILU) {
@@ -192,8 +211,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 r2 = unpack_bf16x2(rw[j]);
-        v[2 * j] = r2.x + bf16r(v[2 * j]);
-        v[2 * j + 1] = r2.y + bf16r(v[2 * j + 1]);
+        float y0 = v[2 * j], y1 = v[2 * j + 1];
+        bf16r2(y0, y1);
+        v[2 * j] = r2.x + y0;
+        v[2 * j + 1] = r2.y + y1;
       }
     }
     uint4 o;
@@ -209,52 +230,77 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const int ep
 // One 128-column head of a fused QKV projection for one token, straight from the accumulators:
 //   x = bf16(acc + bias);  y = bf16(x * rsqrt(mean(x^2) + eps));  z = bf16(y * w);
 //   out = bf16(z * cos + rot(z) * sin)        (diffusers RMSNorm + apply_rotary_emb)
-// — the same rounding chain as rmsnorm_rope_kernel, but without the extra HBM round trip.
-__device__ __forceinline__ void epilogue_head_norm_rope(const GemmParams& p, uint32_t (&a)[128], int n_head0,
-                                                        long long row, __nv_bfloat16* out_row, bool is_k) {
+// — the same rounding chain as rmsnorm_rope_kernel, but without the extra HBM round trip.  The head is pulled from TMEM
+// in four 32-column chunks; x is kept as 64 packed bf16 pairs (not 128 floats) and every rounding is the packed
+// cvt.rn.bf16x2 (the scalar conversion is an XU-pipe instruction: 8 clocks per warp).
+// `release` is called once the last TMEM read of this head has completed.
+template <typename Release>
+__device__ __forceinline__ void epilogue_head_norm_rope(const GemmParams& p, uint32_t taddr, int n_head0, long long row,
+                                                        __nv_bfloat16* out_row, bool is_k, bool active, Release release) {
   const __nv_bfloat16* w = is_k ? p.nw_k : p.nw_q;
+  // pass 1: sum of squares of x = bf16(acc + bias) over the head (nothing kept: the head is re-read from TMEM in pass 2,
+  // which costs less than holding 128 values in registers at 8 epilogue warps per CTA)
   float ss = 0.f;
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t acc[32];
+    B2F_TMEM_LD_X32(taddr + cc * 32, acc);
+    tmem_wait_ld();
 #pragma unroll
-  for (int c = 0; c < 128; c += 8) {
-    const uint4 bq = p.bias ? __ldg(reinterpret_cast<const uint4*>(p.bias + n_head0 + c)) : make_uint4(0, 0, 0, 0);
-    const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+    for (int g = 0; g < 4; ++g) {
+      const int c = cc * 32 + g * 8;
+      const uint4 bq = p.bias ? __ldg(reinterpret_cast<const uint4*>(p.bias + n_head0 + c)) : make_uint4(0, 0, 0, 0);
+      const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 b2 = unpack_bf16x2(bw[j]);
-      const float x0 = bf16r(__uint_as_float(a[c + 2 * j]) + b2.x);
-      const float x1 = bf16r(__uint_as_float(a[c + 2 * j + 1]) + b2.y);
-      ss = fmaf(x0, x0, ss);
-      ss = fmaf(x1, x1, ss);
-      a[c + 2 * j] = __float_as_uint(x0);
-      a[c + 2 * j + 1] = __float_as_uint(x1);
+      for (int jj = 0; jj < 4; ++jj) {
+        const float2 b2 = unpack_bf16x2(bw[jj]);
+        float x0 = __uint_as_float(acc[g * 8 + 2 * jj]) + b2.x, x1 = __uint_as_float(acc[g * 8 + 2 * jj + 1]) + b2.y;
+        bf16r2(x0, x1);
+        ss = fmaf(x0, x0, ss);
+        ss = fmaf(x1, x1, ss);
+      }
     }
   }
   const float r = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
   const float* cs = p.rope_cos + ((long long)p.rope_row0 + row) * 128;
   const float* sn = p.rope_sin + ((long long)p.rope_row0 + row) * 128;
+  // pass 2: normalise, weight, rotate, store
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t acc[32];
+    __syncwarp();
+    B2F_TMEM_LD_X32(taddr + cc * 32, acc);
+    tmem_wait_ld();
+    if (cc == 3) release();
+    if (!active) continue;
 #pragma unroll
-  for (int c = 0; c < 128; c += 8) {
-    const uint4 wq = __ldg(reinterpret_cast<const uint4*>(w + c));
-    const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
-    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cs + c)), c1 = __ldg(reinterpret_cast<const float4*>(cs + c + 4));
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sn + c)), s1 = __ldg(reinterpret_cast<const float4*>(sn + c + 4));
-    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    float o[8];
+    for (int g = 0; g < 4; ++g) {
+      const int c = cc * 32 + g * 8;
+      const uint4 bq = p.bias ? __ldg(reinterpret_cast<const uint4*>(p.bias + n_head0 + c)) : make_uint4(0, 0, 0, 0);
+      const uint4 wq = __ldg(reinterpret_cast<const uint4*>(w + c));
+      const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cs + c)), c1 = __ldg(reinterpret_cast<const float4*>(cs + c + 4));
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(sn + c)), s1 = __ldg(reinterpret_cast<const float4*>(sn + c + 4));
+      const float cc8[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float sc8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 w2 = unpack_bf16x2(ww[j]);
-      const float z0 = bf16r(bf16r(__uint_as_float(a[c + 2 * j]) * r) * w2.x);
-      const float z1 = bf16r(bf16r(__uint_as_float(a[c + 2 * j + 1]) * r) * w2.y);
-      o[2 * j] = z0 * cc[2 * j] - z1 * sc[2 * j];
-      o[2 * j + 1] = z1 * cc[2 * j + 1] + z0 * sc[2 * j + 1];
+      for (int jj = 0; jj < 4; ++jj) {
+        const float2 b2 = unpack_bf16x2(bw[jj]);
+        const float2 w2 = unpack_bf16x2(ww[jj]);
+        float z0 = __uint_as_float(acc[g * 8 + 2 * jj]) + b2.x, z1 = __uint_as_float(acc[g * 8 + 2 * jj + 1]) + b2.y;
+        bf16r2(z0, z1);          // x
+        z0 *= r;
+        z1 *= r;
+        bf16r2(z0, z1);          // y = bf16(x * r)
+        z0 *= w2.x;
+        z1 *= w2.y;
+        bf16r2(z0, z1);          // z = bf16(y * w)
+        o[jj] = pack_bf16x2(z0 * cc8[2 * jj] - z1 * sc8[2 * jj], z1 * cc8[2 * jj + 1] + z0 * sc8[2 * jj + 1]);
+      }
+      *reinterpret_cast<uint4*>(out_row + n_head0 + c) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    uint4 ov;
-    ov.x = pack_bf16x2(o[0], o[1]);
-    ov.y = pack_bf16x2(o[2], o[3]);
-    ov.z = pack_bf16x2(o[4], o[5]);
-    ov.w = pack_bf16x2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(out_row + n_head0 + c) = ov;
   }
 }
 
@@ -265,16 +311,17 @@ __device__ __forceinline__ __nv_bfloat16* out_row_ptr(const GemmParams& p, int b
   return p.out + bidx * p.out_bs + row * p.ldc;
 }
 
-// Epilogue of one output tile for the calling warp's 32 rows: TMEM -> registers -> fused math -> global.
+// Epilogue of one output tile for the calling warp: its 32 rows (TMEM lane quarter q) x its half of the BN columns
+// (`half` = 0 / 1: two warps share a lane quarter).  TMEM -> registers -> fused math -> global.
 // `arrive_cta0`: the CTA-pair kernel hands the accumulator stage back on CTA 0's barrier.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int as, int q, int lane,
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int as, int q, int half, int lane,
                                               int n_blk, bool row_ok, long long row, __nv_bfloat16* out_row,
                                               const __nv_bfloat16* res_row, const __nv_bfloat16* gate_row,
                                               uint64_t* tmem_empty_bar, bool arrive_cta0,
                                               __nv_bfloat16* out_row2 = nullptr) {
   auto release = [&]() {
-    // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+    // all TMEM reads of this warp's part of the accumulator stage are complete: hand it back to the MMA warp
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -284,47 +331,49 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         mbar_arrive(tmem_empty_bar);
     }
   };
+  constexpr int HALF = BN / 2;             // columns per warp: 128 (one head), 96 or 64
+  const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + half * HALF);
   if (p.epi == B2F_EPI_QKV_NORM_ROPE) {
-#pragma unroll 1
-    for (int h0 = 0; h0 < BN; h0 += 128) {
-      uint32_t a[128];
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + h0);
-      __syncwarp();
-      B2F_TMEM_LD_X32(taddr + 0, (a + 0));
-      B2F_TMEM_LD_X32(taddr + 32, (a + 32));
-      B2F_TMEM_LD_X32(taddr + 64, (a + 64));
-      B2F_TMEM_LD_X32(taddr + 96, (a + 96));
-      tmem_wait_ld();
-      if (h0 + 128 == BN) release();
-      const int n_head0 = n_blk * BN + h0;
-      if (!row_ok || n_head0 >= p.N) continue;
-      const int which = n_head0 / p.d_model;  // 0 = Q, 1 = K, 2 = V, >= 3: second output block
-      if (which < 2) {
-        epilogue_head_norm_rope(p, a, n_head0, row, out_row, which == 1);
-      } else {
-        const bool second = p.split_n > 0 && n_head0 >= p.split_n;
-        __nv_bfloat16* orow = second ? out_row2 : out_row;
-        const int epi = second ? p.epi2 : B2F_EPI_BIAS;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t acc[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = a[cc * 32 + j];
-          epilogue_chunk(p, epi, acc, n_head0 + cc * 32, orow, res_row, gate_row);
-        }
+    if (BN != 256) {
+      // 128-wide tiles (small problems): the head belongs to the half-0 warps, the others only release
+      if (half == 1) {
+        __syncwarp();
+        release();
+        return;
       }
+    }
+    const int h0 = BN == 256 ? half * 128 : 0;
+    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + h0);
+    const int n_head0 = n_blk * BN + h0;
+    const int which = n_head0 / p.d_model;  // 0 = Q, 1 = K, 2 = V, >= 3: second output block
+    __syncwarp();
+    if (which < 2 && n_head0 < p.N) {
+      epilogue_head_norm_rope(p, taddr, n_head0, row, out_row, which == 1, row_ok, release);
+      return;
+    }
+    const bool second = p.split_n > 0 && n_head0 >= p.split_n;
+    __nv_bfloat16* orow = second ? out_row2 : out_row;
+    const int epi = second ? p.epi2 : B2F_EPI_BIAS;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t acc[32];
+      __syncwarp();
+      B2F_TMEM_LD_X32(taddr + cc * 32, acc);
+      tmem_wait_ld();
+      if (cc == 3) release();
+      if (!row_ok || n_head0 + cc * 32 >= p.N) continue;
+      epilogue_chunk(p, epi, acc, n_head0 + cc * 32, orow, res_row, gate_row);
     }
     return;
   }
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = 0; c0 < HALF; c0 += 32) {
     uint32_t acc[32];
-    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
     __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
-    B2F_TMEM_LD_X32(taddr, acc);
+    B2F_TMEM_LD_X32(lane_base + c0, acc);
     tmem_wait_ld();
-    if (c0 + 32 == BN) release();
-    const int n0 = n_blk * BN + c0;
+    if (c0 + 32 >= HALF) release();
+    const int n0 = n_blk * BN + half * HALF + c0;
     if (!row_ok || n0 >= p.N) continue;
     epilogue_chunk(p, p.epi, acc, n0, out_row, res_row, gate_row);
   }
@@ -358,7 +407,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -457,6 +506,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns
     const int row_in_tile = q * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
@@ -472,8 +522,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __nv_bfloat16* out_row = out_row_ptr(p, bidx, row);
       const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
       __nv_bfloat16* out_row2 = p.out2 ? p.out2 + bidx * p.out2_bs + row * p.ldc2 - p.split_n : nullptr;
-      epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], false,
-                        out_row2);
+      epilogue_tile<BN>(p, tmem_base, as, q, half, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as],
+                        false, out_row2);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -509,8 +559,12 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cu
   const double kk = MODE == 2 ? (double)p.kbatch * p.K : (double)p.K;
   prof_begin(KC_GEMM, stream);
   gemm_bf16_kernel<BN, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * kk,
-           2.0 * ((double)p.batch * p.M * kk + (double)p.N * kk + (double)p.batch * p.M * p.N));
+  {
+    char tag_[96];
+    snprintf(tag_, sizeof tag_, "gemm1cta%d m%d %dx%dx%d b%d e%d", BN, MODE, p.M, p.N, (int)kk, p.batch, p.epi);
+    prof_end_tagged(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * kk,
+                    2.0 * ((double)p.batch * p.M * kk + (double)p.N * kk + (double)p.batch * p.M * p.N), tag_);
+  }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("gemm_bf16_kernel");
   return B2F_OK;
@@ -582,7 +636,7 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[i], 2 * EPI_WARPS);  // 8 epilogue warps x 2 CTAs
     }
     fence_mbar_init();
   }
@@ -692,6 +746,7 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = int(rank) * BLOCK_M + q * 32 + lane;  // row inside the 256-row pair tile
     int as = 0;
     uint32_t aphase = 0;
@@ -708,8 +763,8 @@ __device__ __forceinline__ void gemm_pair_body(const CUtensorMap* tmA, const CUt
       __nv_bfloat16* out_row = out_row_ptr(p, bidx, row);
       const __nv_bfloat16* res_row = p.resid ? p.resid + bidx * p.resid_bs + row * p.ldr : nullptr;
       __nv_bfloat16* out_row2 = p.out2 ? p.out2 + bidx * p.out2_bs + row * p.ldc2 - p.split_n : nullptr;
-      epilogue_tile<BN>(p, tmem_base, as, q, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as], true,
-                        out_row2);
+      epilogue_tile<BN>(p, tmem_base, as, q, half, lane, n_blk, row_ok, row, out_row, res_row, gate_row, &tmem_empty[as],
+                        true, out_row2);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -786,8 +841,12 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams 
     gemm_bf16_2cta_kernel<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   else
     gemm_grad_2cta_kernel<MODE><<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * kk,
-           2.0 * ((double)p.batch * p.M * kk + (double)p.N * kk + (double)p.batch * p.M * p.N));
+  {
+    char tag_[96];
+    snprintf(tag_, sizeof tag_, "gemm2cta256 m%d %dx%dx%d b%d e%d", MODE, p.M, p.N, (int)kk, p.batch, p.epi);
+    prof_end_tagged(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * kk,
+                    2.0 * ((double)p.batch * p.M * kk + (double)p.N * kk + (double)p.batch * p.M * p.N), tag_);
+  }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("gemm_bf16_2cta_kernel");
   return B2F_OK;
@@ -805,8 +864,12 @@ int launch_gemm_2cta_n192(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmPa
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
   prof_begin(KC_GEMM, stream);
   gemm_bf16_2cta_n192_kernel<<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  prof_end(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * p.K,
-           2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N));
+  {
+    char tag_[96];
+    snprintf(tag_, sizeof tag_, "gemm2cta192 m0 %dx%dx%d b%d e%d", p.M, p.N, p.K, p.batch, p.epi);
+    prof_end_tagged(KC_GEMM, stream, 2.0 * p.batch * (double)p.M * p.N * p.K,
+                    2.0 * ((double)p.batch * p.M * p.K + (double)p.N * p.K + (double)p.batch * p.M * p.N), tag_);
+  }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   B2F_CHECK_LAUNCH("gemm_bf16_2cta_n192_kernel");
   return B2F_OK;

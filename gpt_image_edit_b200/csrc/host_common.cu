@@ -1,8 +1,12 @@
 // Device facts + TMA tensor-map encoding (driver entry point fetched at run time).
 #include "host_common.h"
 
+#include <cstring>
+
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 namespace b2f {
@@ -39,6 +43,8 @@ struct ProfState {
   std::vector<Rec> recs[KC_COUNT];
   double flops[KC_COUNT] = {0}, bytes[KC_COUNT] = {0};
   cudaEvent_t pending[KC_COUNT] = {nullptr};
+  struct Shape { std::vector<Rec> recs; double flops = 0; };
+  std::map<std::string, Shape> shapes;
   cudaEvent_t get() {
     if (!pool.empty()) {
       cudaEvent_t e = pool.back();
@@ -70,7 +76,37 @@ void prof_end(int kc, cudaStream_t s, double flops, double bytes) {
   g_prof.flops[kc] += flops;
   g_prof.bytes[kc] += bytes;
 }
+void prof_end_tagged(int kc, cudaStream_t s, double flops, double bytes, const char* tag) {
+  if (!g_prof.enabled) return;
+  prof_end(kc, s, flops, bytes);
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  auto& sh = g_prof.shapes[tag];
+  sh.recs.push_back(g_prof.recs[kc].back());     // the event pair is shared with the class list (freed there)
+  sh.flops += flops;
+}
 void prof_set(bool on) { g_prof.enabled = on; }
+// "tag\tlaunches\tms\tTFLOP/s\n" per shape since the last call; must be called BEFORE prof_collect (which recycles the events)
+int prof_shapes(char* buf, int cap) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  std::string out;
+  for (auto& kv : g_prof.shapes) {
+    double ms = 0;
+    for (auto& r : kv.second.recs) {
+      if (cudaEventSynchronize(r.b) != cudaSuccess) return B2F_ERR_CUDA;
+      float t = 0;
+      cudaEventElapsedTime(&t, r.a, r.b);
+      ms += t;
+    }
+    char line[256];
+    snprintf(line, sizeof line, "%s\t%zu\t%.4f\t%.1f\n", kv.first.c_str(), kv.second.recs.size(), ms,
+             ms > 0 ? kv.second.flops / (ms * 1e-3) / 1e12 : 0.0);
+    out += line;
+  }
+  g_prof.shapes.clear();
+  if ((int)out.size() + 1 > cap) return B2F_ERR_WORKSPACE;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)out.size();
+}
 int prof_collect(int kc, double* ms, int64_t* launches, double* flops, double* bytes) {
   if (kc < 0 || kc >= KC_COUNT) return B2F_ERR_INVALID;
   std::lock_guard<std::mutex> lk(g_prof.mu);

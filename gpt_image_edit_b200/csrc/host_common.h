@@ -36,6 +36,8 @@ enum KernelClass { KC_GEMM = 0, KC_ATTN = 1, KC_LNMOD = 2, KC_NORMROPE = 3, KC_C
 bool prof_enabled();
 void prof_begin(int kc, cudaStream_t s);
 void prof_end(int kc, cudaStream_t s, double flops, double bytes);
+// the same, additionally filed under a shape tag ("gemm2 8736x3072x15360 e3"): b2f_prof_shapes() lists the per-shape sums
+void prof_end_tagged(int kc, cudaStream_t s, double flops, double bytes, const char* tag);
 
 inline int cuda_err(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return B2F_OK;

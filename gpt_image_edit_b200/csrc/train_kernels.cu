@@ -575,11 +575,10 @@ __global__ void __launch_bounds__(256) blend_kernel(const __nv_bfloat16* a, cons
   float x[8], y[8];
   unpack8(reinterpret_cast<const uint4*>(a)[i], x);
   unpack8(reinterpret_cast<const uint4*>(b)[i], y);
-  // a Python scalar multiplying a bf16 CUDA tensor is first cast to the tensor's dtype (same rule the Euler step found for
-  // its 0-dim dt): the weights are rounded to bf16 before the multiply
-  const float wab = bf16r(wa), wbb = bf16r(wb);
+  // a Python scalar multiplying a bf16 CUDA tensor enters the kernel as an fp32 (opmath) value, NOT rounded to bf16
+  // (checked on the GPU against torch's own expression; a 0-dim TENSOR operand, as in the Euler step, is cast to bf16 first)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = bf16r(x[j] * wab) + bf16r(y[j] * wbb);
+  for (int j = 0; j < 8; ++j) x[j] = bf16r(x[j] * wa) + bf16r(y[j] * wb);
   reinterpret_cast<uint4*>(out)[i] = pack8(x);
 }
 

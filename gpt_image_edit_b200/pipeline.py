@@ -273,7 +273,7 @@ class FluxKontextPipeline:
             # resize can take this path (anything else goes through the float preprocess like the reference)
             ih, iw = int(image.shape[1]), int(image.shape[2])
             if _auto_resize or ih % mult or iw % mult:
-                image = ((image.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+                image = (((image.cpu().permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5).to(image.device)   # host chain of cli.py:99-116
         if image is not None and image.dtype == torch.uint8:
             pass
         elif image is not None and not (isinstance(image, torch.Tensor) and image.size(1) == self.latent_channels):

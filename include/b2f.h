@@ -47,6 +47,9 @@ uint64_t b2f_launch_count(void);
  * 3 rmsnorm_rope, 4 conv, 5 other. */
 void b2f_prof_enable(int on);
 int b2f_prof_collect(int kernel_class, double* ms, int64_t* launches, double* flops, double* bytes);
+/* Per-shape breakdown of the GEMM class since the last call: lines "tag<TAB>launches<TAB>ms<TAB>TFLOP/s" written to buf
+ * (returns the length, or B2F_ERR_WORKSPACE if cap is too small).  Call BEFORE b2f_prof_collect. */
+int b2f_prof_shapes(char* buf, int cap);
 
 /* ------------------------------------------------------------------------------------------
  * Linear layer: out[M,N] = epilogue(A[M,K] · W[N,K]^T + bias[N]).  tcgen05.mma, TMA, TMEM.
@@ -387,7 +390,7 @@ int b2f_clip_coef(const float* sumsq, float max_norm, float pre_scale, float* co
  * NULL: 1), bf16 copy of the new weights written to p16 (NULL: none).  step counts from 1. */
 int b2f_adamw_step(float* p32, float* m, float* v, const float* g, void* p16, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* gscale, b2f_stream_t stream);
-/* out = bf16(bf16(a * bf16(wa)) + bf16(b * bf16(wb))) over n contiguous bf16 elements (n % 8 == 0): the
+/* out = bf16(bf16(a * wa) + bf16(b * wb)) over n contiguous bf16 elements (n % 8 == 0; wa, wb stay fp32): the
  * `old * (1 - f) + image_embeds * f` blend of vlm_residual_image_factor (modeling_univa_qwen2p5vl.py:504-506). */
 int b2f_blend_bf16(const void* a, const void* b, float wa, float wb, void* out, int64_t n, b2f_stream_t stream);
 /* bf16 <-> fp32 copies of flat arrays (master-weight initialisation, gradient buckets). */

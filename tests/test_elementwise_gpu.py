@@ -74,3 +74,17 @@ def test_euler_step_bit_exact():
     ops.euler_step_(xv[0], v[0], float(dt))
     ops.euler_step_(xv[1], v[1], float(dt))
     assert torch.equal(xv, ref)
+
+
+def test_blend_matches_torch_bf16_expression():
+    """`old * (1 - f) + image_embeds * f` (reference modeling_univa_qwen2p5vl.py:505) evaluated by torch on bf16 CUDA
+    tensors vs b2f_blend_bf16: bit-identical."""
+    from gpt_image_edit_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    old = torch.randn(256, 3584, device="cuda", generator=g).bfloat16()
+    emb = torch.randn(256, 3584, device="cuda", generator=g).bfloat16()
+    for f in (0.3, 0.5, 0.85):
+        want = old * (1 - f) + emb * f
+        got = ops.blend(old, emb, 1 - f, f)
+        assert torch.equal(want, got), f

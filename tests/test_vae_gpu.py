@@ -153,7 +153,8 @@ def test_uint8_pixels_in_and_out_equal_the_host_side_chain():
     vae = B200AutoencoderKL(VaeConfig(block_out_channels=(64, 128, 256, 256))).randomize_(seed=4)
     g = torch.Generator(device="cuda").manual_seed(2)
     u8 = torch.randint(0, 256, (2, 96, 128, 3), device="cuda", generator=g, dtype=torch.uint8)
-    ref_in = ((u8.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+    # the reference normalises on the HOST (torch CPU ops: a true division; CUDA's div-by-scalar multiplies by 1/255)
+    ref_in = (((u8.cpu().permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5).cuda()
     m_u8 = vae.encode(u8).latent_dist.mean
     m_f32 = vae.encode(ref_in).latent_dist.mean
     m_bf16 = vae.encode(ref_in.bfloat16()).latent_dist.mean
