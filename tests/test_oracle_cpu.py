@@ -203,3 +203,33 @@ def test_sigma_schedule_matches_torchtitan_and_pins():
         want = torch.tensor(get_schedule(n, seq), dtype=torch.float64)
         got = ours(n, seq, FlowMatchEulerDiscreteScheduler)
         assert torch.allclose(got, want, rtol=0, atol=2e-6), (n, seq, (got - want).abs().max())
+
+
+def test_oracle_guidance_embedder_matches_torchtitan_plus_guidance():
+    """The guidance MLP (`time_text_embed.guidance_embedder`) and where it enters `vec`: oracle vs torchtitan's FLUX with
+    BFL's `guidance_in` term bolted onto torchtitan's own MLPEmbedder / timestep_embedding (tests/golden/make_golden.py::
+    titan_forward_with_guidance), float64 fixture, guidance 3.5 and 1.0 in one batch."""
+    from oracle import flux_oracle as fo
+
+    blob = torch.load(GOLD / "flux_toy_titan_guidance.pt")
+    cfg = fo.FluxConfig(**blob["cfg"])
+    assert cfg.guidance_embeds
+    sd = fo.make_synthetic_state_dict(cfg, seed=blob["seed"], dtype=torch.float64)
+    i = blob["inputs"]
+    d = lambda t: t.double()
+    out = fo.flux_forward(sd, cfg, d(i["hidden_states"]), d(i["encoder_hidden_states"]), d(i["pooled_projections"]),
+                          d(i["timestep"]), i["img_ids"], i["txt_ids"], guidance=d(i["guidance"]))
+    assert _rel_l2(out, blob["output"]) < 2e-6
+    # the embedder matters: dropping it changes the output by orders of magnitude more than the tolerance
+    sd0 = {k: (torch.zeros_like(v) if "guidance_embedder.linear_2" in k else v) for k, v in sd.items()}
+    out0 = fo.flux_forward(sd0, cfg, d(i["hidden_states"]), d(i["encoder_hidden_states"]), d(i["pooled_projections"]),
+                           d(i["timestep"]), i["img_ids"], i["txt_ids"], guidance=d(i["guidance"]))
+    assert _rel_l2(out0, blob["output"]) > 1e-3
+    if pytest.importorskip("torchtitan.experiments.flux.model.layers", reason="live cross-check needs torchtitan"):
+        sys.path.insert(0, str(GOLD))
+        import make_golden as mg
+        inp = {k: (v.double() if v.is_floating_point() else v) for k, v in i.items()}
+        m = mg.titan_from_diffusers(cfg, {k: v for k, v in sd.items() if "guidance_embedder" not in k})
+        with torch.no_grad():
+            live = mg.titan_forward_with_guidance(m, cfg, sd, inp)
+        assert _rel_l2(out, live) < 1e-9
