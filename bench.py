@@ -272,7 +272,7 @@ def run_reference_arm(args):
     val = 1.0 / sec
     cb = {k: last[k] for k in ("unit", "cores", "threads", "kind", "sample", "excluded")}
     cb["value"] = val
-    if not args.no_cpu_extras:
+    if args.cpu_extras:
         cb["vae"] = cpu_vae_seconds(args.height, args.width, last["threads"])
         cb["sec_per_image_with_vae"] = sec + cb["vae"]["vae_encode_s"] + cb["vae"]["vae_decode_s"]
         cb["config1"] = cpu_config1_seconds(last["threads"])
@@ -434,8 +434,9 @@ def main():
     ap.add_argument("--num-inference-steps", type=int, default=28)
     ap.add_argument("--layers", type=str, default=None, help="debug: 'D,S' block counts (invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-cpu-extras", action="store_true", help="reference arm: skip the one-off VAE and 256x256/4-step "
-                    "(BASELINE.json configs[0]) CPU timings")
+    ap.add_argument("--cpu-extras", action="store_true", help="reference arm: also time, once, the oracle VAE at this size and "
+                    "BASELINE.json configs[0] (256x256, 4 steps, fp32) on the host cores (several minutes; recorded in "
+                    "profiles/r02_cpu_reference_extras.json)")
     ap.add_argument("--sweep", default="", help="comma list of SIZE[xBATCH] configurations measured in one process, e.g. "
                     "512,768,1024,1024x4 (BASELINE.json configs[2] and [4]); writes gpurun_out/sweep_n{N}.json")
     ap.add_argument("--workload", default="edit", choices=["edit", "train512"], help="edit: the headline metric; train512: "

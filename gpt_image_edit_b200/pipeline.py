@@ -154,6 +154,45 @@ class FluxKontextPipeline:
                 comp.to(*a, **k)
         return self
 
+    # ------------------------------------------------------------------ argument validation (reference :490-560)
+    _callback_tensor_inputs = ("latents", "prompt_embeds")
+
+    def check_inputs(self, prompt, prompt_2, height, width, negative_prompt=None, negative_prompt_2=None, prompt_embeds=None,
+                     negative_prompt_embeds=None, pooled_prompt_embeds=None, negative_pooled_prompt_embeds=None,
+                     callback_on_step_end_tensor_inputs=None, max_sequence_length=None):
+        """Same rejections, in the same order, as the reference's `check_inputs` (ValueError in every case; a size that
+        is not a multiple of 16 only warns there and is floored by the size rule)."""
+        cb = callback_on_step_end_tensor_inputs
+        bad_cb = [k for k in (cb or ()) if k not in self._callback_tensor_inputs]
+        if bad_cb:
+            raise ValueError(f"`callback_on_step_end_tensor_inputs` has to be in {list(self._callback_tensor_inputs)}, but found {bad_cb}")
+        both = "Please make sure to only forward one of the two."
+        rules = [
+            (prompt is not None and prompt_embeds is not None, f"Cannot forward both `prompt`: {prompt} and `prompt_embeds`. {both}"),
+            (prompt_2 is not None and prompt_embeds is not None, f"Cannot forward both `prompt_2`: {prompt_2} and `prompt_embeds`. {both}"),
+            (prompt is None and prompt_embeds is None,
+             "Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` undefined."),
+            (prompt is not None and not isinstance(prompt, (str, list)), f"`prompt` has to be of type `str` or `list` but is {type(prompt)}"),
+            (prompt_2 is not None and not isinstance(prompt_2, (str, list)),
+             f"`prompt_2` has to be of type `str` or `list` but is {type(prompt_2)}"),
+        ]
+        for cond, msg in rules:          # the reference chains these with elif: the first hit wins
+            if cond:
+                raise ValueError(msg)
+        if negative_prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `negative_prompt`: {negative_prompt} and `negative_prompt_embeds`. {both}")
+        if negative_prompt_2 is not None and negative_prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `negative_prompt_2`: {negative_prompt_2} and `negative_prompt_embeds`. {both}")
+        if prompt_embeds is not None and pooled_prompt_embeds is None:
+            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed. Make sure to generate "
+                             "`pooled_prompt_embeds` from the same text encoder that was used to generate `prompt_embeds`.")
+        if negative_prompt_embeds is not None and negative_pooled_prompt_embeds is None:
+            raise ValueError("If `negative_prompt_embeds` are provided, `negative_pooled_prompt_embeds` also have to be passed. Make sure "
+                             "to generate `negative_pooled_prompt_embeds` from the same text encoder that was used to generate "
+                             "`negative_prompt_embeds`.")
+        if max_sequence_length is not None and max_sequence_length > 512:
+            raise ValueError(f"`max_sequence_length` cannot be greater than 512 but is {max_sequence_length}")
+
     # ------------------------------------------------------------------ layout helpers (reference :561-598)
     @staticmethod
     def _prepare_latent_image_ids(batch_size, height, width, device, dtype):
@@ -224,15 +263,21 @@ class FluxKontextPipeline:
                  pooled_prompt_embeds=None, negative_prompt_embeds=None, negative_pooled_prompt_embeds=None,
                  output_type: str = "pil", return_dict: bool = True, joint_attention_kwargs=None,
                  callback_on_step_end: Optional[Callable] = None, callback_on_step_end_tensor_inputs=("latents",),
-                 max_sequence_length: int = 512, max_area: int = 1024 ** 2, _auto_resize: bool = True):
+                 max_sequence_length: int = 512, max_area: int = 1024 ** 2, _auto_resize: bool = True,
+                 ip_adapter_image=None, ip_adapter_image_embeds=None, negative_ip_adapter_image=None,
+                 negative_ip_adapter_image_embeds=None):
         self._interrupt = False                    # reference :922 resets the flag at the start of every call
-        if prompt is not None and prompt_embeds is not None:
-            raise ValueError("Cannot forward both `prompt` and `prompt_embeds`. Please make sure to only forward one of the two.")
-        if prompt_embeds is not None and pooled_prompt_embeds is None:
-            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+        if any(a is not None for a in (ip_adapter_image, ip_adapter_image_embeds, negative_ip_adapter_image,
+                                       negative_ip_adapter_image_embeds)):
+            # the reference forwards these to an image encoder + IP-adapter attention processors (:441-488, 1024-1050);
+            # neither cli.py nor the eval drivers ever pass them, and FLUX-Kontext checkpoints ship no IP-adapter
+            raise NotImplementedError("IP-adapter inputs are accepted by the reference's pipeline but not built in this engine")
+        self.check_inputs(prompt, prompt_2, height, width, negative_prompt=negative_prompt, negative_prompt_2=negative_prompt_2,
+                          prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
+                          pooled_prompt_embeds=pooled_prompt_embeds, negative_pooled_prompt_embeds=negative_pooled_prompt_embeds,
+                          callback_on_step_end_tensor_inputs=list(callback_on_step_end_tensor_inputs or ()),
+                          max_sequence_length=max_sequence_length)
         if prompt_embeds is None:
-            if prompt is None:
-                raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both undefined.")
             # string prompts: CLIP pooled + T5 hidden states through the libb2f encoders (reference :925-944)
             prompt_embeds, pooled_prompt_embeds, _ = self.encode_prompt(
                 prompt, prompt_2, device=self._execution_device, num_images_per_prompt=1,

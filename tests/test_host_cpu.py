@@ -232,8 +232,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     from pathlib import Path
 
     root = Path(__file__).resolve().parent.parent
-    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0",
-                        "--no-cpu-extras"],    # the one-off VAE / 256px-4-step CPU timings take minutes on a small host
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
@@ -288,3 +287,26 @@ def test_ctypes_signatures_match_the_header():
         want = [k for k in (kind(a) for a in args.split(",")) if k]
         have = [m.get(h, "p") for h in _lib._SIGNATURES[name][1]]
         assert want == have, (name, want, have)
+
+
+def test_pipeline_check_inputs_rejects_what_the_reference_rejects():
+    """`FluxKontextPipeline.check_inputs` against the outputs of the reference's own function source
+    (tests/golden/check_inputs_ref.pt, made by make_check_inputs_golden.py): the same argument combinations are rejected,
+    with a ValueError whose message starts the same way."""
+    from pathlib import Path
+
+    from gpt_image_edit_b200.pipeline import FluxKontextPipeline
+
+    pipe = FluxKontextPipeline.__new__(FluxKontextPipeline)
+    pipe.vae_scale_factor = 8
+    ref = torch.load(Path(__file__).parent / "golden" / "check_inputs_ref.pt", weights_only=False)
+    assert sum(r["raised"] for r in ref) >= 9 and sum(not r["raised"] for r in ref) >= 6
+    for r in ref:
+        try:
+            pipe.check_inputs(**r["kwargs"])
+            raised, msg = False, ""
+        except ValueError as e:
+            raised, msg = True, str(e)
+        assert raised == r["raised"], (r["kwargs"], r["message"], msg)
+        if raised:
+            assert msg.split(":")[0].split(".")[0][:40] == r["message"].split(":")[0].split(".")[0][:40], (msg, r["message"])
