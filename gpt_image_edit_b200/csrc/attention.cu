@@ -13,13 +13,19 @@
 // warpgroup itself, between "S ready" (which also proves the previous P·V finished) and "P ready".
 //
 // Kernels in this file (B2F_ATTN_VARIANT selects at run time; all parity-green, tests/test_attention_gpu.py):
-//   51 (default)  attn_fwd_kernel_2cta<4>: the same two-tile structure as a CTA PAIR (cta_group::2, M = 256 MMAs,
-//                 each CTA stores half of every K / V tile) for non-causal, bias-free calls with >= 512 query rows
-//                 (the FLUX joint attention); anything else falls through to
-//   1             attn_fwd_kernel<4>: the single-CTA two-tile kernel described above (causal, GQA, bias, short)
-//   0,2,5,6       other fractions of exponentials on the FMA pipe;  50/52 the same for the pair kernel
-//   10-12, 30-32, 40-42, 60-62   experiments kept for the record (S sub-blocks / single tile with S double
-//                 buffering / column-split warpgroups): none is faster, see DESIGN.md section 7
+//   54 (default)  attn_fwd_kernel_2cta_nr<3>: the same two-tile structure as a CTA PAIR (cta_group::2, M = 256 MMAs, each
+//                 CTA stores half of every K / V tile) for non-causal, bias-free calls with >= 512 query rows (the FLUX
+//                 joint attention).  Warps 0-3 are a light warpgroup (TMA, MMA issue, TMEM allocator) that hands its
+//                 registers to the eight softmax warps with setmaxnreg (80 / 208: no spills); a third of the
+//                 exponentials run as a polynomial on the FMA pipe.  53 / 56: a quarter / none of them.
+//   51            attn_fwd_kernel_2cta<4>: the pair kernel with warps 2.. as softmax warps at the 168 registers the launch
+//                 bounds give (3 warps per sub-partition): 3-5 % slower
+//   1             attn_fwd_kernel<4>: the single-CTA two-tile kernel described above (causal, GQA, bias, short): what
+//                 the pair kernels do not cover falls through to it
+//   0,2,5,6       other fractions of exponentials on the FMA pipe;  50/52 the same for the 168-register pair kernel
+//   10-12, 30-32, 40-42, 60-62   experiments kept for the record in attention_experiments.cu (`make EXPERIMENTS=1`);
+//                 round-2 structural experiments (column-split pair, one tile per CTA with double / triple buffered S and
+//                 register prefetch) were measured and removed, see DESIGN.md section 7 and profiles/r02_attn_variants_*.json
 //
 // Replaces F.scaled_dot_product_attention as reached by diffusers FluxAttnProcessor2_0
 // (reference call site univa/utils/flux_pipeline.py:1067) and flash_attn as reached
@@ -29,7 +35,7 @@
 #include <cstdlib>
 
 #ifndef B2F_ATTN_DEFAULT_VARIANT
-#define B2F_ATTN_DEFAULT_VARIANT 51
+#define B2F_ATTN_DEFAULT_VARIANT 54
 #endif
 
 #include "attention_common.cuh"
@@ -406,11 +412,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 constexpr int P2_SLOTS = 8;                       // half tiles of 16 KB: K_j/2, V_j/2 alternating
 constexpr int P2_HALF = TILE_BYTES / 2;
 constexpr int P2_SMEM = 2 * TILE_BYTES + P2_SLOTS * P2_HALF + 256 + 1024;
+constexpr int P2_THREADS_NR = 128 + 8 * 32;       // light warpgroup + 8 softmax warps
 
-template <int POLY>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_THREADS, 1)
-attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+// NR = 0: warps 0 / 1 = TMA / MMA, warps 2.. = softmax (register budget from the launch bounds: 168 with 3 warps per
+// sub-partition).  NR > 0: warps 0-3 form a light warpgroup (TMA, MMA, TMEM allocator, idle) that gives its registers
+// up with setmaxnreg.dec and the softmax warpgroups (warps 4..) grow to NR registers.
+template <int POLY, int NR>
+static __device__ __forceinline__ void attn_pair_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                                      const AttnParams& p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -462,7 +471,10 @@ attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  constexpr int SW0 = NR > 0 ? 4 : 2;   // first softmax warp
 
+  if (warp < SW0) {
+  if constexpr (NR > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(80));
   if (warp == 0) {
     if (lane == 0) {
       // ---------------------------------------------------------------- TMA producer (one per CTA)
@@ -596,9 +608,12 @@ attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       commit(&o_done[0]);
       commit(&o_done[1]);
     }
+  }
   } else {
+  if constexpr (NR > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NR));
+  {
     // ------------------------------------------------------------------ softmax warpgroups (both CTAs)
-    const int t = (warp - 2) >> 2;
+    const int t = (warp - SW0) >> 2;
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     const int q_row = q0 + t * 2 * BQ + int(crank) * BQ + row_in_tile;
@@ -611,18 +626,18 @@ attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
         uint32_t sr[128];
+        const int kv0 = j * BKV;
+        float mx4[4];
         B2F_TMEM_LD_X32(s_tmem + 0, (sr + 0));
         B2F_TMEM_LD_X32(s_tmem + 32, (sr + 32));
         B2F_TMEM_LD_X32(s_tmem + 64, (sr + 64));
         B2F_TMEM_LD_X32(s_tmem + 96, (sr + 96));
         tmem_wait_ld();
-        const int kv0 = j * BKV;
         if (kv0 + BKV > p.Skv) {
 #pragma unroll
           for (int c = 0; c < 128; ++c)
             if (kv0 + c >= p.Skv) sr[c] = 0xff800000u;  // -inf
         }
-        float mx4[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) mx4[i] = fmaxf(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1]));
 #pragma unroll
@@ -704,6 +719,7 @@ attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   }
+  }
 
   tc_fence_before();
   cluster_sync_all();   // both CTAs are done with each other's barriers / smem halves / TMEM
@@ -713,6 +729,19 @@ attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+template <int POLY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_THREADS, 1)
+attn_fwd_kernel_2cta(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  attn_pair_body<POLY, 0>(tmQ, tmK, tmV, p);
+}
+// light warpgroup + 8 softmax warps at 208 registers (3 warps per sub-partition: 80 + 2 x 208 <= 512)
+template <int POLY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS_NR, 1)
+attn_fwd_kernel_2cta_nr(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  attn_pair_body<POLY, 208>(tmQ, tmK, tmV, p);
+}
 }  // namespace
 
 static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
@@ -737,7 +766,7 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     const int variant = ev ? atoi(ev) : B2F_ATTN_DEFAULT_VARIANT;
     Variant sel = {nullptr, ATTN_THREADS, ATTN_SMEM, false};
     switch (variant) {
-      case 1: case 50: case 51: case 52:                          // (50-52: what the CTA-pair kernel does not cover)
+      case 1: case 50: case 51: case 52: case 53: case 54: case 55: case 56: case 57: case 58: case 59:   // (50-59: what the CTA-pair kernel does not cover)
         sel.fn = attn_fwd_kernel<4, false>; break;               // 25 % of the exponentials on the FMA pipe
       case 2: sel.fn = attn_fwd_kernel<2, false>; break;         // 50 %
       case 3: sel.fn = attn_fwd_kernel<0, true>; break;
@@ -756,16 +785,24 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     var = sel;
   }
   // CTA-pair kernel (B2F_ATTN_VARIANT 50 / 51 / 52): non-causal, no bias, at least one full 512-row pair
-  static const int pair_poly = [] {
+  static const int pair_variant = [] {
     const char* v = getenv("B2F_ATTN_VARIANT");
     const int variant = v ? atoi(v) : B2F_ATTN_DEFAULT_VARIANT;
-    return variant == 50 ? 0 : variant == 51 ? 4 : variant == 52 ? 2 : -1;
+    return (variant >= 50 && variant <= 59) ? variant : -1;
   }();
-  if (pair_poly >= 0 && !causal && !bias && Sq >= 4 * BQ) {
+  if (pair_variant >= 0 && !causal && !bias && Sq >= 4 * BQ) {
     static KernelFn pk = nullptr;
+    static int pk_threads = ATTN_THREADS, pk_rows = 4 * BQ, pk_smem = P2_SMEM;
     if (!pk) {
-      pk = pair_poly == 0 ? attn_fwd_kernel_2cta<0> : pair_poly == 4 ? attn_fwd_kernel_2cta<4> : attn_fwd_kernel_2cta<2>;
-      cudaError_t e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
+      switch (pair_variant) {
+        case 50: pk = attn_fwd_kernel_2cta<0>; break;
+        case 52: pk = attn_fwd_kernel_2cta<2>; break;
+        case 51: pk = attn_fwd_kernel_2cta<4>; break;
+        case 53: pk = attn_fwd_kernel_2cta_nr<4>; pk_threads = P2_THREADS_NR; break;
+        case 56: pk = attn_fwd_kernel_2cta_nr<0>; pk_threads = P2_THREADS_NR; break;
+        default: pk = attn_fwd_kernel_2cta_nr<3>; pk_threads = P2_THREADS_NR; break;   // 54
+      }
+      cudaError_t e = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, pk_smem);
       if (e != cudaSuccess) return cuda_err(e, "attention pair smem attribute");
     }
     CUtensorMap tQ, tK, tV;
@@ -787,9 +824,9 @@ static int attention_impl(const void* q, int64_t ldq, const void* k, int64_t ldk
     pp.ldo = ldo;
     pp.lse = lse;
     pp.lse_stride = lse_stride;
-    dim3 grid_p(2 * ((Sq + 4 * BQ - 1) / (4 * BQ)), H, B);
+    dim3 grid_p(2 * ((Sq + pk_rows - 1) / pk_rows), H, B);
     prof_begin(KC_ATTN, stream);
-    pk<<<grid_p, ATTN_THREADS, P2_SMEM, stream>>>(tQ, tK, tV, pp);
+    pk<<<grid_p, pk_threads, pk_smem, stream>>>(tQ, tK, tV, pp);
     prof_end(KC_ATTN, stream, 4.0 * B * H * (double)Sq * Skv * DH, 2.0 * DH * B * (2.0 * H * Sq + 2.0 * Hkv * Skv));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     B2F_CHECK_LAUNCH("attn_fwd_kernel_2cta");
