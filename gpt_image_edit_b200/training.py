@@ -359,6 +359,46 @@ def flow_matching_loss(pred, target, weight=None, grad_scale: float = 1.0):
     return T.mse_loss(pred.contiguous(), target.contiguous(), weight=weight, grad_scale=grad_scale)
 
 
+def pad_x_and_mask(xs, masks=None, max_h=None, max_w=None):
+    """Mixed-size batches (train_denoiser.py:158-183): zero-pad a list of [1, C, h_i, w_i] tensors on the right / bottom to
+    a common size and concatenate; `masks` (same shapes) are cut to one channel and padded the same way.
+    Returns (x [B, C, H, W], mask [B, 1, H, W] | None)."""
+    F = torch.nn.functional
+    max_h = max(t.shape[2] for t in xs) if max_h is None else max_h
+    max_w = max(t.shape[3] for t in xs) if max_w is None else max_w
+    pad = lambda t: F.pad(t, (0, max_w - t.shape[3], 0, max_h - t.shape[2]), mode="constant", value=0)
+    x = torch.cat([pad(t) for t in xs], dim=0)
+    if masks is None or masks[0] is None:
+        return x, None
+    return x, torch.cat([pad(m[:, :1]) for m in masks], dim=0)
+
+
+def loss_weights(weighting, B, C, h, w, area_weights=None, weight_mask=None, unpad_sizes=None):
+    """The element weights of the flow-matching loss and the factor that turns their weighted MEAN over [B, C, h, w] into
+    the reference's loss (train_denoiser.py:1117-1165):
+      weighting [B,1,1,1] (SD3 scheme or sigmas) x area-mask weights (tensor, nearest-resized to the latent; or, for mixed-size
+      batches, a list resized to each sample's own latent size and zero-padded) x weight_mask (1 inside each sample's latent);
+      loss = mean(w * err^2) without a weight_mask, sum(w * err^2) / weight_mask.sum() / C with one.
+    Returns (weights [B,1,h,w] or [B,1,1,1] fp32, scale)."""
+    F = torch.nn.functional
+    wt = weighting.float()
+    if area_weights is not None:
+        if isinstance(area_weights, (list, tuple)):
+            sizes = unpad_sizes if unpad_sizes is not None else [(h, w)] * len(area_weights)
+            aw = [F.interpolate(a.float(), size=tuple(sz), mode="nearest") for a, sz in zip(area_weights, sizes)]
+            aw, _ = pad_x_and_mask(aw, max_h=h, max_w=w)
+        else:
+            aw = area_weights.float()
+            if aw.shape[-2:] != (h, w):
+                aw = F.interpolate(aw, size=(h, w), mode="nearest")
+        wt = wt * aw
+    scale = 1.0
+    if weight_mask is not None:
+        wt = wt * weight_mask.float()
+        scale = float(B * C * h * w) / (float(weight_mask.float().sum()) * C)
+    return wt, scale
+
+
 # ------------------------------------------------------------------------------------------------ one optimisation step
 def compute_density_for_timestep_sampling(weighting_scheme, batch_size, logit_mean=0.0, logit_std=1.0, mode_scale=1.29,
                                           generator=None, device="cpu"):
@@ -474,13 +514,24 @@ class Stage2Trainer:
         tc, mc = self.tc, self.mc
         dev = self.model.device
         pipe = self.pipe
-        gen_img = batch["generated_image"].to(dev)
+        gen_img = batch["generated_image"]
         cond = batch.get("ref_pixel_values")
         if cond is not None:
             if cond.ndim == 5:
                 cond = cond.view(-1, *cond.shape[2:])
             cond = cond.to(dev, dtype=torch.float32)
-        model_input = self._vae_latents(gen_img, self.gen)                                   # [B,16,h,w] fp32
+        weight_mask = unpad_sizes = None
+        if isinstance(gen_img, (list, tuple)):
+            # mixed-size batch (:907-916): every target encoded at its own size, latents zero-padded to the largest; the
+            # padding is excluded from the loss through weight_mask.  (The reference also builds a token mask and passes it
+            # as joint_attention_kwargs, which UnivaDenoiseTower.forward pops and drops (:77): attention sees the padding.)
+            if len(gen_img) == 1:
+                raise ValueError("a list of target images needs batch_size != 1 (train_denoiser.py:909)")
+            unpad = [self._vae_latents(x.to(dev), self.gen) for x in gen_img]
+            unpad_sizes = [tuple(x.shape[-2:]) for x in unpad]
+            model_input, weight_mask = pad_x_and_mask(unpad, [torch.ones_like(x) for x in unpad])
+        else:
+            model_input = self._vae_latents(gen_img.to(dev), self.gen)                       # [B,16,h,w] fp32
         B, C, h, w = model_input.shape
         noise = torch.randn(model_input.shape, device=dev, dtype=model_input.dtype, generator=self.gen)
         sigmas, timesteps = self.sample_sigmas(B, (h, w), dev)
@@ -514,15 +565,13 @@ class Stage2Trainer:
         target = pipe._pack_latents(noise - model_input, B, C, h, w).float().contiguous()   # packing is a permutation
         weighting = sigmas.view(B, 1, 1, 1) if tc.sigmas_as_weight else \
             compute_loss_weighting_for_sd3(tc.weighting_scheme, sigmas).view(B, 1, 1, 1)
+        am = batch.get("weights") if tc.mask_weight_type is not None else None
+        if am is not None:
+            am = [a.to(dev) for a in am] if isinstance(am, (list, tuple)) else am.to(dev)
+        wt, wscale = loss_weights(weighting, B, C, h, w, area_weights=am, weight_mask=weight_mask, unpad_sizes=unpad_sizes)
         wts = None
-        am = batch.get("weights")
-        if tc.mask_weight_type is not None and am is not None:
-            am = am.to(dev).float()
-            if am.shape[-2:] != (h, w):
-                am = torch.nn.functional.interpolate(am, size=(h, w), mode="nearest")
-            weighting = weighting.float() * am
-        if weighting.numel() > 1 and not bool((weighting == 1).all()):
-            wts = pipe._pack_latents(weighting.expand(B, C, h, w).contiguous(), B, C, h, w).float().contiguous()
+        if wscale != 1.0 or (wt.numel() > 1 and not bool((wt == 1).all())):
+            wts = pipe._pack_latents((wt * wscale).expand(B, C, h, w).contiguous(), B, C, h, w).float().contiguous()
         ga = tc.gradient_accumulation_steps
         loss, dpred = flow_matching_loss(pred, target, weight=wts, grad_scale=1.0 / ga)
         if getattr(self, "trace", None) is not None:          # test / debug hook: checksums of the step's intermediates

@@ -310,3 +310,31 @@ def test_pipeline_check_inputs_rejects_what_the_reference_rejects():
         assert raised == r["raised"], (r["kwargs"], r["message"], msg)
         if raised:
             assert msg.split(":")[0].split(".")[0][:40] == r["message"].split(":")[0].split(".")[0][:40], (msg, r["message"])
+
+
+def test_mixed_size_batches_match_the_reference_statements():
+    """pad_x_and_mask and the loss weights / normalisation of mixed-size batches against tests/golden/mixed_size_ref.pt
+    (the reference's own statements, train_denoiser.py:158-183 and :1104-1165, executed by make_mixed_size_golden.py)."""
+    import torch
+    from gpt_image_edit_b200.training import compute_loss_weighting_for_sd3, loss_weights, pad_x_and_mask
+    from pathlib import Path
+    ref = torch.load(Path(__file__).parent / "golden" / "mixed_size_ref.pt", weights_only=False)
+    assert len(ref["cases"]) == 5
+    for c in ref["cases"]:
+        mixed = len(set(c["sizes"])) > 1
+        if mixed:
+            x, mask = pad_x_and_mask(c["unpad"], [torch.ones_like(t) for t in c["unpad"]])
+            assert torch.equal(x, c["model_input"]) and torch.equal(mask, c["mask"]), c["name"]
+        else:
+            x, mask = c["model_input"], None
+        B, C, h, w = x.shape
+        sig = c["sigmas"]
+        weighting = sig if c["sigmas_as_weight"] else compute_loss_weighting_for_sd3(c["scheme"], sig)
+        area = c["area_weights"] if c["mask_weight_type"] is not None else None
+        wt, scale = loss_weights(weighting, B, C, h, w, area_weights=area, weight_mask=mask,
+                                 unpad_sizes=[tuple(t.shape[-2:]) for t in c["unpad"]] if mixed else None)
+        assert torch.allclose(wt.expand(B, 1, h, w), c["weighting"], rtol=0, atol=0), c["name"]
+        # what Stage2Trainer hands to the loss kernel: mean(scale * wt * err^2) over [B, C, h, w]
+        err2 = (c["model_pred"].float() - c["target"].float()) ** 2
+        loss = (scale * wt * err2).mean()
+        assert abs(float(loss) - float(c["loss"])) <= 2e-6 * abs(float(c["loss"])), (c["name"], float(loss), float(c["loss"]))

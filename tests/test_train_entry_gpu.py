@@ -53,3 +53,38 @@ def test_gradient_accumulation_and_batch_two(tmp_path, capsys):
     assert trainer.global_step == 2 and trainer._micro == 4
     out = capsys.readouterr().out
     assert out.count("\nstep ") + out.startswith("step ") >= 2
+
+
+def test_mixed_size_batch_masks_the_padding(tmp_path, monkeypatch):
+    """A batch whose targets have different sizes (train_denoiser.py:907-916, 1151-1165): latents are zero-padded to the
+    largest, the padding carries zero loss weight and the loss is normalised by the unpadded area.  The weights themselves
+    are pinned to the reference's statements on CPU (tests/test_host_cpu.py); here the step runs on the engine and the
+    kernel's loss is recomputed in torch from what it was given."""
+    import train_denoiser as td
+    from gpt_image_edit_b200 import training as T
+
+    conf = _conf(tmp_path, max_train_steps=1, checkpointing_steps=1000)
+    conf.dataset_config.batch_size = 2
+    conf.dataset_config.synthetic_target_sizes = [[256, 256], [192, 320]]
+    seen = {}
+    real = T.flow_matching_loss
+
+    def spy(pred, target, weight=None, grad_scale=1.0):
+        loss, d = real(pred, target, weight=weight, grad_scale=grad_scale)
+        seen.update(pred=pred.float().clone(), target=target.clone(), weight=weight.clone(), loss=loss.clone(), d=d.float().clone())
+        return loss, d
+
+    monkeypatch.setattr(T, "flow_matching_loss", spy)
+    trainer = td.main(conf)
+    assert trainer.global_step == 1
+    B, S, D = seen["pred"].shape                       # packed [2, (32/2)*(40/2), 64]
+    assert (B, S, D) == (2, 16 * 20, 64)
+    w = seen["weight"]
+    # sample 0 is 32x32 latent inside a 32x40 pad, sample 1 is 24x40: unpack the weights and look at the padding
+    wl = w.view(B, 16, 20, 16, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, 16, 32, 40)
+    assert float(wl[0, :, :, 32:].abs().max()) == 0 and float(wl[1, :, 24:, :].abs().max()) == 0
+    assert float(wl[0, :, :, :32].min()) > 0 and float(wl[1, :, :24, :].min()) > 0
+    ref = (w.double() * (seen["pred"].double() - seen["target"].double()) ** 2).mean()
+    assert abs(float(seen["loss"]) - float(ref)) <= 1e-4 * abs(float(ref))
+    assert float(seen["d"][0].view(16, 20, 16, 2, 2)[:, 16:].abs().max()) == 0      # no gradient into sample 0's padding
+    assert torch.isfinite(seen["d"]).all()

@@ -109,7 +109,7 @@ def main(conf):
         trainer.opt.load_state_dict(torch.load(ck / f"optimizer_rank{rank}.pt", map_location=device))
         start = json.loads((ck / "trainer_state.json").read_text())["global_step"]
         trainer.global_step = start
-    data = SyntheticEditDataset(dc.height, dc.width, dc.synthetic_len, seed=tc.seed + rank)
+    data = SyntheticEditDataset(dc.height, dc.width, dc.synthetic_len, seed=tc.seed + rank, target_sizes=dc.synthetic_target_sizes)
     loader = torch.utils.data.DataLoader(data, batch_size=dc.batch_size, collate_fn=collate, num_workers=0,
                                          pin_memory=dc.pin_memory)
     max_steps = tc.max_train_steps or (len(loader) * tc.num_train_epochs // tc.gradient_accumulation_steps)

@@ -112,6 +112,8 @@ class DatasetConfig:
     validation_SEGit2i_path: Optional[str] = None
     # addition: length of the synthetic dataset (dataset_type: "synthetic")
     synthetic_len: int = 1 << 30
+    # addition: target sizes [[H, W], ...] the synthetic samples cycle through (mixed-size batches, batch_size != 1)
+    synthetic_target_sizes: Optional[list] = None
 
 
 @dataclass

@@ -19,8 +19,11 @@ import torch
 
 class SyntheticEditDataset(torch.utils.data.Dataset):
     def __init__(self, height: int = 512, width: int = 512, length: int = 1 << 30, seed: int = 0, n_text: int = 22,
-                 vocab: int = 152064):
+                 vocab: int = 152064, target_sizes=None):
         self.h, self.w, self.length, self.seed, self.n_text, self.vocab = height, width, length, seed, n_text, vocab
+        # mixed-size batches (train_denoiser.py:907-916): sample i's TARGET has size target_sizes[i % len]; the source
+        # image keeps (height, width), as the reference stacks condition_pixel_values
+        self.target_sizes = [tuple(int(v) for v in s) for s in target_sizes] if target_sizes else None
 
     def __len__(self):
         return self.length
@@ -33,14 +36,20 @@ class SyntheticEditDataset(torch.utils.data.Dataset):
         src_u8 = torch.randint(0, 256, (3, self.h, self.w), generator=g, dtype=torch.uint8)
         src = src_u8.float() / 127.5 - 1.0
         # the target is the source with a rectangular region re-drawn: a real edit changes part of the picture
-        tgt = src.clone()
-        bh, bw = max(16, self.h // 4), max(16, self.w // 4)
-        y0 = int(torch.randint(0, self.h - bh + 1, (1,), generator=g))
-        x0 = int(torch.randint(0, self.w - bw + 1, (1,), generator=g))
+        th, tw = self.target_sizes[i % len(self.target_sizes)] if self.target_sizes else (self.h, self.w)
+        if (th, tw) == (self.h, self.w):
+            tgt = src.clone()
+        else:                                   # integer nearest-neighbour view of the source at the target's size
+            ty = (torch.arange(th) * self.h) // th
+            tx = (torch.arange(tw) * self.w) // tw
+            tgt = src_u8[:, ty][:, :, tx].float() / 127.5 - 1.0
+        bh, bw = max(16, th // 4), max(16, tw // 4)
+        y0 = int(torch.randint(0, th - bh + 1, (1,), generator=g))
+        x0 = int(torch.randint(0, tw - bw + 1, (1,), generator=g))
         tgt[:, y0:y0 + bh, x0:x0 + bw] = torch.randint(0, 256, (3, bh, bw), generator=g, dtype=torch.uint8).float() / 127.5 - 1.0
-        lh, lw = self.h // 8, self.w // 8
+        lh, lw = th // 8, tw // 8
         weights = torch.ones(1, lh, lw)
-        ratio = (self.h * self.w) / (bh * bw)
+        ratio = (th * tw) / (bh * bw)
         weights[:, y0 // 8:(y0 + bh) // 8, x0 // 8:(x0 + bw) // 8] = math.log2(ratio) + 1.0
         # 448x448 nearest-neighbour view of the source for the VLM: 32x32 patches of 14 -> 1024 rows of 1176, 256 image tokens
         iy = (torch.arange(448) * self.h) // 448
@@ -54,11 +63,15 @@ class SyntheticEditDataset(torch.utils.data.Dataset):
 
 
 def collate(samples: list) -> dict:
-    """Equal-size samples only (the synthetic set has one resolution; the reference's mixed-size list path needs
-    attention masks, which this engine does not implement)."""
+    """Targets of one size are stacked; targets of different sizes stay a LIST of [1, 3, H_i, W_i] tensors (and their
+    area-mask weights a list of [1, 1, h_i, w_i]), which is what the reference's loop tests for (train_denoiser.py:907,
+    :1120)."""
     out = {}
-    for k in ("generated_image", "ref_pixel_values", "input_ids", "attention_mask", "weights"):
+    for k in ("ref_pixel_values", "input_ids", "attention_mask"):
         out[k] = torch.stack([s[k] for s in samples])
+    mixed = len({tuple(s["generated_image"].shape) for s in samples}) > 1
+    for k in ("generated_image", "weights"):
+        out[k] = [s[k][None] for s in samples] if mixed else torch.stack([s[k] for s in samples])
     out["pixel_values"] = torch.cat([s["pixel_values"] for s in samples], dim=0)
     out["image_grid_thw"] = torch.stack([s["image_grid_thw"] for s in samples])
     out["prompts"] = [s["prompts"] for s in samples]
