@@ -119,6 +119,35 @@ def test_hoisted_schedule_equals_per_step_modulation():
         model._schedule = model_sched
         assert torch.equal(o1, o2), f"step {i}"
 
+def test_forward_replays_from_a_cuda_graph():
+    """include/b2f.h: b2f_flux_forward allocates nothing and never synchronises with the host, so a stream capture
+    records it.  Capture one forward on static buffers, change the inputs in place, replay: the result equals an eager
+    call on the new inputs, bit for bit."""
+    ocfg, sd, model, inp = _setup(TOY, 2, 40, 10, 10, seed=9)
+    ts = (torch.tensor([1000.0, 976.2225, 500.0], device="cuda").bfloat16() / 1000)
+    model.prepare_schedule(ts, inp["guidance"], inp["pooled_projections"])
+    static = dict(inp, timestep=ts[0].expand(2))
+    kw = dict(return_dict=False, joint_attention_kwargs={"_b2f_schedule_step": 0})
+    model(**static, **kw)                                   # warm-up: workspaces and RoPE tables exist before the capture
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            out_static = model(**static, **kw)[0]
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    for step in (1, 2):
+        new_h = torch.randn(static["hidden_states"].shape, device="cuda", generator=g).bfloat16()
+        static["hidden_states"].copy_(new_h)
+        model._schedule.mod[0].copy_(model._schedule.mod[step])        # the captured call reads step 0's modulation rows
+        graph.replay()
+        torch.cuda.synchronize()
+        got = out_static.clone()
+        want = model(**dict(static, hidden_states=new_h), return_dict=False, joint_attention_kwargs={"_b2f_schedule_step": step})[0]
+        assert torch.equal(got, want), f"step {step}"
+
 
 def test_full_width_single_double_block_matches_oracle():
     """Real layer width (d=3072, 24 heads, joint 4096) with 1 double + 1 single block at the 256^2
