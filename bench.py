@@ -49,7 +49,9 @@ def ncu_traffic(kernel_class: str):
     None when no capture of that class is committed — the figure is never borrowed from another kernel."""
     want = "attn" if kernel_class == "attention" else "gemm"
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for f in sorted((ROOT / "profiles").glob("r*_ncu_full*summary.json"), reverse=True):
+    # captures of the training step (scripts/profile_train.py) hold dgrad / wgrad launches: not this workload's kernels
+    files = [f for f in (ROOT / "profiles").glob("r*_ncu_full*summary.json") if "train" not in f.name]
+    for f in sorted(files, reverse=True):
         try:
             launches = json.loads(f.read_text())["launches"]
         except Exception:

@@ -213,12 +213,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float* lse_s = vec_smem + stage * 256;
       const float* dl_s = lse_s + 128;
       const int col0 = i * 128;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t sr[32], dr[32];
-        B2F_TMEM_LD_X32(t_s + c0, sr);
-        B2F_TMEM_LD_X32(t_dp + c0, dr);
+      // A warp reads TMEM at ~40 B/clk and its loads do not overlap each other (scripts/debug/ldtm_bw.cu): the two
+      // 32-column loads of chunk c + 1 are issued before the (MUFU-bound) arithmetic of chunk c, two register sets.
+      uint32_t sr[2][32], dr[2][32];
+      B2F_TMEM_LD_X32(t_s, sr[0]);
+      B2F_TMEM_LD_X32(t_dp, dr[0]);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const int c0 = ch * 32;
+        uint32_t* sc = sr[ch & 1];
+        uint32_t* dc = dr[ch & 1];
         tmem_wait_ld();
+        if (ch < 3) {
+          B2F_TMEM_LD_X32(t_s + c0 + 32, sr[(ch + 1) & 1]);
+          B2F_TMEM_LD_X32(t_dp + c0 + 32, dr[(ch + 1) & 1]);
+        }
+        B2F_TIE16(sc);       // after the loads of the next chunk: the arithmetic below cannot be scheduled above them
+        B2F_TIE16(sc + 16);
+        B2F_TIE16(dc);
+        B2F_TIE16(dc + 16);
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -232,20 +245,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             l0 = l1 = my_lse;
             d0 = d1 = my_delta;
           }
-          float p0 = ex2(fmaf(__uint_as_float(sr[j]), p.scale_log2, -l0));
-          float p1 = ex2(fmaf(__uint_as_float(sr[j + 1]), p.scale_log2, -l1));
+          float p0 = ex2(fmaf(__uint_as_float(sc[j]), p.scale_log2, -l0));
+          float p1 = ex2(fmaf(__uint_as_float(sc[j + 1]), p.scale_log2, -l1));
           if (MODE == 0) {
             if (!row_ok) p0 = p1 = 0.f;                       // K/V rows beyond the sequence (zero-filled tiles)
           } else {
             if (col0 + c0 + j >= p.S) p0 = 0.f;               // K/V columns beyond the sequence
             if (col0 + c0 + j + 1 >= p.S) p1 = 0.f;
           }
-          const float s0 = p0 * (__uint_as_float(dr[j]) - d0);
-          const float s1 = p1 * (__uint_as_float(dr[j + 1]) - d1);
+          const float s0 = p0 * (__uint_as_float(dc[j]) - d0);
+          const float s1 = p1 * (__uint_as_float(dc[j + 1]) - d1);
           pk[j >> 1] = pack_bf16x2(p0, p1);
           dk[j >> 1] = pack_bf16x2(s0, s1);
         }
-        // bf16 pairs over the fp32 columns already consumed: columns [c0/2, c0/2 + 16) <= c0 + 32
+        // bf16 pairs over the fp32 columns already consumed: columns [c0/2, c0/2 + 16) end at or before c0 + 32, the first
+        // column of the chunk in flight
         if (MODE == 0) B2F_TMEM_ST_X16(t_s + (c0 >> 1), pk);
         B2F_TMEM_ST_X16(t_dp + (c0 >> 1), dk);
       }

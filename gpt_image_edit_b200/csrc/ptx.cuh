@@ -317,6 +317,14 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+// The registers a tcgen05.ld wrote become usable only after tcgen05.wait::ld; nothing else orders the two for the
+// compiler, so when loads are kept in flight across other code, pass their registers through an empty volatile asm placed
+// after the wait (volatile asms keep their order).
+#define B2F_TIE16(r)                                                                                                  \
+  asm volatile("" : "+r"((r)[0]), "+r"((r)[1]), "+r"((r)[2]), "+r"((r)[3]), "+r"((r)[4]), "+r"((r)[5]), "+r"((r)[6]), \
+               "+r"((r)[7]), "+r"((r)[8]), "+r"((r)[9]), "+r"((r)[10]), "+r"((r)[11]), "+r"((r)[12]), "+r"((r)[13]),  \
+               "+r"((r)[14]), "+r"((r)[15]))
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

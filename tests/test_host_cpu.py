@@ -338,3 +338,22 @@ def test_mixed_size_batches_match_the_reference_statements():
         err2 = (c["model_pred"].float() - c["target"].float()) ** 2
         loss = (scale * wt * err2).mean()
         assert abs(float(loss) - float(c["loss"])) <= 2e-6 * abs(float(c["loss"])), (c["name"], float(loss), float(c["loss"]))
+
+
+def test_synthetic_dataset_collates_mixed_target_sizes_as_lists():
+    """Targets of one size are stacked, targets of different sizes stay lists of [1, 3, H, W] / [1, 1, h, w] (what the
+    reference's loop branches on, train_denoiser.py:907, 1120); the source image and the VLM inputs are stacked either way."""
+    import torch
+    from univa.training.synthetic_data import SyntheticEditDataset, collate
+
+    ds = SyntheticEditDataset(64, 64, length=4, seed=3, target_sizes=[[64, 64], [48, 80]])
+    a, b = ds[0], ds[1]
+    assert a["generated_image"].shape == (3, 64, 64) and b["generated_image"].shape == (3, 48, 80)
+    assert b["weights"].shape == (1, 6, 10) and b["ref_pixel_values"].shape == (3, 64, 64)
+    assert torch.equal(ds[1]["generated_image"], b["generated_image"])            # a sample is a function of its index
+    mixed = collate([a, b])
+    assert isinstance(mixed["generated_image"], list) and [tuple(t.shape) for t in mixed["generated_image"]] == [(1, 3, 64, 64), (1, 3, 48, 80)]
+    assert [tuple(t.shape) for t in mixed["weights"]] == [(1, 1, 8, 8), (1, 1, 6, 10)]
+    assert mixed["ref_pixel_values"].shape == (2, 3, 64, 64) and mixed["input_ids"].shape[0] == 2
+    same = collate([ds[0], ds[2]])
+    assert same["generated_image"].shape == (2, 3, 64, 64) and same["weights"].shape == (2, 1, 8, 8)
