@@ -492,7 +492,7 @@ class Stage2Trainer:
                                                       generator=self.gen, device=device)
             n = self.sched.config["num_train_timesteps"]
             idx = (u * n).long().clamp_(max=n - 1)
-            sig = torch.linspace(1.0, 1.0 / n, n, device=device)      # FlowMatchEulerDiscreteScheduler's training table
+            sig = torch.linspace(1, n, n, device=device).flip(0) / n   # FlowMatchEulerDiscreteScheduler's table: (N..1) / N
             if not self.sched.config.get("use_dynamic_shifting", True):   # FLUX: dynamic shifting, table left unshifted
                 shift = self.sched.config.get("shift", 1.0)
                 sig = shift * sig / (1 + (shift - 1) * sig)

@@ -357,3 +357,30 @@ def test_synthetic_dataset_collates_mixed_target_sizes_as_lists():
     assert mixed["ref_pixel_values"].shape == (2, 3, 64, 64) and mixed["input_ids"].shape[0] == 2
     same = collate([ds[0], ds[2]])
     assert same["generated_image"].shape == (2, 3, 64, 64) and same["weights"].shape == (2, 1, 8, 8)
+
+
+def test_sigma_sampling_matches_the_reference_statements():
+    """Stage2Trainer.sample_sigmas + the flow-matching noising against tests/golden/sigma_sampling_ref.pt: the reference's
+    own statements (train_denoiser.py:935-995 and get_sigmas :779-788) executed on the CPU with the same seed — both the
+    continuous branch (logit-normal sigmas with FLUX's resolution-dependent shift) and the discrete one."""
+    from pathlib import Path
+    from types import SimpleNamespace
+
+    import torch
+    from gpt_image_edit_b200.training import Stage2Trainer
+
+    ref = torch.load(Path(__file__).parent / "golden" / "sigma_sampling_ref.pt", weights_only=False)
+    assert len(ref["cases"]) == 5
+    for c in ref["cases"]:
+        gen = torch.Generator().manual_seed(c["seed"])        # the stream torch.manual_seed(seed) gives the global generator
+        x = c["model_input"]
+        noise = torch.randn(x.shape, generator=gen, dtype=x.dtype)
+        assert torch.equal(noise, c["noise"]), c["name"]
+        me = SimpleNamespace(tc=SimpleNamespace(discrete_timestep=c["discrete"], weighting_scheme=c["scheme"], logit_mean=0.0,
+                                                logit_std=1.0, mode_scale=1.29),
+                             sched=SimpleNamespace(config=c["sched"]), gen=gen)
+        sigmas, timesteps = Stage2Trainer.sample_sigmas(me, x.shape[0], tuple(x.shape[-2:]), "cpu")
+        assert torch.equal(sigmas.view(-1), c["sigmas"].view(-1)), (c["name"], sigmas, c["sigmas"].view(-1))
+        assert torch.allclose(timesteps.view(-1), c["timesteps"].view(-1).float(), rtol=1e-6, atol=0), c["name"]
+        s4 = sigmas.view(-1, 1, 1, 1)
+        assert torch.equal((1.0 - s4) * x + s4 * noise, c["noisy"]), c["name"]
