@@ -460,21 +460,26 @@ class Stage2Trainer:
             self.opt.reduce_bucket(bucket)
 
     def lr_at(self, step: int) -> float:
-        """diffusers get_scheduler("constant" | "constant_with_warmup" | "linear" | "cosine") (:604-611)."""
+        """The learning rate of optimizer step `step` (0-based) under diffusers' get_scheduler("constant" |
+        "constant_with_warmup" | "linear" | "cosine") as the reference builds it (:707-716): warm-up and total steps are both
+        multiplied by the process count there because accelerate steps the scheduler once per process, so in optimizer steps
+        the multiplier is step / warmup during the warm-up (0 for the very first update, as LambdaLR gives) and the named
+        decay over max_train_steps after it."""
         import math
         tc = self.tc
-        base, warm, total = tc.learning_rate, tc.lr_warmup_steps, max(tc.max_train_steps or 1, 1)
+        base, warm, total = tc.learning_rate, int(tc.lr_warmup_steps or 0), max(tc.max_train_steps or 1, 1)
         name = tc.lr_scheduler
         if name == "constant":
             return base
-        w = min(1.0, (step + 1) / warm) if warm > 0 else 1.0
-        if name == "constant_with_warmup" or step < warm:
-            return base * w
+        if step < warm:
+            return base * step / max(1, warm)
+        if name == "constant_with_warmup":
+            return base
         prog = (step - warm) / max(1, total - warm)
         if name == "linear":
             return base * max(0.0, 1.0 - prog)
         if name == "cosine":
-            return base * max(0.0, 0.5 * (1.0 + math.cos(math.pi * tc.lr_num_cycles * 2.0 * prog)))
+            return base * max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(tc.lr_num_cycles) * 2.0 * prog)))
         raise _lib.B2FError(f"lr_scheduler={name!r} is not built")
 
     @torch.no_grad()

@@ -384,3 +384,42 @@ def test_sigma_sampling_matches_the_reference_statements():
         assert torch.allclose(timesteps.view(-1), c["timesteps"].view(-1).float(), rtol=1e-6, atol=0), c["name"]
         s4 = sigmas.view(-1, 1, 1, 1)
         assert torch.equal((1.0 - s4) * x + s4 * noise, c["noisy"]), c["name"]
+
+
+@pytest.mark.parametrize("name", ["constant", "constant_with_warmup", "linear", "cosine"])
+def test_lr_schedule_follows_diffusers_get_scheduler(name):
+    """Stage2Trainer.lr_at against the LambdaLR multipliers of diffusers.optimization.get_scheduler (third party, absent
+    here: its published lambdas are restated below) driven the way the reference drives it (train_denoiser.py:707-716:
+    warm-up and total steps x num_processes, one scheduler.step() per process and optimizer step)."""
+    import math
+    from types import SimpleNamespace
+
+    import torch
+    from gpt_image_edit_b200.training import Stage2Trainer
+
+    warm, total, procs, base, cycles = 5, 40, 8, 3e-4, 0.5
+    W, T = warm * procs, total * procs
+
+    def lam(k):                     # k = scheduler steps taken so far
+        if name == "constant":
+            return 1.0
+        if k < W:
+            return k / max(1, W)
+        if name == "constant_with_warmup":
+            return 1.0
+        if name == "linear":
+            return max(0.0, (T - k) / max(1, T - W))
+        prog = (k - W) / max(1, T - W)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * cycles * 2.0 * prog)))
+
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=base)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lam)
+    me = SimpleNamespace(tc=SimpleNamespace(learning_rate=base, lr_warmup_steps=warm, max_train_steps=total, lr_scheduler=name,
+                                            lr_num_cycles=cycles))
+    for step in range(total):
+        want = opt.param_groups[0]["lr"]            # the rate optimizer.step() number `step` runs with
+        got = Stage2Trainer.lr_at(me, step)
+        assert abs(got - want) <= 1e-12 + 1e-9 * abs(want), (name, step, got, want)
+        opt.step()
+        for _ in range(procs):                      # accelerate's scheduler wrapper: one step per process
+            sched.step()
