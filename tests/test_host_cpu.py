@@ -423,3 +423,41 @@ def test_lr_schedule_follows_diffusers_get_scheduler(name):
         opt.step()
         for _ in range(procs):                      # accelerate's scheduler wrapper: one step per process
             sched.step()
+
+
+def test_training_config_schema_matches_the_reference_dataclasses():
+    """univa/training/configuration_denoise.py against tests/golden/config_schema_ref.json (the reference's own module,
+    imported by make_config_golden.py): every reference field exists here with the same default; what this repo adds is
+    listed; the reference's stage-2 yaml loads field by field, its stage-1 yaml (keys outside its own schema) is rejected."""
+    import dataclasses
+    import json
+    from pathlib import Path
+
+    from univa.training import configuration_denoise as C
+
+    ref = json.loads((Path(__file__).parent / "golden" / "config_schema_ref.json").read_text())
+    additions = {"TrainingConfig": set(), "DatasetConfig": {"synthetic_len", "synthetic_target_sizes"},
+                 "ModelConfig": {"synthetic", "small"}}
+    for cls, fields in ref["classes"].items():
+        ours = {f.name: f for f in dataclasses.fields(getattr(C, cls))}
+        assert set(fields) <= set(ours), (cls, sorted(set(fields) - set(ours)))
+        assert set(ours) - set(fields) <= additions[cls], (cls, sorted(set(ours) - set(fields)))
+        for name, rf in fields.items():
+            if rf["has_default"]:
+                assert ours[name].default == rf["default"], (cls, name, ours[name].default, rf["default"])
+    for yname, rec in ref["yamls"].items():
+        raw = {sec: dict(v["values"]) for sec, v in rec.items()}
+        unknown = [k for v in rec.values() for k in v["unknown"]]
+        if unknown:
+            # the values fixture keeps scalars only: put the unknown keys back so the loader sees them
+            raw["model_config"].update({k: None for k in rec["model_config"]["unknown"]})
+            with pytest.raises(Exception):
+                C.from_mapping(raw)
+        else:
+            conf = C.from_mapping(raw)
+            for sec, v in rec.items():
+                for k, val in v["values"].items():
+                    got = getattr(getattr(conf, sec), k)
+                    if isinstance(val, str) and isinstance(got, (int, float)) and not isinstance(got, bool):
+                        val = float(val)            # PyYAML reads `1e-8` as a string; the typed schema makes it a float
+                    assert got == val or (isinstance(val, (int, float)) and float(got) == float(val)), (yname, sec, k, got, val)
