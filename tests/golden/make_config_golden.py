@@ -1,5 +1,5 @@
 """Generates tests/golden/config_schema_ref.json by IMPORTING the reference's own univa/training/configuration_denoise.py
-(plain dataclasses, no third-party imports) and recording, per config class, every field's name, annotation and default;
+and univa/eval/configuration_eval.py (plain dataclasses, no third-party imports) and recording, per config class, every field's name, annotation and default;
 plus, for each stage yaml the reference ships under scripts/denoiser/, its key set per section and whether every key is a
 field of the schema (OmegaConf's structured merge rejects unknown keys, and so does this repo's loader).
 Run here (needs /root/reference):  python tests/golden/make_config_golden.py"""
@@ -25,6 +25,12 @@ def main():
             fields[f.name] = {"type": str(f.type).replace("typing.", ""), "default": default,
                               "has_default": f.default is not dataclasses.MISSING}
         out["classes"][cls] = fields
+    spec2 = importlib.util.spec_from_file_location("ref_configuration_eval", REF / "univa/eval/configuration_eval.py")
+    mod2 = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(mod2)
+    out["classes"]["EvalConfig"] = {
+        f.name: {"type": str(f.type).replace("typing.", ""), "default": None if f.default is dataclasses.MISSING else f.default,
+                 "has_default": f.default is not dataclasses.MISSING} for f in dataclasses.fields(mod2.EvalConfig)}
     sections = {"training_config": "TrainingConfig", "dataset_config": "DatasetConfig", "model_config": "ModelConfig"}
     for y in sorted((REF / "scripts/denoiser").glob("*.yaml")):
         raw = yaml.safe_load(y.read_text())

@@ -438,13 +438,18 @@ def test_training_config_schema_matches_the_reference_dataclasses():
     ref = json.loads((Path(__file__).parent / "golden" / "config_schema_ref.json").read_text())
     additions = {"TrainingConfig": set(), "DatasetConfig": {"synthetic_len", "synthetic_target_sizes"},
                  "ModelConfig": {"synthetic", "small"}}
+    from univa.eval import configuration_eval as E
+    additions["EvalConfig"] = {"synthetic", "small"}
     for cls, fields in ref["classes"].items():
-        ours = {f.name: f for f in dataclasses.fields(getattr(C, cls))}
+        ours = {f.name: f for f in dataclasses.fields(getattr(E if cls == "EvalConfig" else C, cls))}
         assert set(fields) <= set(ours), (cls, sorted(set(fields) - set(ours)))
         assert set(ours) - set(fields) <= additions[cls], (cls, sorted(set(ours) - set(fields)))
         for name, rf in fields.items():
             if rf["has_default"]:
                 assert ours[name].default == rf["default"], (cls, name, ours[name].default, rf["default"])
+    with pytest.raises(KeyError):
+        E.EvalConfig.from_mapping({"num_inference_step": 28})          # a typo is an error, as under OmegaConf
+    assert E.EvalConfig.from_mapping({"guidance_scale": 4, "height": 512}).guidance_scale == 4.0
     for yname, rec in ref["yamls"].items():
         raw = {sec: dict(v["values"]) for sec, v in rec.items()}
         unknown = [k for v in rec.values() for k in v["unknown"]]
