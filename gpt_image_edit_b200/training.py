@@ -373,6 +373,22 @@ def pad_x_and_mask(xs, masks=None, max_h=None, max_w=None):
     return x, torch.cat([pad(m[:, :1]) for m in masks], dim=0)
 
 
+def pack_training_latents(pipe, noisy, cond, device, dtype):
+    """The transformer's token inputs for one training micro-batch (train_denoiser.py:996-1056): the noised target latents
+    [B, C, h, w] packed into 2x2 patches, followed — when a context image is given — by the packed VAE latents of the
+    context (`prepare_latents` encodes it and returns it PACKED, the target comes back unpacked and is packed here), and
+    the position ids of both (context ids carry 1 in their first coordinate).  Returns (tokens [B, S, 4C], ids [S, 3])."""
+    B, C, h, w = noisy.shape
+    vsf = pipe.vae_scale_factor
+    if cond is not None:
+        latents, image_latents, ids_t, ids_c = pipe.prepare_latents(cond, B, C, h * vsf, w * vsf, dtype, device, None, noisy)
+        packed_t = pipe._pack_latents(latents, B, C, h, w)
+        if image_latents is None:
+            return packed_t, ids_t
+        return torch.cat([packed_t, image_latents], dim=1), torch.cat([ids_t, ids_c], dim=0)
+    return pipe._pack_latents(noisy.to(dtype), B, C, h, w), pipe._prepare_latent_image_ids(B, h // 2, w // 2, device, dtype)
+
+
 def loss_weights(weighting, B, C, h, w, area_weights=None, weight_mask=None, unpad_sizes=None):
     """The element weights of the flow-matching loss and the factor that turns their weighted MEAN over [B, C, h, w] into
     the reference's loss (train_denoiser.py:1117-1165):
@@ -542,16 +558,7 @@ class Stage2Trainer:
         sigmas, timesteps = self.sample_sigmas(B, (h, w), dev)
         s4 = sigmas.view(B, 1, 1, 1)
         noisy = (1.0 - s4) * model_input + s4 * noise                                       # :995
-        vsf = pipe.vae_scale_factor
-        if cond is not None:
-            latents, image_latents, ids_t, ids_c = pipe.prepare_latents(cond, B, C, h * vsf, w * vsf, torch.bfloat16, dev,
-                                                                        None, noisy)
-            packed_t = pipe._pack_latents(latents, B, C, h, w)
-            packed = torch.cat([packed_t, image_latents], dim=1)
-            img_ids = torch.cat([ids_t, ids_c], dim=0)
-        else:
-            packed = pipe._pack_latents(noisy.to(torch.bfloat16), B, C, h, w)
-            img_ids = pipe._prepare_latent_image_ids(B, h // 2, w // 2, dev, torch.bfloat16)
+        packed, img_ids = pack_training_latents(pipe, noisy, cond, dev, torch.bfloat16)
         S_tgt = (h // 2) * (w // 2)
         guidance = torch.full((B,), float(mc.guidance_scale), device=dev)
         if mc.vlm_residual_image_factor:

@@ -466,3 +466,40 @@ def test_training_config_schema_matches_the_reference_dataclasses():
                     if isinstance(val, str) and isinstance(got, (int, float)) and not isinstance(got, bool):
                         val = float(val)            # PyYAML reads `1e-8` as a string; the typed schema makes it a float
                     assert got == val or (isinstance(val, (int, float)) and float(got) == float(val)), (yname, sec, k, got, val)
+
+
+def test_training_token_inputs_match_the_reference_statements():
+    """training.pack_training_latents over the product pipeline's helpers against tests/golden/train_pack_ref.pt: the
+    reference's own statements (train_denoiser.py:998-1056) run with the reference's own FluxKontextPipeline helpers and the
+    same stub VAE — tokens and position ids of [noised target ‖ context], a context of another size, no context."""
+    import sys
+    from pathlib import Path
+    from types import SimpleNamespace
+
+    import torch
+
+    sys.path.insert(0, str(Path(__file__).parent / "golden"))
+    from gpt_image_edit_b200.pipeline import FluxKontextPipeline
+    from gpt_image_edit_b200.training import pack_training_latents
+
+    class StubVae:      # the same fixed arithmetic as tests/golden/make_train_pack_golden.py::StubVae
+        dtype = torch.float32
+
+        def __init__(self):
+            self.config = SimpleNamespace(block_out_channels=(1, 1, 1, 1), latent_channels=16, scaling_factor=0.3611,
+                                          shift_factor=0.1159)
+
+        def encode(self, x):
+            z = torch.nn.functional.avg_pool2d(x.float(), 8)
+            ch = torch.arange(16, dtype=torch.float32).view(1, 16, 1, 1)
+            z = z[:, :1] * (1 + 0.1 * ch) + z[:, 1:2] * 0.01 * ch + z[:, 2:3]
+            return SimpleNamespace(latent_dist=SimpleNamespace(mode=lambda: z, sample=lambda generator=None: z))
+
+    pipe = FluxKontextPipeline(transformer=SimpleNamespace(device=torch.device("cpu")), vae=StubVae())
+    assert pipe.vae_scale_factor == 8
+    ref = torch.load(Path(__file__).parent / "golden" / "train_pack_ref.pt", weights_only=False)
+    assert [c["name"] for c in ref["cases"]] == ["context_same_size", "context_other_size", "no_context"]
+    for c in ref["cases"]:
+        tokens, ids = pack_training_latents(pipe, c["noisy"], c["cond"], torch.device("cpu"), torch.float32)
+        assert torch.equal(tokens, c["tokens"]), c["name"]
+        assert torch.equal(ids.float(), c["ids"].float()), c["name"]
