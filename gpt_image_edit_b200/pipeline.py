@@ -50,45 +50,120 @@ class FluxPipelineOutput(SimpleNamespace):
     pass
 
 
+def randn_tensor(shape, generator=None, device=None, dtype=None):
+    """diffusers.utils.torch_utils.randn_tensor as the reference calls it (flux_pipeline.py:702) [dep-spec]: a CPU
+    generator draws on the CPU and the result is moved, a CUDA generator cannot serve a CPU tensor, a list of generators
+    (a list of one counts as that one) draws one batch item each."""
+    shape = tuple(shape)
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    rand_device = device
+    if generator is not None:
+        gen_type = (generator[0] if isinstance(generator, list) else generator).device.type
+        if gen_type != device.type and gen_type == "cpu":
+            rand_device = torch.device("cpu")
+        elif gen_type != device.type and gen_type == "cuda":
+            raise ValueError(f"Cannot generate a {device} tensor from a generator of type {gen_type}.")
+    if isinstance(generator, list) and len(generator) == 1:
+        generator = generator[0]
+    if isinstance(generator, list):
+        one = (1,) + shape[1:]
+        parts = [torch.randn(one, generator=generator[i], device=rand_device, dtype=dtype) for i in range(shape[0])]
+        return torch.cat(parts, dim=0).to(device)
+    return torch.randn(shape, generator=generator, device=rand_device, dtype=dtype).to(device)
+
+
 class VaeImageProcessor:
-    """The three behaviours of diffusers' VaeImageProcessor the reference reaches with tensor inputs
-    (SURVEY.md A.4): nearest resize, [-1,1] pass-through, postprocess to uint8/PIL."""
+    """diffusers' VaeImageProcessor as the reference pipeline configures and reaches it (`VaeImageProcessor(
+    vae_scale_factor=16)`, flux_pipeline.py:228: do_resize, lanczos, do_normalize) [dep-spec, SURVEY.md A.4]:
+    `get_default_height_width`, `resize`, `preprocess` for tensors, PIL images, arrays and lists of them, and
+    `postprocess` to "pt" / "np" / "pil"."""
 
     def __init__(self, vae_scale_factor: int = 16):
         self.vae_scale_factor = vae_scale_factor
 
     @staticmethod
-    def get_default_height_width(image):
-        return int(image.shape[-2]), int(image.shape[-1])
+    def _is_pil(x):
+        return hasattr(x, "resize") and hasattr(x, "height") and not isinstance(x, (torch.Tensor, np.ndarray))
 
-    @staticmethod
-    def resize(image: torch.Tensor, height: int, width: int) -> torch.Tensor:
-        if image.shape[-2] == height and image.shape[-1] == width:
-            return image
-        return torch.nn.functional.interpolate(image, size=(height, width))
+    def get_default_height_width(self, image, height=None, width=None):
+        """(height, width) of the input, floored to a multiple of vae_scale_factor (tensors are [.., H, W], arrays
+        [N, H, W, C])."""
+        if isinstance(image, list):
+            image = image[0]
+        if height is None:
+            height = image.height if self._is_pil(image) else (image.shape[2] if isinstance(image, torch.Tensor)
+                                                               else image.shape[1])
+        if width is None:
+            width = image.width if self._is_pil(image) else (image.shape[3] if isinstance(image, torch.Tensor)
+                                                             else image.shape[2])
+        f = self.vae_scale_factor
+        return int(height) - int(height) % f, int(width) - int(width) % f
 
-    @staticmethod
-    def preprocess(image: torch.Tensor, height=None, width=None) -> torch.Tensor:
-        if image.dim() == 3:
+    def resize(self, image, height: int, width: int):
+        """PIL: lanczos; tensor: nearest `interpolate`; array: through the tensor path; lists element-wise."""
+        if isinstance(image, list):
+            return [self.resize(i, height, width) for i in image]
+        if self._is_pil(image):
+            from PIL import Image
+            return image.resize((width, height), resample=Image.LANCZOS)
+        if isinstance(image, torch.Tensor):
+            if image.shape[-2] == height and image.shape[-1] == width:
+                return image                      # nearest interpolation to the same size is the identity
+            return torch.nn.functional.interpolate(image, size=(height, width))
+        t = torch.from_numpy(image.transpose(0, 3, 1, 2) if image.ndim == 4 else image[..., None].transpose(0, 3, 1, 2))
+        t = torch.nn.functional.interpolate(t, size=(height, width))
+        return t.cpu().permute(0, 2, 3, 1).float().numpy()
+
+    def preprocess(self, image, height=None, width=None) -> torch.Tensor:
+        """-> float tensor [N, 3, H, W] in [-1, 1].  PIL / arrays are scaled from [0, 255] / taken as [0, 1], resized to
+        (height, width) (default: their own size floored to the scale factor) and normalised; tensors are resized the
+        same way and normalised unless they already hold negative values (then they pass as [-1, 1])."""
+        if isinstance(image, torch.Tensor) and image.dim() == 3:
             image = image[None]
-        if image.min() >= 0:  # [0,1] inputs are normalised; [-1,1] inputs pass through
-            image = 2.0 * image - 1.0
-        return image
+        if isinstance(image, np.ndarray) and image.ndim == 3:
+            image = image[None]
+        if self._is_pil(image) or isinstance(image, (torch.Tensor, np.ndarray)):
+            image = [image]
+        if not isinstance(image, list) or not image:
+            raise ValueError("image must be a PIL image, an array, a tensor or a non-empty list of one of them")
+        if self._is_pil(image[0]):
+            h, w = self.get_default_height_width(image[0], height, width)
+            image = [self.resize(i, h, w) for i in image]
+            arr = np.stack([np.array(i).astype(np.float32) / 255.0 for i in image], axis=0)
+            if arr.ndim == 3:
+                arr = arr[..., None]
+            x = torch.from_numpy(arr.transpose(0, 3, 1, 2))
+        elif isinstance(image[0], np.ndarray):
+            arr = np.concatenate(image, axis=0) if image[0].ndim == 4 else np.stack(image, axis=0)
+            if arr.ndim == 3:
+                arr = arr[..., None]
+            x = torch.from_numpy(arr.transpose(0, 3, 1, 2))
+            h, w = self.get_default_height_width(x, height, width)
+            x = torch.nn.functional.interpolate(x, size=(h, w))
+        else:
+            x = torch.cat(image, dim=0) if image[0].dim() == 4 else torch.stack(image, dim=0)
+            h, w = self.get_default_height_width(x, height, width)
+            x = self.resize(x, h, w)
+        if x.min() < 0:              # already [-1, 1] (diffusers warns and skips the normalisation)
+            return x
+        return 2.0 * x - 1.0
 
     @staticmethod
     def postprocess(image: torch.Tensor, output_type: str = "pil"):
-        if output_type == "latent" or output_type == "pt_raw":
+        if output_type == "latent":
             return image
-        img = (image.float() / 2 + 0.5).clamp(0, 1)
+        if output_type not in ("pt", "np", "pil"):
+            raise ValueError(f"output_type={output_type!r}: one of 'pil', 'np', 'pt', 'latent'")
+        img = (image.float() / 2 + 0.5).clamp(0, 1)      # fp32 (diffusers denormalises in the VAE's dtype)
         if output_type == "pt":
             return img
-        arr = img.permute(0, 2, 3, 1).cpu().numpy()
+        arr = img.cpu().permute(0, 2, 3, 1).numpy()
         if output_type == "np":
             return arr
         from PIL import Image
 
         arr8 = (arr * 255).round().astype("uint8")
-        return [Image.fromarray(a) for a in arr8]
+        return [Image.fromarray(a.squeeze(-1), mode="L") if a.shape[-1] == 1 else Image.fromarray(a) for a in arr8]
 
 
 class FluxKontextPipeline:
@@ -99,13 +174,39 @@ class FluxKontextPipeline:
         self.scheduler = scheduler
         self.text_encoder, self.tokenizer = text_encoder, tokenizer
         self.text_encoder_2, self.tokenizer_2 = text_encoder_2, tokenizer_2
+        self.image_encoder, self.feature_extractor = image_encoder, feature_extractor
         boc = getattr(getattr(vae, "config", None), "block_out_channels", (128, 256, 512, 512))
         self.vae_scale_factor = 2 ** (len(boc) - 1)
         self.latent_channels = getattr(getattr(vae, "config", None), "latent_channels", 16)
         self.image_processor = VaeImageProcessor(vae_scale_factor=self.vae_scale_factor * 2)
+        self.tokenizer_max_length = getattr(tokenizer, "model_max_length", 77) if tokenizer is not None else 77
         self.default_sample_size = 128
         self._execution_device = getattr(transformer, "device", torch.device("cuda"))
         self._interrupt = False
+        self._guidance_scale = None
+        self._joint_attention_kwargs = None
+        self._num_timesteps = 0
+        self._current_timestep = None
+
+    # read-only views of the running call, as the reference exposes them to step callbacks (flux_pipeline.py:710-728)
+    guidance_scale = property(lambda self: self._guidance_scale)
+    joint_attention_kwargs = property(lambda self: self._joint_attention_kwargs)
+    num_timesteps = property(lambda self: self._num_timesteps)
+    current_timestep = property(lambda self: self._current_timestep)
+    interrupt = property(lambda self: self._interrupt)
+
+    # VAE memory options (reference :615-646) are forwarded to the VAE object, which must offer them
+    def enable_vae_slicing(self):
+        self.vae.enable_slicing()
+
+    def disable_vae_slicing(self):
+        self.vae.disable_slicing()
+
+    def enable_vae_tiling(self):
+        self.vae.enable_tiling()
+
+    def disable_vae_tiling(self):
+        self.vae.disable_tiling()
 
     @classmethod
     def from_pretrained(cls, flux_path, transformer=None, torch_dtype=torch.bfloat16, **kw):
@@ -121,8 +222,6 @@ class FluxKontextPipeline:
         clip, tok, t5, tok2 = load_text_encoders(flux_path, device=dev)
         return cls(transformer=transformer, vae=vae, scheduler=scheduler, text_encoder=clip, tokenizer=tok,
                    text_encoder_2=t5, tokenizer_2=tok2)
-
-    tokenizer_max_length = 77
 
     def encode_prompt(self, prompt, prompt_2=None, device=None, num_images_per_prompt: int = 1, prompt_embeds=None,
                       pooled_prompt_embeds=None, max_sequence_length: int = 512, lora_scale=None):
@@ -218,7 +317,13 @@ class FluxKontextPipeline:
         return x.reshape(batch_size, channels // 4, height, width)
 
     def _encode_vae_image(self, image, generator=None):
-        z = self.vae.encode(image if image.dtype == torch.uint8 else image.to(self.vae.dtype)).latent_dist.mode()
+        """Mode of the VAE posterior, shifted and scaled (reference :600-613; with a list of generators the reference
+        encodes one batch item per call, kept so that the kernels see the same shapes)."""
+        image = image if image.dtype == torch.uint8 else image.to(self.vae.dtype)
+        if isinstance(generator, list):
+            z = torch.cat([self.vae.encode(image[i:i + 1]).latent_dist.mode() for i in range(image.shape[0])], dim=0)
+        else:
+            z = self.vae.encode(image).latent_dist.mode()
         return (z - self.vae.config.shift_factor) * self.vae.config.scaling_factor
 
     def prepare_latents(self, image, batch_size, num_channels_latents, height, width, dtype, device, generator=None,
@@ -247,7 +352,7 @@ class FluxKontextPipeline:
             image_ids[..., 0] = 1  # context image index
         latent_ids = self._prepare_latent_image_ids(batch_size, height // 2, width // 2, device, dtype)
         if latents is None:
-            noise = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+            noise = randn_tensor(shape, generator=generator, device=device, dtype=dtype)
             latents = self._pack_latents(noise, batch_size, num_channels_latents, height, width)
         else:
             # a private copy: the Euler kernel updates the latents in place, the caller's tensor must not change
@@ -266,7 +371,10 @@ class FluxKontextPipeline:
                  max_sequence_length: int = 512, max_area: int = 1024 ** 2, _auto_resize: bool = True,
                  ip_adapter_image=None, ip_adapter_image_embeds=None, negative_ip_adapter_image=None,
                  negative_ip_adapter_image_embeds=None):
-        self._interrupt = False                    # reference :922 resets the flag at the start of every call
+        self._interrupt = False                    # reference :919-922: per-call state
+        self._guidance_scale = guidance_scale
+        self._joint_attention_kwargs = joint_attention_kwargs
+        self._current_timestep = None
         if any(a is not None for a in (ip_adapter_image, ip_adapter_image_embeds, negative_ip_adapter_image,
                                        negative_ip_adapter_image_embeds)):
             # the reference forwards these to an image encoder + IP-adapter attention processors (:441-488, 1024-1050);
@@ -319,7 +427,7 @@ class FluxKontextPipeline:
             ih, iw = int(image.shape[1]), int(image.shape[2])
             if _auto_resize or ih % mult or iw % mult:
                 image = (((image.cpu().permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5).to(image.device)   # host chain of cli.py:99-116
-        if image is not None and image.dtype == torch.uint8:
+        if isinstance(image, torch.Tensor) and image.dtype == torch.uint8:
             pass
         elif image is not None and not (isinstance(image, torch.Tensor) and image.size(1) == self.latent_channels):
             ih, iw = self.image_processor.get_default_height_width(image)
@@ -360,6 +468,7 @@ class FluxKontextPipeline:
         for i, t in enumerate(timesteps):
             if self._interrupt:
                 continue
+            self._current_timestep = t
             x_in = latents if image_latents is None else torch.cat([latents, image_latents], dim=1)
             timestep = t.expand(B).to(latents.dtype)
             if hoist:
@@ -380,8 +489,12 @@ class FluxKontextPipeline:
                 noise_pred = neg_noise_pred + true_cfg_scale * (noise_pred - neg_noise_pred)
             latents = self.scheduler.step(noise_pred, t, latents, return_dict=False)[0]
             if callback_on_step_end is not None:
-                out = callback_on_step_end(self, i, t, {"latents": latents})
+                # the tensors named in callback_on_step_end_tensor_inputs, and what the callback may hand back (:1105-1112)
+                avail = {"latents": latents, "prompt_embeds": prompt_embeds}
+                out = callback_on_step_end(self, i, t, {k: avail[k] for k in callback_on_step_end_tensor_inputs})
                 latents = out.pop("latents", latents)
+                prompt_embeds = out.pop("prompt_embeds", prompt_embeds)
+        self._current_timestep = None
 
         if output_type == "latent":
             images = latents

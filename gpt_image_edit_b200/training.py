@@ -119,6 +119,11 @@ class _B2FMath:
         return T.cast(src.contiguous(), torch.float32)
 
     @staticmethod
+    def cast_to_bf16(src):
+        from . import train_ops as T
+        return T.cast(src.contiguous(), torch.bfloat16)
+
+    @staticmethod
     def sumsq(g, out, accumulate):
         from . import train_ops as T
         T.grad_sumsq(g, out=out, accumulate=accumulate)
@@ -249,12 +254,30 @@ class ShardedAdamW:
                 "buckets": [None if bk is None else {"p32": bk.p32, "m": bk.m, "v": bk.v} for bk in self.buckets]}
 
     def load_state_dict(self, sd):
-        if sd["world"] != self.world:
-            raise _lib.B2FError(f"optimizer state was partitioned over {sd['world']} ranks, this run has {self.world}")
+        """Restore a `state_dict()` of the same partitioning: step count, fp32 master slices and moments — and the bf16
+        weights the model computes with, which are the rounded masters of ALL ranks (each rank rounds its slice, the
+        slices are all-gathered and scattered into the model's storage, exactly as at the end of `step`).  What
+        `accelerator.load_state` does for the reference (train_denoiser.py:769: DeepSpeed reloads module + optimizer)."""
+        if sd["world"] != self.world or sd.get("rank", self.rank) != self.rank:
+            raise _lib.B2FError(f"optimizer state is rank {sd.get('rank')} of {sd['world']} ranks, this process is rank "
+                                f"{self.rank} of {self.world}")
+        if len(sd["buckets"]) != len(self.buckets):
+            raise _lib.B2FError(f"optimizer state has {len(sd['buckets'])} buckets, this run has {len(self.buckets)}")
+        for bk, s in zip(self.buckets, sd["buckets"]):
+            if (bk is None) != (s is None) or (bk is not None and s["p32"].numel() != bk.p32.numel()):
+                raise _lib.B2FError("optimizer state does not match this run's trainable set (bucket sizes differ)")
         self.step_count = sd["step"]
         for bk, s in zip(self.buckets, sd["buckets"]):
-            if bk is not None:
-                bk.p32.copy_(s["p32"]); bk.m.copy_(s["m"]); bk.v.copy_(s["v"])
+            if bk is None:
+                continue
+            bk.p32.copy_(s["p32"]); bk.m.copy_(s["m"]); bk.v.copy_(s["v"])
+            n = bk.size // self.world
+            lo = self.rank * n
+            bk.flat_p16[lo:lo + n].copy_(self.math.cast_to_bf16(bk.p32))
+            if self.world > 1:
+                dist.all_gather_into_tensor(bk.flat_p16, bk.flat_p16[lo:lo + n].clone(), group=self.group)
+            for p in bk.params:
+                p.storage.copy_(bk.flat_p16[p.offset:p.offset + p.storage.numel()].view(p.storage.shape))
 
 
 # ------------------------------------------------------------------------------------------------ forward / backward

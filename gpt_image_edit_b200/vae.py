@@ -86,6 +86,7 @@ class DiagonalGaussianDistribution:
     """diffusers' latent_dist over the moments the encoder produced (mean | logvar on dim 1)."""
 
     def __init__(self, moments: torch.Tensor):
+        self.parameters = moments
         self.mean, logvar = torch.chunk(moments, 2, dim=1)
         self.logvar = torch.clamp(logvar, -30.0, 20.0)
         self.std = torch.exp(0.5 * self.logvar)
@@ -94,7 +95,8 @@ class DiagonalGaussianDistribution:
         return self.mean
 
     def sample(self, generator=None):
-        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        from .pipeline import randn_tensor      # diffusers samples through randn_tensor (CPU generators allowed)
+        noise = randn_tensor(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
         return self.mean + self.std * noise
 
 
@@ -134,6 +136,31 @@ class B200AutoencoderKL(torch.nn.Module):
         for k, t in self._store.items():
             check(_lib.lib.b2f_vae_bind_weight(self._h, k.encode(), ptr(t), t.numel()), f"bind {k}")
         self._ws = None
+        self.use_slicing = False
+
+    # diffusers' AutoencoderKL memory options, reached through FluxKontextPipeline.enable_vae_slicing / _tiling
+    # (reference flux_pipeline.py:615-646).  Slicing runs one batch item per kernel sequence (same results: every
+    # normalisation of the VAE is per item) and bounds the workspace to one image.  Tiling changes the output (overlapping
+    # tiles are blended) to fit small memories; with 180 GB of HBM per GPU it is refused rather than approximated.
+    def enable_slicing(self):
+        self.use_slicing = True
+
+    def disable_slicing(self):
+        self.use_slicing = False
+
+    def enable_tiling(self, *a, **k):
+        raise _lib.B2FError("tiled VAE encode / decode is not built: a 1024x1024 decode needs < 2 GB of workspace here")
+
+    def disable_tiling(self):
+        pass
+
+    def _sliced(self, fn, x):
+        """fn over single-item views of x, results concatenated (use_slicing with a batch)."""
+        self.use_slicing = False
+        try:
+            return [fn(x[i:i + 1]) for i in range(x.shape[0])]
+        finally:
+            self.use_slicing = True
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -244,6 +271,10 @@ class B200AutoencoderKL(torch.nn.Module):
         if not x.is_cuda or x.dim() != 4 or x.dtype not in (torch.bfloat16, torch.float32, torch.uint8):
             raise _lib.B2FError("vae.encode: CUDA [N,3,H,W] bf16/fp32 tensor or uint8 [N,H,W,3] pixels required")
         x = x.contiguous()
+        if self.use_slicing and x.shape[0] > 1:
+            mom = torch.cat([d.latent_dist.parameters for d in self._sliced(self.encode, x)], dim=0)
+            dist = DiagonalGaussianDistribution(mom)
+            return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
         if x.dtype == torch.uint8:
             N, H, W, C = x.shape
             if C != self.config.in_channels:
@@ -263,6 +294,9 @@ class B200AutoencoderKL(torch.nn.Module):
         if not z.is_cuda or z.dim() != 4:
             raise _lib.B2FError("vae.decode: CUDA [N,C,h,w] tensor required")
         z = z.to(torch.bfloat16).contiguous()
+        if self.use_slicing and z.shape[0] > 1:
+            img = torch.cat([d.sample for d in self._sliced(self.decode, z)], dim=0)
+            return SimpleNamespace(sample=img) if return_dict else (img,)
         N, _, h, w = z.shape
         ws, n = self._workspace(N, 8 * h, 8 * w)
         img = torch.empty((N, self.config.out_channels, 8 * h, 8 * w), device=self._dev, dtype=torch.bfloat16)
@@ -276,6 +310,8 @@ class B200AutoencoderKL(torch.nn.Module):
         if not z.is_cuda or z.dim() != 4:
             raise _lib.B2FError("vae.decode_u8: CUDA [N,C,h,w] tensor required")
         z = z.to(torch.bfloat16).contiguous()
+        if self.use_slicing and z.shape[0] > 1:
+            return torch.cat(self._sliced(self.decode_u8, z), dim=0)
         N, _, h, w = z.shape
         ws, n = self._workspace(N, 8 * h, 8 * w)
         img = torch.empty((N, 8 * h, 8 * w, self.config.out_channels), device=self._dev, dtype=torch.uint8)

@@ -18,6 +18,10 @@ class TorchMath:
         return src.float().clone()
 
     @staticmethod
+    def cast_to_bf16(src):
+        return src.to(torch.bfloat16)
+
+    @staticmethod
     def sumsq(g, out, accumulate):
         s = g.double().pow(2).sum().float()
         out.copy_(out + s if accumulate else s.reshape(1))

@@ -503,3 +503,35 @@ def test_training_token_inputs_match_the_reference_statements():
         tokens, ids = pack_training_latents(pipe, c["noisy"], c["cond"], torch.device("cpu"), torch.float32)
         assert torch.equal(tokens, c["tokens"]), c["name"]
         assert torch.equal(ids.float(), c["ids"].float()), c["name"]
+
+
+def test_resume_resolution_and_checkpoint_pruning_match_the_reference_statements(tmp_path):
+    """train_denoiser.resolve_resume_checkpoint / prune_checkpoints against the outputs of the reference's own statements
+    (train_denoiser.py:348-374, 1195-1225; tests/golden/make_train_resume_golden.py) on the same directory trees."""
+    import json
+    import os
+    from pathlib import Path
+    from types import SimpleNamespace
+
+    import train_denoiser as td
+
+    fx = json.loads((Path(__file__).parent / "golden" / "train_resume_ref.json").read_text())
+    for i, c in enumerate(fx["resume"]):
+        out = tmp_path / f"r{i}"
+        for d in c["dirs"]:
+            (out / d).mkdir(parents=True)
+        said = []
+        tc = SimpleNamespace(resume_from_checkpoint=c["resume_from_checkpoint"], output_dir=str(out))
+        path, step = td.resolve_resume_checkpoint(tc, log=said.append)
+        assert (None if path is None else os.path.relpath(path, out)) == c["chosen"], c
+        assert step == c["initial_global_step"] and said == c["said"], c
+    with pytest.raises(FileNotFoundError):       # an explicit checkpoint that is not there: the reference dies in load_state
+        td.resolve_resume_checkpoint(SimpleNamespace(resume_from_checkpoint="checkpoint-7", output_dir=str(tmp_path / "r0")),
+                                     log=lambda *_: None)
+    for i, c in enumerate(fx["prune"]):
+        out = tmp_path / f"p{i}"
+        for d in c["dirs"]:
+            (out / d).mkdir(parents=True)
+        said = []
+        td.prune_checkpoints(out, c["limit"], log=said.append)
+        assert sorted(os.listdir(out)) == c["left"] and said == c["said"], c

@@ -7,6 +7,8 @@ rank-averaged gradients).  Reference: scripts/accelerate_configs/zero2.json, tra
 import os
 import socket
 
+import pytest
+
 import torch
 import torch.multiprocessing as mp
 
@@ -126,3 +128,67 @@ def test_trainable_set_names_follow_the_references_contract():
     comps = tr.get_trainable_params([0, 20], 19, True)
     assert comps[0] == "denoise_tower.denoiser.transformer_blocks.0.attn.norm_q"
     assert "denoise_tower.denoiser.single_transformer_blocks.1.norm.linear" in comps and len(comps) == 7 + 6
+
+
+def _resume_worker(rank, world, port, out_dir):
+    """3 steps straight through  vs  2 steps, state_dict -> a FRESH optimizer over the INITIAL weights, load, 1 more step."""
+    os.environ.update(WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("gloo")
+    from gpt_image_edit_b200.training import ShardedAdamW
+    from oracle.train_oracle import TorchMath
+
+    def run(opt, params, steps):
+        for step in steps:
+            for p, g in zip(params, _grads(rank, step)):
+                p.grad.copy_(g)
+            opt.reduce_all()
+            opt.step()
+
+    kw = dict(math=TorchMath, lr=HP["lr"], betas=HP["betas"], eps=HP["eps"], weight_decay=HP["weight_decay"],
+              max_grad_norm=HP["max_grad_norm"])
+    straight = _make()
+    run(ShardedAdamW(straight, **kw), straight, range(3))
+    first = _make()
+    opt = ShardedAdamW(first, **kw)
+    run(opt, first, range(2))
+    torch.save(opt.state_dict(), f"{out_dir}/opt{rank}.pt")
+    after_two = [p.storage.clone() for p in first]
+    resumed = _make()                                                # the weights a restarted process starts from
+    opt2 = ShardedAdamW(resumed, **kw)
+    opt2.load_state_dict(torch.load(f"{out_dir}/opt{rank}.pt"))
+    restored = all(torch.equal(a, p.storage) for a, p in zip(after_two, resumed))
+    run(opt2, resumed, [2])
+    same = all(torch.equal(a.storage, b.storage) for a, b in zip(straight, resumed))
+    torch.save(dict(restored=restored, same=same, steps=opt2.step_count), f"{out_dir}/res{rank}.pt")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_optimizer_state_restores_the_models_weights_and_continues_bit_exactly(tmp_path, world):
+    """Resume (train_denoiser.py:769 accelerator.load_state): loading a rank's optimizer partition must also bring back the
+    bf16 weights the model computes with — a restarted process holds the INITIAL weights — and the next step must equal the
+    uninterrupted run's."""
+    if world == 1:
+        _resume_worker(0, 1, 0, str(tmp_path))
+    else:
+        mp.spawn(_resume_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(tmp_path / f"res{r}.pt")
+        assert res["restored"] and res["same"] and res["steps"] == 3, res
+
+
+def test_optimizer_state_of_another_partitioning_is_refused():
+    from gpt_image_edit_b200 import _lib
+    from gpt_image_edit_b200.training import ShardedAdamW
+    from oracle.train_oracle import TorchMath
+
+    opt = ShardedAdamW(_make(), math=TorchMath)
+    sd = opt.state_dict()
+    with pytest.raises(_lib.B2FError):
+        opt.load_state_dict({**sd, "world": 2})
+    with pytest.raises(_lib.B2FError):
+        opt.load_state_dict({**sd, "buckets": sd["buckets"][:-1]})

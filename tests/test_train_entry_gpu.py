@@ -37,10 +37,16 @@ def test_train_denoiser_entry_steps_checkpoints_and_resumes(tmp_path, capsys):
     names = set(load_state_dict_from_dir(ck / "denoiser_trainable"))
     assert "transformer_blocks.0.attn.to_q.weight" in names and "single_transformer_blocks.0.norm.linear.bias" in names
     assert not any("ff.net" in n or "add_q_proj" in n for n in names)            # frozen tensors are not in the checkpoint
-    # resume: the optimizer partition and the step counter come back
-    conf2 = _conf(tmp_path, resume_from_checkpoint=str(ck), max_train_steps=3)
+    assert (ck / "random_states_0.pkl").exists()
+    # resume ("latest" = checkpoint-2): optimizer partition, the bf16 weights rounded from its masters, the step counter
+    # and the random streams come back; one more step reaches max_train_steps
+    conf2 = _conf(tmp_path, resume_from_checkpoint="latest", max_train_steps=3)
     t2 = td.main(conf2)
+    out2 = capsys.readouterr().out
+    assert "Resuming from checkpoint checkpoint-2" in out2 and out2.count("\nstep ") + out2.startswith("step ") == 1
     assert t2.global_step == 3 and t2.opt.step_count == 3
+    loss3 = float(out2.split("step 3  loss ")[1].split()[0])
+    assert loss3 == loss3 and 0 < loss3 < 100
 
 
 def test_gradient_accumulation_and_batch_two(tmp_path, capsys):

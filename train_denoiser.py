@@ -46,19 +46,74 @@ def build_models(conf, device):
     return model, pipe.vae, pipe, empty_pooled.to(torch.bfloat16)
 
 
+def resolve_resume_checkpoint(tc, log=print):
+    """(directory | None, global step it was written at) for `training_config.resume_from_checkpoint`, by the reference's
+    rule (train_denoiser.py:347-374): "latest" picks the `checkpoint-<step>` directory of `output_dir` with the largest
+    step; any other value contributes only its BASENAME, looked up under `output_dir` (missing: an error, as
+    accelerator.load_state raises there); "latest" with no checkpoint starts a fresh run and says so.  The step is parsed from the directory name.
+
+    One deliberate difference: the reference resets its step counter to 0 after parsing it (:764), so a resumed run counts
+    — and names its checkpoints — from 0 again while optimizer and LR schedule continue; here the counter continues from
+    the checkpoint's step, which is what `max_train_steps` and the checkpoint names mean."""
+    want = tc.resume_from_checkpoint
+    if not want:
+        return None, 0
+    out = Path(tc.output_dir)
+    if want != "latest":
+        name = os.path.basename(os.path.normpath(str(want)))
+    else:
+        dirs = sorted((d for d in (os.listdir(out) if out.is_dir() else []) if d.startswith("checkpoint")),
+                      key=lambda x: int(x.split("-")[1]))
+        name = dirs[-1] if dirs else None
+    if name is None:
+        log(f"Checkpoint '{want}' does not exist. Starting a new training run.")
+        return None, 0
+    log(f"Resuming from checkpoint {name}")
+    if not (out / name).is_dir():          # the reference fails at this point inside accelerator.load_state
+        raise FileNotFoundError(f"resume_from_checkpoint: {out / name} is not a directory")
+    return out / name, int(name.split("-")[1])
+
+
+def prune_checkpoints(output_dir, limit, log=print):
+    """Before a new checkpoint is written at most `limit - 1` may remain: the oldest `checkpoint-<step>` directories go
+    (train_denoiser.py:1195-1225).  Returns the removed names."""
+    if limit is None:
+        return []
+    out = Path(output_dir)
+    old = sorted((d for d in os.listdir(out) if d.startswith("checkpoint")), key=lambda x: int(x.split("-")[1]))
+    if len(old) < limit:
+        return []
+    removing = old[:len(old) - limit + 1]
+    log(f"{len(old)} checkpoints already exist, removing {len(removing)} checkpoints")
+    log(f"removing checkpoints: {', '.join(removing)}")
+    for d in removing:
+        shutil.rmtree(out / d)
+    return removing
+
+
+def load_checkpoint(path: Path, trainer, rank: int, device):
+    """accelerator.load_state (:769) for this engine: the rank's optimizer partition — which also restores the bf16
+    weights the model computes with (ShardedAdamW.load_state_dict) — and the rank's random streams."""
+    trainer.opt.load_state_dict(torch.load(path / f"optimizer_rank{rank}.pt", map_location=device))
+    rs = path / f"random_states_{rank}.pkl"
+    if rs.exists():
+        st = torch.load(rs, map_location="cpu", weights_only=False)
+        torch.set_rng_state(st["torch"])
+        if st.get("noise") is not None and getattr(trainer, "gen", None) is not None:
+            trainer.gen.set_state(st["noise"])
+
+
 def save_checkpoint(conf, trainer, model, step: int, rank: int, world: int):
     """checkpoint-{step}/: the trainable tensors under their diffusers names (safetensors, rank 0), denoise_projector.bin
-    (reference :1231-1236) and this rank's optimizer partition (ZeRO: one file per rank, :1229 accelerator.save_state)."""
+    (reference :1231-1236), this rank's optimizer partition and random streams (ZeRO: one file per rank, :1229
+    accelerator.save_state writes `random_states_<rank>.pkl` the same way)."""
     from gpt_image_edit_b200 import checkpoint as ck
 
     tc = conf.training_config
     out = Path(tc.output_dir)
     out.mkdir(parents=True, exist_ok=True)
-    if rank == 0 and tc.checkpoints_total_limit is not None:
-        old = sorted((d for d in os.listdir(out) if d.startswith("checkpoint")), key=lambda x: int(x.split("-")[1]))
-        if len(old) >= tc.checkpoints_total_limit:
-            for d in old[:len(old) - tc.checkpoints_total_limit + 1]:
-                shutil.rmtree(out / d)
+    if rank == 0:
+        prune_checkpoints(out, tc.checkpoints_total_limit)
     save = out / f"checkpoint-{step}"
     save.mkdir(parents=True, exist_ok=True)
     if rank == 0:
@@ -74,6 +129,9 @@ def save_checkpoint(conf, trainer, model, step: int, rank: int, world: int):
             torch.save(proj, save / "denoise_projector.bin")
         (save / "trainer_state.json").write_text(json.dumps({"global_step": step, "world_size": world}))
     torch.save(trainer.opt.state_dict(), save / f"optimizer_rank{rank}.pt")
+    gen = getattr(trainer, "gen", None)
+    torch.save({"torch": torch.get_rng_state(), "noise": None if gen is None else gen.get_state().cpu()},
+               save / f"random_states_{rank}.pkl")
     return save
 
 
@@ -103,11 +161,9 @@ def main(conf):
     if rank == 0:
         print(f"trainable tensors: {len(trainer.params)}  parameters: {n_train / 1e9:.3f} B  world: {world}  "
               f"ZeRO-2 buckets: {sum(b is not None for b in trainer.opt.buckets)}", flush=True)
-    start = 0
-    if tc.resume_from_checkpoint:
-        ck = Path(tc.resume_from_checkpoint)
-        trainer.opt.load_state_dict(torch.load(ck / f"optimizer_rank{rank}.pt", map_location=device))
-        start = json.loads((ck / "trainer_state.json").read_text())["global_step"]
+    ck, start = resolve_resume_checkpoint(tc, log=print if rank == 0 else (lambda *a: None))
+    if ck is not None:
+        load_checkpoint(ck, trainer, rank, device)
         trainer.global_step = start
     data = SyntheticEditDataset(dc.height, dc.width, dc.synthetic_len, seed=tc.seed + rank, target_sizes=dc.synthetic_target_sizes)
     loader = torch.utils.data.DataLoader(data, batch_size=dc.batch_size, collate_fn=collate, num_workers=0,
