@@ -129,6 +129,24 @@ def vision_rot_pos_ids(grid_thw, spatial_merge_size=2):
 
 
 # ------------------------------------------------------------------------------------------------ model
+def padding_spans(attention_mask):
+    """[(lo, hi)] per batch row: the run of ones of a 2-D attention mask (right- or left-padded prompts, as the
+    processor's `padding=True` produces them).  Holes inside a prompt are not a padding pattern and are refused."""
+    am = attention_mask.detach().to("cpu") != 0
+    if am.dim() != 2:
+        raise _lib.B2FError(f"attention_mask: expected [B, L], got {tuple(am.shape)}")
+    spans = []
+    for b in range(am.shape[0]):
+        idx = am[b].nonzero().squeeze(1)
+        if idx.numel() == 0:
+            raise _lib.B2FError(f"attention_mask row {b} is empty")
+        lo, hi = int(idx[0]), int(idx[-1]) + 1
+        if hi - lo != idx.numel():
+            raise _lib.B2FError(f"attention_mask row {b} is not one contiguous run of ones (left or right padding)")
+        spans.append((lo, hi))
+    return spans
+
+
 class B200Qwen2p5VL(torch.nn.Module):
     """Weights in kernel layout + the prefill forward.  `denoise_projector` (MLP2) is owned by the
     denoise tower (univa.models.modeling_univa_denoise_tower)."""
@@ -351,13 +369,18 @@ class B200Qwen2p5VL(torch.nn.Module):
         sin = pick(emb.sin()).bfloat16().float().reshape(n, hd).to(self._dev).contiguous()
         return cos, sin
 
-    def _decoder(self, x, cos, sin, B, L, kv_cache=None, past: int = 0):
+    def _decoder(self, x, cos, sin, B, L, kv_cache=None, past: int = 0, spans=None):
         """The 28 decoder layers + final norm on x [B*L, hidden] (updated in place).  With `kv_cache`
         ([layers, 2, B, Lmax, Hkv, head_dim]) the post-RoPE K and V of these L tokens are stored at
-        [past, past+L) and attention runs over the cached prefix as well (L == 1: decode step)."""
+        [past, past+L) and attention runs over the cached prefix as well (L == 1: decode step).
+        `spans` [(lo, hi)] * B marks the real tokens of a padded batch: attention then runs per sequence over its
+        own tokens only and the padding rows get a zero attention output — what transformers' flash_attention_2
+        path does (unpad -> varlen attention -> pad_input), the backend the reference selects (cli.py:40,
+        train_denoiser.py:1633)."""
         tc, W, hd = self.tc, self.W, self.thd
         nq, nkv = tc.num_attention_heads, tc.num_key_value_heads
-        o = torch.empty((B * L, nq * hd), device=self._dev, dtype=torch.bfloat16)
+        # padded batch: the rows no launch writes must read as zeros in every layer
+        o = (torch.zeros if spans is not None else torch.empty)((B * L, nq * hd), device=self._dev, dtype=torch.bfloat16)
         if past and L != 1:
             raise _lib.B2FError("chunked prefill is not implemented: use past == 0 (prefill) or one new token (decode)")
         for i in range(tc.num_hidden_layers):
@@ -377,6 +400,10 @@ class B200Qwen2p5VL(torch.nn.Module):
                 for b in range(B):
                     ops.attention(q[b:b + 1], kv_cache[i, 0, b:b + 1, :past + 1], kv_cache[i, 1, b:b + 1, :past + 1],
                                   out=o.unflatten(0, (B, L))[b:b + 1])
+            elif spans is not None:
+                o3 = o.unflatten(0, (B, L))
+                for b, (lo, hi) in enumerate(spans):
+                    ops.attention(q[b:b + 1, lo:hi], k[b:b + 1, lo:hi], v[b:b + 1, lo:hi], out=o3[b:b + 1, lo:hi], causal=True)
             else:
                 ops.attention(q, k, v, out=o.unflatten(0, (B, L)), causal=True)
             ops.linear(o, W[p + "o.w"], None, epilogue=ops.EPI_RESID, resid=x, out=x)
@@ -444,9 +471,13 @@ class B200Qwen2p5VL(torch.nn.Module):
                 return_image_embeds: bool = False, kv_cache=None, return_rope_deltas: bool = False):
         """-> last hidden state after model.norm, [B, L, hidden] (what the reference feeds to MLP2)."""
         tc, W = self.tc, self.W
-        if attention_mask is not None and not bool((attention_mask == 1).all()):
-            raise _lib.B2FError("padded batches (attention_mask with zeros) are not implemented in the libb2f prefill")
         B, L = input_ids.shape
+        spans = None
+        if attention_mask is not None and not bool((attention_mask == 1).all()):
+            spans = padding_spans(attention_mask)
+            if kv_cache is not None:
+                raise _lib.B2FError("generate() with a padded batch is not built (the KV-cache decode attends to every cached "
+                                    "position): decode one prompt per call, as cli.py does")
         ids = input_ids.to(self._dev)
         x = ops.gather_rows(W["model.embed_tokens"], ids.reshape(-1).contiguous())
         image_embeds = None
@@ -461,7 +492,7 @@ class B200Qwen2p5VL(torch.nn.Module):
                                 spatial_merge_size=self.vc.spatial_merge_size, image_token_id=tc.image_token_id,
                                 vision_start_token_id=tc.vision_start_token_id)
         cos, sin = self._rope_tables(pos)
-        h = self._decoder(x, cos, sin, B, L, kv_cache).view(B, L, tc.hidden_size)
+        h = self._decoder(x, cos, sin, B, L, kv_cache, spans=spans).view(B, L, tc.hidden_size)
         if return_rope_deltas:
             return h, deltas
         return (h, image_embeds) if return_image_embeds else h

@@ -273,6 +273,21 @@ def rope_index_golden():
     for ids, grid in cases:
         pos, delta = ns["get_rope_index"](fake, ids, grid)
         out.append(dict(input_ids=ids, image_grid_thw=grid, position_ids=pos, deltas=delta))
+    # padded batches (processor(..., padding=True)): right padding, left padding, text only
+    pad = 0
+    row_a = [1, 2, 3, 902] + img32 + [903, 5, 6, 7, 8, 9, 10]
+    row_b = [1, 902] + img4 + [903, 4, 5]
+    n = len(row_a)
+    masked = [
+        (torch.tensor([row_a, row_b + [pad] * (n - len(row_b))]),
+         torch.tensor([[1] * n, [1] * len(row_b) + [0] * (n - len(row_b))]), torch.tensor([[1, 16, 8], [1, 4, 4]])),
+        (torch.tensor([row_a, [pad] * (n - len(row_b)) + row_b]),
+         torch.tensor([[1] * n, [0] * (n - len(row_b)) + [1] * len(row_b)]), torch.tensor([[1, 16, 8], [1, 4, 4]])),
+        (torch.tensor([[5, 6, 7, 8, 9, 10], [5, 6, 7, pad, pad, pad]]), torch.tensor([[1] * 6, [1, 1, 1, 0, 0, 0]]), None),
+    ]
+    for ids, mask, grid in masked:
+        pos, delta = ns["get_rope_index"](fake, ids, grid, None, None, mask)
+        out.append(dict(input_ids=ids, image_grid_thw=grid, attention_mask=mask, position_ids=pos, deltas=delta))
     torch.save(out, HERE / "rope_index_ref.pt")
     print("rope_index golden:", [tuple(o["position_ids"].shape) for o in out])
 

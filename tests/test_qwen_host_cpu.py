@@ -29,9 +29,10 @@ def test_get_rope_index_matches_reference_golden():
     from gpt_image_edit_b200.qwen2p5vl import get_rope_index
 
     cases = torch.load(Path(__file__).parent / "golden" / "rope_index_ref.pt")
-    assert len(cases) == 3
+    assert len(cases) == 6 and sum("attention_mask" in c for c in cases) == 3      # 3 of them padded batches
     for c in cases:
-        pos, delta = get_rope_index(c["input_ids"], c["image_grid_thw"], None, image_token_id=900, vision_start_token_id=902)
+        pos, delta = get_rope_index(c["input_ids"], c["image_grid_thw"], c.get("attention_mask"), image_token_id=900,
+                                    vision_start_token_id=902)
         assert torch.equal(pos, c["position_ids"])
         assert torch.equal(delta.flatten(), c["deltas"].flatten())
     # worked example of SURVEY.md Appendix B: 4 prefix tokens get 0..3, a 16x16 llm grid gets t=4, h=4+row, w=4+col
