@@ -129,6 +129,37 @@ def load_processor(model_path, min_pixels=448 * 448, max_pixels=448 * 448):
     return AutoProcessor.from_pretrained(str(root), min_pixels=min_pixels, max_pixels=max_pixels)
 
 
+TEXT_KEYS = ("hidden_size", "num_hidden_layers", "num_attention_heads", "num_key_value_heads", "intermediate_size",
+             "vocab_size", "rms_norm_eps", "rope_theta")
+VISION_KEYS = ("depth", "hidden_size", "num_heads", "intermediate_size", "patch_size", "temporal_patch_size",
+               "spatial_merge_size", "window_size", "fullatt_block_indexes", "out_hidden_size", "tokens_per_second")
+
+
+def univa_config_kwargs(raw: dict) -> dict:
+    """Keyword arguments of UnivaQwen2p5VLConfig from a checkpoint's config.json.  The reference's config class extends
+    transformers-4.50's Qwen2_5_VLConfig (configuration_univa_qwen2p5vl.py:7-52), whose json keeps the language-model
+    fields at the TOP level and M-RoPE under `rope_scaling`; transformers-5 files nest them under `text_config` /
+    `rope_parameters`.  Both are read; a field that is absent keeps the Qwen2.5-VL-7B default."""
+    nested = dict(raw.get("text_config") or {})
+    text = {k: nested.get(k, raw.get(k)) for k in TEXT_KEYS if nested.get(k, raw.get(k)) is not None}
+    rope = nested.get("rope_parameters") or nested.get("rope_scaling") or raw.get("rope_parameters") or raw.get("rope_scaling") or {}
+    if rope.get("mrope_section") is not None:
+        text["mrope_section"] = tuple(rope["mrope_section"])
+    if rope.get("rope_theta") is not None and "rope_theta" not in text:
+        text["rope_theta"] = rope["rope_theta"]
+    vraw = dict(raw.get("vision_config") or {})
+    vision = {k: vraw[k] for k in VISION_KEYS if k in vraw}
+    if "in_chans" in vraw or "in_channels" in vraw:
+        vision["in_channels"] = vraw.get("in_channels", vraw.get("in_chans"))
+    if "fullatt_block_indexes" in vision:
+        vision["fullatt_block_indexes"] = tuple(vision["fullatt_block_indexes"])
+    kw = dict(denoise_tower=raw.get("denoise_tower"), text_config=text, vision_config=vision)
+    for k in ("image_token_id", "video_token_id", "vision_start_token_id", "shortcut_image_embeds", "shortcut_projector_type"):
+        if raw.get(k) is not None:
+            kw[k] = raw[k]
+    return kw
+
+
 def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_pixels=448 * 448):
     """-> (UnivaQwen2p5VLForConditionalGeneration, task_head, processor) from a Univa checkpoint directory
     (reference cli.py:30-56)."""
@@ -138,8 +169,7 @@ def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_p
     root = Path(model_path)
     processor = load_processor(root, min_pixels, max_pixels)
     raw = json.loads((root / "config.json").read_text()) if (root / "config.json").exists() else {}
-    cfg = UnivaQwen2p5VLConfig(denoise_tower=raw.get("denoise_tower"), text_config=raw.get("text_config"),
-                               vision_config=raw.get("vision_config"))
+    cfg = UnivaQwen2p5VLConfig(**univa_config_kwargs(raw))
     model = UnivaQwen2p5VLForConditionalGeneration(cfg, device=device)
     sd = load_state_dict_from_dir(root)
     lvlm_sd = {k: v for k, v in sd.items() if k.startswith(("visual.", "model.", "lm_head."))}
@@ -155,8 +185,9 @@ def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_p
                                                            if k.startswith("denoise_tower.denoise_projector.")})
     head = TaskHead(cfg.hidden_size, device=device)
     th = root / "task_head_final.pt"
-    if th.exists():
-        t = torch.load(th, map_location="cpu")
-        head.w0.copy_(t["0.weight"]); head.b0.copy_(t["0.bias"])
-        head.w3[:2].copy_(t["3.weight"]); head.b3[:2].copy_(t["3.bias"])
+    if not th.exists():      # the reference's torch.load (cli.py:49) fails here; a zero head would answer every turn with text
+        raise FileNotFoundError(f"{th}: the generate / understand router of the Univa checkpoint is missing")
+    t = torch.load(th, map_location="cpu")
+    head.w0.copy_(t["0.weight"]); head.b0.copy_(t["0.bias"])
+    head.w3[:2].copy_(t["3.weight"]); head.b3[:2].copy_(t["3.bias"])
     return model, head, processor

@@ -535,3 +535,41 @@ def test_resume_resolution_and_checkpoint_pruning_match_the_reference_statements
         said = []
         td.prune_checkpoints(out, c["limit"], log=said.append)
         assert sorted(os.listdir(out)) == c["left"] and said == c["said"], c
+
+
+def test_univa_config_is_read_from_both_config_json_layouts():
+    """The Univa checkpoint's config.json is written by transformers 4.50 (the reference's pin): language-model fields at the
+    top level, M-RoPE under `rope_scaling`, `in_chans` in the vision block, `denoise_tower` next to them
+    (configuration_univa_qwen2p5vl.py:7-52).  transformers 5 nests the language model under `text_config`."""
+    from gpt_image_edit_b200.checkpoint import univa_config_kwargs
+    from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig
+
+    flat = {"architectures": ["UnivaQwen2p5VLForConditionalGeneration"], "hidden_size": 2048, "intermediate_size": 11008,
+            "num_attention_heads": 16, "num_hidden_layers": 36, "num_key_value_heads": 2, "rms_norm_eps": 1e-06,
+            "rope_theta": 1000000.0, "rope_scaling": {"type": "mrope", "mrope_section": [16, 24, 24]}, "vocab_size": 151936,
+            "image_token_id": 151655, "video_token_id": 151656, "vision_start_token_id": 151652, "tie_word_embeddings": True,
+            "vision_config": {"depth": 32, "hidden_size": 1280, "intermediate_size": 3420, "num_heads": 16, "in_chans": 3,
+                              "out_hidden_size": 2048, "patch_size": 14, "spatial_merge_size": 2, "window_size": 112,
+                              "fullatt_block_indexes": [7, 15, 23, 31], "tokens_per_second": 2, "temporal_patch_size": 2,
+                              "hidden_act": "silu"},
+            "denoise_tower": {"denoiser_type": "flux", "denoise_projector_type": "mlp2x_gelu", "output_hidden_size": 4096,
+                              "denoiser_config": {"num_layers": 19, "num_single_layers": 38}}}
+    cfg = UnivaQwen2p5VLConfig(**univa_config_kwargs(flat))
+    tc, vc = cfg.text_config, cfg.vision_config
+    assert (tc.hidden_size, tc.num_hidden_layers, tc.num_attention_heads, tc.num_key_value_heads) == (2048, 36, 16, 2)
+    assert tc.intermediate_size == 11008 and tc.vocab_size == 151936 and tuple(tc.mrope_section) == (16, 24, 24)
+    assert vc.out_hidden_size == 2048 and vc.in_channels == 3 and tuple(vc.fullatt_block_indexes) == (7, 15, 23, 31)
+    assert cfg.denoise_tower.input_hidden_size == 2048 and cfg.denoise_tower.output_hidden_size == 4096   # :44-45
+    assert cfg.denoise_tower.denoiser_config["num_single_layers"] == 38 and cfg.hidden_size == 2048
+    nested = {"text_config": {k: flat[k] for k in ("hidden_size", "intermediate_size", "num_attention_heads",
+                                                    "num_hidden_layers", "num_key_value_heads", "vocab_size")} |
+              {"rope_parameters": {"rope_type": "default", "rope_theta": 5e5, "mrope_section": [8, 12, 12]}},
+              "vision_config": flat["vision_config"], "image_token_id": 900, "vision_start_token_id": 902}
+    cfg2 = UnivaQwen2p5VLConfig(**univa_config_kwargs(nested))
+    assert cfg2.text_config.hidden_size == 2048 and tuple(cfg2.text_config.mrope_section) == (8, 12, 12)
+    assert cfg2.text_config.rope_theta == 5e5 and cfg2.image_token_id == 900 and cfg2.text_config.vision_start_token_id == 902
+    # nothing given: the Qwen2.5-VL-7B sizes of the released checkpoint
+    cfg3 = UnivaQwen2p5VLConfig(**univa_config_kwargs({}))
+    assert (cfg3.text_config.hidden_size, cfg3.text_config.num_hidden_layers, cfg3.vision_config.depth) == (3584, 28, 32)
+    with pytest.raises(Exception, match="shortcut_image_embeds"):
+        UnivaQwen2p5VLConfig(**univa_config_kwargs({"shortcut_image_embeds": True}))

@@ -4,7 +4,8 @@
     torchrun --nproc-per-node N -m univa.eval.gedit.step1_gen_samples cfg.yaml [--output_dir ...]
 
 Same contract as the reference: a prompt file {key: {"prompt": ..., "id": <relative image path>}}, one full
-model replica per rank (no collective during sampling), items strided `rank::world_size`, `seed + rank`,
+model replica per rank (no collective during sampling), items strided `rank::world_size`, `seed + rank` seeding of the
+default generators (the pipeline is given no generator of its own),
 outputs written to `output_dir/<id>` and skipped when they already exist, generation size from
 `pick_ratio(any_17ratio)` + `compute_size(stride 16, anchor height*width)`, a fixed 448x448 view for the VLM,
 an empty T5 prompt unless `joint_with_t5`.  Judges / metrics (step2) are out of scope.
@@ -65,10 +66,11 @@ def run_model_and_return_samples(args: EvalConfig, state: dict, prompt_text: str
                               image_grid_thw=grid, output_type="denoise_embeds")
     t5, pooled = encode_prompt(state["text_encoders"], state["tokenizers"], prompt_text if args.joint_with_t5 else "", 256, dev, 1)
     embeds = t5 if args.only_use_t5 else (torch.cat([lvlm, t5], dim=1) if args.joint_with_t5 else lvlm)
+    # no `generator=`, as in the reference (:195-204): the noise comes from the device's default generator, which main()
+    # seeded with seed + rank, so the i-th image of a rank continues that stream exactly as it does there
     return state["pipe"](image=image_to_condition_tensor(img).to(dev), prompt_embeds=embeds, pooled_prompt_embeds=pooled,
                          height=gen_h, width=gen_w, num_inference_steps=args.num_inference_steps,
-                         guidance_scale=args.guidance_scale, num_images_per_prompt=args.num_images_per_prompt,
-                         generator=torch.Generator(device=dev).manual_seed(D.rank_seed(args.seed, args.local_rank))).images
+                         guidance_scale=args.guidance_scale, num_images_per_prompt=args.num_images_per_prompt).images
 
 
 def main(args: EvalConfig):
@@ -79,8 +81,10 @@ def main(args: EvalConfig):
     torch.cuda.set_device(device)
     D.init_from_env(device=device)
     args.local_rank, args.world_size = rank, world
-    torch.manual_seed(D.rank_seed(args.seed, rank))                           # set_seed(seed, rank, device_specific=True)
+    import random
+    random.seed(D.rank_seed(args.seed, rank))                                 # set_seed(seed, rank, device_specific=True) (:33-43)
     np.random.seed(D.rank_seed(args.seed, rank))
+    torch.manual_seed(D.rank_seed(args.seed, rank))                           # CPU and every CUDA device
     model, _, processor = cli.load_main_model_and_processor(args.pretrained_lvlm_name_or_path, device, args.synthetic, args.small)
     pipe, tokenizers, text_encoders = cli.load_pipe(model.denoise_tower.denoiser, args.pretrained_denoiser_name_or_path, device,
                                                     args.synthetic, args.small)

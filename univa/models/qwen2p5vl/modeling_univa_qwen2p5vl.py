@@ -44,7 +44,11 @@ class UnivaQwen2p5VLConfig:
         self.image_token_id, self.video_token_id = image_token_id, video_token_id
         self.vision_start_token_id = vision_start_token_id
         self.hidden_size = self.text_config.hidden_size
-        self.shortcut_projector_type, self.shortcut_image_embeds = shortcut_projector_type, shortcut_image_embeds
+        if shortcut_image_embeds:
+            # the reference's shortcut branch (:421-441, 507-520) cannot run there either (`len(num_blocks)` of an int) and no
+            # shipped configuration enables it
+            raise B2FError("shortcut_image_embeds=True is not built")
+        self.shortcut_projector_type, self.shortcut_image_embeds = None, False       # :29-31: no projector without the flag
 
 
 class UnivaQwen2p5VLForConditionalGeneration(torch.nn.Module):
