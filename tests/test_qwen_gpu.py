@@ -177,63 +177,3 @@ def test_generate_kv_cache_decode_matches_transformers():
                           eos_token_id=(eos_tok,))
     if bool(clear[0, :3].all()):
         assert short.shape[1] == ids.shape[1] + 3 and int(short[0, -1]) == eos_tok
-
-
-@pytest.mark.parametrize("side", ["right", "left"])
-def test_padded_batch_prefill(side):
-    """A batch of prompts of different lengths (`processor(..., padding=True)`, train_denoiser.py batches > 1): every
-    sequence attends to its own tokens only — checked on the real tokens against transformers given the same mask
-    (right padding) and against this engine's own unpadded runs (both sides) — and a padding row gets a ZERO attention
-    output in every layer, i.e. it only passes through the MLPs, as under transformers' flash_attention_2 path (the
-    backend the reference selects): checked against that chain written out in fp32."""
-    from gpt_image_edit_b200.qwen2p5vl import get_rope_index
-
-    ref, mine = _models()
-    g = torch.Generator().manual_seed(5)
-    grid = torch.tensor([[1, 16, 8]])
-    pix = torch.randn(128, 1176, generator=g).bfloat16()
-    row_a = [1, 2, 3, VSTART] + [IMG] * 32 + [903] + list(range(10, 25))
-    row_b = list(range(40, 51))
-    n, nb, PAD = len(row_a), len(row_b), 7
-    if side == "right":
-        ids = torch.tensor([row_a, row_b + [PAD] * (n - nb)])
-        mask = torch.tensor([[1] * n, [1] * nb + [0] * (n - nb)])
-        real_b = slice(0, nb)
-    else:
-        ids = torch.tensor([row_a, [PAD] * (n - nb) + row_b])
-        mask = torch.tensor([[1] * n, [0] * (n - nb) + [1] * nb])
-        real_b = slice(n - nb, n)
-    h = mine(ids.cuda(), pixel_values=pix.cuda(), attention_mask=mask.cuda(), image_grid_thw=grid)
-    assert h.shape == (2, n, 256) and torch.isfinite(h.float()).all()
-    # (1) the engine's own unpadded runs of the two prompts
-    h_a = mine(torch.tensor([row_a]).cuda(), pixel_values=pix.cuda(), image_grid_thw=grid)
-    h_b = mine(torch.tensor([row_b]).cuda())
-    assert _rel_l2(h[0], h_a[0]) < 2e-3 and _rel_l2(h[1, real_b], h_b[0]) < 2e-3
-    ref32 = ref.to("cuda", torch.float32)
-    with torch.no_grad():
-        for p in ref32.parameters():
-            p.copy_(p.bfloat16().float())
-        if side == "right":
-            # (2) transformers with the same mask and the reference's position ids, real tokens only
-            pos, _ = get_rope_index(ids, grid, mask, spatial_merge_size=2, image_token_id=IMG, vision_start_token_id=VSTART)
-            h32 = ref32(input_ids=ids.cuda(), attention_mask=mask.cuda(), pixel_values=pix.cuda().float(),
-                        image_grid_thw=grid.cuda(), position_ids=pos.cuda()).last_hidden_state
-            assert _rel_l2(h[0], h32[0]) < 2e-2 and _rel_l2(h[1, real_b], h32[1, real_b]) < 2e-2
-        # (3) padding rows: embedding -> (x += mlp(post_attention_layernorm(x))) per layer -> final norm
-        lm = ref32.language_model
-        x = lm.embed_tokens(torch.tensor([PAD], device="cuda"))
-        for layer in lm.layers:
-            x = x + layer.mlp(layer.post_attention_layernorm(x))
-        want = lm.norm(x)[0]
-    pad_rows = h[1][mask[1] == 0]
-    assert pad_rows.shape[0] == n - nb
-    assert all(_rel_l2(r, want) < 2e-2 for r in pad_rows)
-
-
-def test_generate_refuses_padded_batches():
-    from gpt_image_edit_b200 import _lib
-
-    _, mine = _models()
-    ids = torch.tensor([[1, 2, 3, 4], [5, 6, 7, 7]]).cuda()
-    with pytest.raises(_lib.B2FError):
-        mine.generate(ids, attention_mask=torch.tensor([[1, 1, 1, 1], [1, 1, 1, 0]]).cuda(), max_new_tokens=2)

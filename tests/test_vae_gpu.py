@@ -165,28 +165,3 @@ def test_uint8_pixels_in_and_out_equal_the_host_side_chain():
     got = vae.decode_u8(z)
     assert got.dtype == torch.uint8 and tuple(got.shape) == (2, 96, 128, 3)
     assert all(np.array_equal(w, g_.cpu().numpy()) for w, g_ in zip(want, got))
-
-
-def test_vae_slicing_runs_one_item_per_pass_with_the_same_results():
-    """`pipe.enable_vae_slicing()` (reference flux_pipeline.py:615-630 -> AutoencoderKL.enable_slicing): one batch item per
-    kernel sequence.  Every normalisation in the VAE is per item, so the outputs are those of the batched call."""
-    from gpt_image_edit_b200 import _lib as L
-    from gpt_image_edit_b200.pipeline import FluxKontextPipeline
-    from gpt_image_edit_b200.vae import B200AutoencoderKL, VaeConfig
-
-    vae = B200AutoencoderKL(VaeConfig(block_out_channels=(64, 128, 256, 256))).randomize_(seed=6)
-    pipe = FluxKontextPipeline(transformer=None, vae=vae)
-    g = torch.Generator(device="cuda").manual_seed(8)
-    img = (torch.rand(3, 3, 64, 96, device="cuda", generator=g) * 2 - 1).bfloat16()
-    z = torch.randn(3, 16, 8, 12, device="cuda", generator=g).bfloat16()
-    want = vae.encode(img).latent_dist.mode(), vae.decode(z, return_dict=False)[0], vae.decode_u8(z)
-    pipe.enable_vae_slicing()
-    assert vae.use_slicing
-    got = vae.encode(img).latent_dist.mode(), vae.decode(z, return_dict=False)[0], vae.decode_u8(z)
-    pipe.disable_vae_slicing()
-    assert not vae.use_slicing
-    assert got[0].shape == want[0].shape and _rel_l2(got[0], want[0]) < 1e-3
-    assert got[1].shape == want[1].shape and _rel_l2(got[1], want[1]) < 1e-3
-    assert got[2].shape == want[2].shape and (got[2].int() - want[2].int()).abs().max().item() <= 1
-    with pytest.raises(L.B2FError):
-        pipe.enable_vae_tiling()
