@@ -53,6 +53,14 @@ def check_param_is_in_components(name: str, components) -> bool:      # train_de
     return any(component in name for component in components)
 
 
+def trained_flux_layers(mc) -> list:
+    """Block indices whose components train under a ModelConfig (train_denoiser.py:527-543): none with `only_tune_mlp2`,
+    none when `flux_train_layer_idx` is left at its default None, else the listed ones (0-18 double, 19-56 single)."""
+    if mc.only_tune_mlp2 or mc.flux_train_layer_idx is None:
+        return []
+    return list(mc.flux_train_layer_idx)
+
+
 @dataclass
 class Param:
     name: str            # diffusers-style name(s) this tensor answers to (for the log / checkpoint)
@@ -473,11 +481,14 @@ class Stage2Trainer:
         self.model, self.vae, self.pipe, self.tc, self.mc = model, vae, pipe, tc, mc
         self.empty_pooled = empty_pooled                      # [1, 768] CLIP pooled embedding of "" (:795-805)
         den = model.denoise_tower.denoiser
-        if mc.only_tune_mlp2:
-            params = [p for p in trainable_params(model, layers_to_train=[], with_tune_mlp2=True)]
-        else:
-            params = trainable_params(model, layers_to_train=mc.flux_train_layer_idx, only_img_branch=mc.only_tune_image_branch,
-                                      with_tune_mlp2=mc.with_tune_mlp2)
+        # which tensors train (train_denoiser.py:513-548): everything is frozen first; `only_tune_mlp2` un-freezes MLP2 alone;
+        # otherwise the FLUX components of `flux_train_layer_idx` — None (the schema's default) un-freezes NO FLUX layer, the
+        # stage-2 yaml lists all 57 — and, with `with_tune_mlp2`, MLP2
+        params = trainable_params(model, layers_to_train=trained_flux_layers(mc), only_img_branch=mc.only_tune_image_branch,
+                                  with_tune_mlp2=bool(mc.only_tune_mlp2 or mc.with_tune_mlp2))
+        if not params:
+            raise _lib.B2FError("nothing to train: set model_config.flux_train_layer_idx, with_tune_mlp2 or only_tune_mlp2 "
+                                "(the reference's optimizer would be built over an empty parameter list)")
         if tc.optimizer.lower() != "adamw":
             raise _lib.B2FError(f"optimizer={tc.optimizer!r}: only AdamW is built (the stage yamls of the reference use adamw)")
         if tc.gradient_checkpointing:

@@ -18,7 +18,8 @@ def main():
     conf = from_mapping(dict(
         training_config=dict(seed=5, learning_rate=1e-4, adam_beta2=0.99, adam_weight_decay=0.0, discrete_timestep=False,
                              mask_weight_type="log", max_grad_norm=1e9),
-        model_config=dict(synthetic=True, small=True, with_tune_mlp2=True, joint_ref_feature=True),
+        model_config=dict(synthetic=True, small=True, with_tune_mlp2=True, joint_ref_feature=True,
+                          flux_train_layer_idx=list(range(57))),
         dataset_config=dict(dataset_type="synthetic", batch_size=1, height=256, width=256)))
     model, vae, pipe, empty = td.build_models(conf, dev)
     tr = Stage2Trainer(model, vae, pipe, conf.training_config, conf.model_config, empty)

@@ -573,3 +573,22 @@ def test_univa_config_is_read_from_both_config_json_layouts():
     assert (cfg3.text_config.hidden_size, cfg3.text_config.num_hidden_layers, cfg3.vision_config.depth) == (3584, 28, 32)
     with pytest.raises(Exception, match="shortcut_image_embeds"):
         UnivaQwen2p5VLConfig(**univa_config_kwargs({"shortcut_image_embeds": True}))
+
+
+def test_which_flux_layers_train_follows_the_reference_rule():
+    """train_denoiser.py:527-543: `only_tune_mlp2` trains no FLUX tensor; otherwise the components of `flux_train_layer_idx`
+    — and the schema's default None un-freezes nothing (the guard `is not None` at :531), although get_trainable_params'
+    own default would list all 57 blocks."""
+    from types import SimpleNamespace
+
+    from gpt_image_edit_b200.training import get_trainable_params, trained_flux_layers
+
+    mc = lambda **k: SimpleNamespace(**{**dict(only_tune_mlp2=False, flux_train_layer_idx=None), **k})
+    assert trained_flux_layers(mc()) == []
+    assert trained_flux_layers(mc(flux_train_layer_idx=[0, 20])) == [0, 20]
+    assert trained_flux_layers(mc(only_tune_mlp2=True, flux_train_layer_idx=list(range(57)))) == []
+    assert get_trainable_params(trained_flux_layers(mc())) == [] and len(get_trainable_params(None)) == 19 * 7 + 38 * 6
+    from univa.training.configuration_denoise import load_config
+    from pathlib import Path
+    conf = load_config(Path(__file__).parent.parent / "scripts" / "denoiser" / "flux_qwen2p5vl_7b_vlm_stage2_512_synthetic.yaml")
+    assert trained_flux_layers(conf.model_config) == list(range(57))       # BASELINE.json configs[3] trains all 57 blocks

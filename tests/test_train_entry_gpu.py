@@ -16,7 +16,8 @@ def _conf(tmp_path, **tc):
                 mask_weight_type="log", report_to="none")
     base.update(tc)
     return from_mapping(dict(training_config=base,
-                             model_config=dict(synthetic=True, small=True, with_tune_mlp2=True, joint_ref_feature=True),
+                             model_config=dict(synthetic=True, small=True, with_tune_mlp2=True, joint_ref_feature=True,
+                                               flux_train_layer_idx=list(range(57))),
                              dataset_config=dict(dataset_type="synthetic", batch_size=1, height=256, width=256)))
 
 

@@ -118,8 +118,8 @@ def save_checkpoint(conf, trainer, model, step: int, rank: int, world: int):
     save.mkdir(parents=True, exist_ok=True)
     if rank == 0:
         den = model.denoise_tower.denoiser.state_dict()
-        from gpt_image_edit_b200.training import check_param_is_in_components, get_trainable_params
-        comps = get_trainable_params(conf.model_config.flux_train_layer_idx, model.denoise_tower.denoiser.config.num_layers,
+        from gpt_image_edit_b200.training import check_param_is_in_components, get_trainable_params, trained_flux_layers
+        comps = get_trainable_params(trained_flux_layers(conf.model_config), model.denoise_tower.denoiser.config.num_layers,
                                      conf.model_config.only_tune_image_branch)
         trained = {k: v for k, v in den.items() if check_param_is_in_components("denoise_tower.denoiser." + k, comps)}
         ck.save_state_dict(trained, save / "denoiser_trainable")
