@@ -43,7 +43,7 @@ def test_padded_batch_prefill(side):
     # (1) the engine's own unpadded runs of the two prompts
     h_a = mine(torch.tensor([row_a]).cuda(), pixel_values=pix.cuda(), image_grid_thw=grid)
     h_b = mine(torch.tensor([row_b]).cuda())
-    assert _rel_l2(h[0], h_a[0]) < 2e-3 and _rel_l2(h[1, real_b], h_b[0]) < 2e-3
+    assert _rel_l2(h[0], h_a[0]) < 5e-3 and _rel_l2(h[1, real_b], h_b[0]) < 5e-3
     ref32 = ref.to("cuda", torch.float32)
     with torch.no_grad():
         for p in ref32.parameters():
@@ -92,8 +92,8 @@ def test_vae_slicing_runs_one_item_per_pass_with_the_same_results():
     got = vae.encode(img).latent_dist.mode(), vae.decode(z, return_dict=False)[0], vae.decode_u8(z)
     pipe.disable_vae_slicing()
     assert not vae.use_slicing
-    assert got[0].shape == want[0].shape and _rel_l2(got[0], want[0]) < 1e-3
-    assert got[1].shape == want[1].shape and _rel_l2(got[1], want[1]) < 1e-3
+    assert got[0].shape == want[0].shape and _rel_l2(got[0], want[0]) < 4e-3
+    assert got[1].shape == want[1].shape and _rel_l2(got[1], want[1]) < 4e-3
     assert got[2].shape == want[2].shape and (got[2].int() - want[2].int()).abs().max().item() <= 1
     with pytest.raises(L.B2FError):
         pipe.enable_vae_tiling()
