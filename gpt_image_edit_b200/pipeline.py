@@ -51,7 +51,7 @@ class FluxPipelineOutput(SimpleNamespace):
 
 
 def randn_tensor(shape, generator=None, device=None, dtype=None):
-    """diffusers.utils.torch_utils.randn_tensor as the reference calls it (flux_pipeline.py:702) [dep-spec]: a CPU
+    """diffusers.utils.torch_utils.randn_tensor as the reference calls it (flux_pipeline.py:703) [dep-spec]: a CPU
     generator draws on the CPU and the result is moved, a CUDA generator cannot serve a CPU tensor, a list of generators
     (a list of one counts as that one) draws one batch item each."""
     shape = tuple(shape)
@@ -74,7 +74,7 @@ def randn_tensor(shape, generator=None, device=None, dtype=None):
 
 class VaeImageProcessor:
     """diffusers' VaeImageProcessor as the reference pipeline configures and reaches it (`VaeImageProcessor(
-    vae_scale_factor=16)`, flux_pipeline.py:228: do_resize, lanczos, do_normalize) [dep-spec, SURVEY.md A.4]:
+    vae_scale_factor=16)`, flux_pipeline.py:259: do_resize, lanczos, do_normalize) [dep-spec, SURVEY.md A.4]:
     `get_default_height_width`, `resize`, `preprocess` for tensors, PIL images, arrays and lists of them, and
     `postprocess` to "pt" / "np" / "pil"."""
 
@@ -489,7 +489,7 @@ class FluxKontextPipeline:
                 noise_pred = neg_noise_pred + true_cfg_scale * (noise_pred - neg_noise_pred)
             latents = self.scheduler.step(noise_pred, t, latents, return_dict=False)[0]
             if callback_on_step_end is not None:
-                # the tensors named in callback_on_step_end_tensor_inputs, and what the callback may hand back (:1105-1112)
+                # the tensors named in callback_on_step_end_tensor_inputs, and what the callback may hand back (:1106-1113)
                 avail = {"latents": latents, "prompt_embeds": prompt_embeds}
                 out = callback_on_step_end(self, i, t, {k: avail[k] for k in callback_on_step_end_tensor_inputs})
                 latents = out.pop("latents", latents)
