@@ -371,7 +371,7 @@ class FluxKontextPipeline:
                  max_sequence_length: int = 512, max_area: int = 1024 ** 2, _auto_resize: bool = True,
                  ip_adapter_image=None, ip_adapter_image_embeds=None, negative_ip_adapter_image=None,
                  negative_ip_adapter_image_embeds=None):
-        self._interrupt = False                    # reference :919-922: per-call state
+        self._interrupt = False                    # reference :907-910: per-call state
         self._guidance_scale = guidance_scale
         self._joint_attention_kwargs = joint_attention_kwargs
         self._current_timestep = None
