@@ -141,7 +141,8 @@ class VaeImageProcessor:
             h, w = self.get_default_height_width(x, height, width)
             x = torch.nn.functional.interpolate(x, size=(h, w))
         else:
-            x = torch.cat(image, dim=0) if image[0].dim() == 4 else torch.stack(image, dim=0)
+            x = image[0] if (len(image) == 1 and image[0].dim() == 4) else \
+                (torch.cat(image, dim=0) if image[0].dim() == 4 else torch.stack(image, dim=0))
             h, w = self.get_default_height_width(x, height, width)
             x = self.resize(x, h, w)
         if x.min() < 0:              # already [-1, 1] (diffusers warns and skips the normalisation)
