@@ -10,8 +10,12 @@ reference's bf16 rounding chain, and running it on fp32/fp64 tensors gives the e
 PARITY UNPINNED by the reference: /root/reference holds no tests, golden vectors or fixtures for
 this path.  The pins this repo adds instead:
   * oracle ≡ torchtitan.experiments.flux (an independent BFL-layout FLUX in site-packages) to
-    fp32 round-off, with weights mapped by SURVEY.md A.7 — tests/test_oracle_crosscheck.py, and the
-    fixtures that script generates under tests/golden/;
+    fp32 round-off, with weights mapped by SURVEY.md A.7 — tests/test_oracle_cpu.py
+    (test_oracle_matches_torchtitan_golden, test_live_crosscheck_against_torchtitan_if_available,
+    test_oracle_guidance_embedder_matches_torchtitan_plus_guidance) over the fixtures tests/golden/make_golden.py writes
+    (flux_toy_titan.pt, flux_toy_titan_guidance.pt);
+  * the sampling loop built on it is bit-identical to the reference's own FluxKontextPipeline.__call__ executed from its
+    file (oracle/pipeline_oracle.py, tests/golden/pipeline_ref_loop.pt);
   * scheduler/packing invariants quoted in SURVEY.md §8c.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
