@@ -290,6 +290,34 @@ def rope_index_golden():
         out.append(dict(input_ids=ids, image_grid_thw=grid, attention_mask=mask, position_ids=pos, deltas=delta))
     torch.save(out, HERE / "rope_index_ref.pt")
     print("rope_index golden:", [tuple(o["position_ids"].shape) for o in out])
+    # a randomized sweep: 60 batches of 1-3 prompts with 0-3 images each (even grids up to 12x16 patches), random text
+    # runs between them, padded to the longest prompt on a random side
+    import random
+    rng = random.Random(1234)
+    sweep = []
+    for _ in range(60):
+        rows, grids = [], []
+        for _b in range(rng.randint(1, 3)):
+            toks = [rng.randint(1, 800) for _ in range(rng.randint(0, 6))]
+            for _i in range(rng.randint(0, 3)):
+                gh, gw = 2 * rng.randint(1, 6), 2 * rng.randint(1, 8)
+                grids.append([1, gh, gw])
+                toks += [902] + [900] * (gh * gw // 4) + [903] + [rng.randint(1, 800) for _ in range(rng.randint(0, 9))]
+            if not toks:
+                toks = [5]
+            rows.append(toks)
+        n = max(map(len, rows))
+        left = rng.random() < 0.5
+        ids = torch.tensor([([0] * (n - len(r)) + r) if left else (r + [0] * (n - len(r))) for r in rows])
+        mask = torch.tensor([([0] * (n - len(r)) + [1] * len(r)) if left else ([1] * len(r) + [0] * (n - len(r))) for r in rows])
+        grid = torch.tensor(grids) if grids else None
+        use_mask = not bool(mask.all()) or rng.random() < 0.5
+        pos, delta = ns["get_rope_index"](fake, ids, grid, None, None, mask if use_mask else None)
+        sweep.append(dict(input_ids=ids.to(torch.int16), image_grid_thw=grid, attention_mask=mask.to(torch.int8) if use_mask else None,
+                          position_ids=pos.to(torch.int16), deltas=delta.to(torch.int16)))
+    torch.save(sweep, HERE / "rope_index_sweep_ref.pt")
+    print("rope_index sweep:", len(sweep), "cases,", sum(c["image_grid_thw"] is not None for c in sweep), "with images,",
+          sum(c["attention_mask"] is not None for c in sweep), "with a mask")
 
 
 if __name__ == "__main__":

@@ -43,6 +43,23 @@ def test_get_rope_index_matches_reference_golden():
     assert p2[:, 0, 4 + 256].tolist() == [20, 20, 20]
 
 
+def test_get_rope_index_matches_the_references_function_on_a_random_sweep():
+    """60 random batches (1-3 prompts, 0-3 images each, random text runs, left or right padding, with and without an
+    attention mask) through the reference's own get_rope_index (tests/golden/make_golden.py::rope_index_golden ->
+    rope_index_sweep_ref.pt): positions and deltas must be identical."""
+    from pathlib import Path
+
+    from gpt_image_edit_b200.qwen2p5vl import get_rope_index
+
+    cases = torch.load(Path(__file__).parent / "golden" / "rope_index_sweep_ref.pt")
+    assert len(cases) == 60 and sum(c["attention_mask"] is not None for c in cases) >= 20
+    for i, c in enumerate(cases):
+        mask = None if c["attention_mask"] is None else c["attention_mask"].long()
+        pos, delta = get_rope_index(c["input_ids"].long(), c["image_grid_thw"], mask, image_token_id=900, vision_start_token_id=902)
+        assert torch.equal(pos, c["position_ids"].long()), i
+        assert torch.equal(delta.flatten(), c["deltas"].long().flatten()), i
+
+
 def test_text_only_positions():
     from gpt_image_edit_b200.qwen2p5vl import get_rope_index
 
