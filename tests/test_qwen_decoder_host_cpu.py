@@ -1,0 +1,170 @@
+"""Host orchestration of the Qwen2.5-VL decoder prefill (gpt_image_edit_b200/qwen2p5vl.py: B200Qwen2p5VL.forward /
+_decoder / _rope_tables / padding_spans) run on the CPU with TORCH DOUBLES in place of the libb2f kernels (`ops.*` is
+monkeypatched inside this test only; the product has no such path and raises on CPU tensors).  What this checks is the
+part that is Python: which rows each launch sees, the views and pitches handed to the attention call, the zeroed rows of
+a padded batch, M-RoPE tables, weight fusion order.  Checker: transformers' Qwen2_5_VLModel on the same weights.
+
+Padded batches follow transformers' flash_attention_2 semantics (the backend the reference selects, cli.py:40): a sequence
+attends to its own tokens only and a padding row receives a zero attention output, i.e. it only passes through the MLPs."""
+import types
+
+import pytest
+import torch
+
+hf = pytest.importorskip("transformers.models.qwen2_5_vl.modeling_qwen2_5_vl")
+BF = torch.bfloat16
+
+
+def _doubles():
+    from gpt_image_edit_b200 import ops
+
+    def rmsnorm(x, weight, *, out=None, eps=1e-6):
+        xf = x.float()
+        return (weight.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))).to(BF)
+
+    def linear(x, weight, bias=None, *, epilogue=ops.EPI_BIAS, out=None, resid=None, gate=None):
+        y = x.float() @ weight.float().t()
+        if bias is not None:
+            y = y + bias.float()
+        if epilogue == ops.EPI_RESID:
+            y = y + resid.float()
+        elif epilogue != ops.EPI_BIAS:
+            raise AssertionError(f"epilogue {epilogue} is not used by the decoder")
+        y = y.to(BF)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
+    def rope_half_(x, heads, head_pitch, cos, sin, *, fp32_math):
+        v = x[:, : heads * head_pitch].float().reshape(x.shape[0], heads, head_pitch)
+        half = head_pitch // 2
+        rot = torch.cat((-v[..., half:], v[..., :half]), dim=-1)
+        x[:, : heads * head_pitch] = (v * cos[:, None, :] + rot * sin[:, None, :]).reshape(x.shape[0], -1).to(BF)
+        return x
+
+    def attention(q, k, v, *, out=None, causal=False, scale=None, bias=None):
+        assert bias is None and q.stride(-1) == 1 and q.stride(2) == q.shape[3]          # what ops.attention requires
+        B, Sq, H, dh = q.shape
+        Skv, Hkv = k.shape[1], k.shape[2]
+        qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+        kf, vf = (t.repeat_interleave(H // Hkv, dim=1) for t in (kf, vf))
+        s = qf @ kf.transpose(-1, -2) * (scale or dh ** -0.5)
+        if causal:
+            s = s.masked_fill(torch.ones(Sq, Skv, dtype=torch.bool).triu(Skv - Sq + 1), float("-inf"))
+        o = (s.softmax(-1) @ vf).permute(0, 2, 1, 3).reshape(B, Sq, H * dh)
+        assert out.shape == o.shape
+        out.copy_(o.to(BF))
+        return out
+
+    def swiglu(gu, inter, *, out=None):
+        return (torch.nn.functional.silu(gu[:, :inter].float()) * gu[:, inter:2 * inter].float()).to(BF)
+
+    def gather_rows(table, idx, *, out=None):
+        return table[idx].clone()
+
+    return dict(rmsnorm=rmsnorm, linear=linear, rope_half_=rope_half_, attention=attention, swiglu=swiglu, gather_rows=gather_rows)
+
+
+@pytest.fixture()
+def engine(monkeypatch):
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLConfig
+
+    from gpt_image_edit_b200 import ops
+    from gpt_image_edit_b200.qwen2p5vl import B200Qwen2p5VL, QwenTextConfig, QwenVisionConfig
+
+    for name, fn in _doubles().items():
+        monkeypatch.setattr(ops, name, fn)
+    tc = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1, intermediate_size=512,
+              vocab_size=1000, rms_norm_eps=1e-6)
+    cfg = Qwen2_5_VLConfig(
+        text_config=dict(tc, rope_parameters=dict(rope_type="default", rope_theta=1e6, mrope_section=[16, 24, 24])),
+        vision_config=dict(depth=1, hidden_size=256, num_heads=4, intermediate_size=340, out_hidden_size=256,
+                           fullatt_block_indexes=[0]),
+        image_token_id=900, video_token_id=901, vision_start_token_id=902, vision_end_token_id=903)
+    torch.manual_seed(0)
+    ref = hf.Qwen2_5_VLModel(cfg).eval().float()
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+            p.copy_(p.to(BF).float())                        # both sides hold the same bf16-representable weights
+    lm = ref.language_model
+    me = types.SimpleNamespace(tc=QwenTextConfig(**tc, image_token_id=900, video_token_id=901, vision_start_token_id=902),
+                               vc=QwenVisionConfig(), thd=128, _dev=torch.device("cpu"), W={})
+    W = me.W
+    W["model.embed_tokens"] = lm.embed_tokens.weight.detach().to(BF)
+    for i, layer in enumerate(lm.layers):                    # the fused layout B200Qwen2p5VL.load_state_dict builds
+        p, a, m = f"model.layers.{i}.", layer.self_attn, layer.mlp
+        W[p + "ln1"], W[p + "ln2"] = layer.input_layernorm.weight.detach().to(BF), layer.post_attention_layernorm.weight.detach().to(BF)
+        W[p + "qkv.w"] = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight]).detach().to(BF)
+        W[p + "qkv.b"] = torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias]).detach().to(BF)
+        W[p + "o.w"] = a.o_proj.weight.detach().to(BF)
+        W[p + "gu.w"] = torch.cat([m.gate_proj.weight, m.up_proj.weight]).detach().to(BF)
+        W[p + "down.w"] = m.down_proj.weight.detach().to(BF)
+    W["model.norm"] = lm.norm.weight.detach().to(BF)
+    for name in ("_rope_tables", "_decoder"):
+        setattr(me, name, types.MethodType(getattr(B200Qwen2p5VL, name), me))
+    run = lambda ids, mask=None: B200Qwen2p5VL.forward(me, ids, attention_mask=mask)
+    return ref, run
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def _hf(ref, ids, mask=None):
+    from gpt_image_edit_b200.qwen2p5vl import get_rope_index
+    pos, _ = get_rope_index(ids, None, mask)
+    with torch.no_grad():
+        return ref(input_ids=ids, attention_mask=mask, position_ids=pos).last_hidden_state
+
+
+def test_unpadded_prefill_orchestration_matches_transformers(engine):
+    ref, run = engine
+    ids = torch.randint(1, 800, (2, 23), generator=torch.Generator().manual_seed(1))
+    h = run(ids)
+    assert h.shape == (2, 23, 256) and h.dtype == BF
+    assert _rel(h, _hf(ref, ids)) < 2e-2
+    assert _rel(run(ids, torch.ones_like(ids)), _hf(ref, ids)) < 2e-2              # an all-ones mask is the same path
+
+
+@pytest.mark.parametrize("side", ["right", "left"])
+def test_padded_batch_orchestration(engine, side):
+    ref, run = engine
+    g = torch.Generator().manual_seed(2)
+    rows = [torch.randint(1, 800, (n,), generator=g).tolist() for n in (19, 7, 12)]
+    n, PAD = 19, 3
+    pad = lambda r, fill: (r + [fill] * (n - len(r))) if side == "right" else ([fill] * (n - len(r)) + r)
+    ids = torch.tensor([pad(r, PAD) for r in rows])
+    mask = torch.tensor([pad([1] * len(r), 0) for r in rows])
+    h = run(ids, mask)
+    assert h.shape == (3, n, 256) and torch.isfinite(h.float()).all()
+    lm = ref.language_model
+    with torch.no_grad():
+        x = lm.embed_tokens(torch.tensor([PAD]))
+        for layer in lm.layers:                                   # a row whose attention output is zero
+            x = x + layer.mlp(layer.post_attention_layernorm(x))
+        pad_want = lm.norm(x)[0]
+    for b, r in enumerate(rows):
+        real = mask[b].bool()
+        alone = _hf(ref, torch.tensor([r]))[0]                    # the prompt on its own, no padding
+        assert _rel(h[b][real], alone) < 2e-2, (side, b)
+        for row in h[b][~real]:
+            assert _rel(row, pad_want) < 2e-2, (side, b)
+    if side == "right":                                           # transformers given the same mask agrees on the real tokens
+        full = _hf(ref, ids, mask)
+        for b in range(3):
+            assert _rel(h[b][mask[b].bool()], full[b][mask[b].bool()]) < 2e-2
+
+
+def test_padding_spans_and_refusals():
+    from gpt_image_edit_b200 import _lib
+    from gpt_image_edit_b200.qwen2p5vl import padding_spans
+
+    assert padding_spans(torch.tensor([[1, 1, 0, 0], [0, 1, 1, 1], [1, 1, 1, 1]])) == [(0, 2), (1, 4), (0, 4)]
+    for bad in ([[1, 0, 1, 1]], [[0, 0, 0, 0]]):
+        with pytest.raises(_lib.B2FError):
+            padding_spans(torch.tensor(bad))
+    with pytest.raises(_lib.B2FError):
+        padding_spans(torch.ones(4))
