@@ -75,19 +75,30 @@ def smart_resize(height: int, width: int, factor: int = IMAGE_FACTOR, min_pixels
 
 
 def fetch_image(ele: dict, size_factor: int = IMAGE_FACTOR):
-    """One {"type": "image", "image": path | PIL.Image, [min_pixels, max_pixels | resized_height, resized_width]}
-    content item -> RGB PIL image resized as qwen_vl_utils.fetch_image does (PIL's default bicubic)."""
+    """One {"type": "image", "image": path | file:// | http(s):// | data:image;base64, | PIL.Image, [min_pixels,
+    max_pixels | resized_height, resized_width]} content item -> RGB PIL image resized as qwen_vl_utils.fetch_image does
+    (PIL's default bicubic)."""
     from PIL import Image
 
     image = ele.get("image", ele.get("image_url"))
+    obj = None
     if isinstance(image, Image.Image):
         obj = image
+    elif isinstance(image, str) and image.startswith(("http://", "https://")):
+        import requests                                   # as qwen_vl_utils does; needs a network
+        from io import BytesIO
+        obj = Image.open(BytesIO(requests.get(image, stream=True).content))
     elif isinstance(image, str) and image.startswith("file://"):
         obj = Image.open(image[7:])
-    elif isinstance(image, str) and image.startswith(("http://", "https://", "data:image")):
-        raise ValueError("remote / inline images are not supported offline: pass a local path")
+    elif isinstance(image, str) and image.startswith("data:image"):
+        if "base64," in image:
+            import base64
+            from io import BytesIO
+            obj = Image.open(BytesIO(base64.b64decode(image.split("base64,", 1)[1])))
     else:
         obj = Image.open(image)
+    if obj is None:
+        raise ValueError(f"Unrecognized image input, support local path, http url, base64 and PIL.Image, got {image}")
     obj = obj.convert("RGB")
     if "resized_height" in ele and "resized_width" in ele:
         rh, rw = smart_resize(ele["resized_height"], ele["resized_width"], factor=size_factor)

@@ -119,3 +119,28 @@ def test_process_vision_info_matches_the_image_processors_own_resize(env):
         {"type": "image", "image": str(env.td / "a.png"), "min_pixels": 448 * 448, "max_pixels": 448 * 448}]}])
     assert vids is None and imgs[0].size == (532, 392)            # 420x300 scaled UP to the 448^2 budget (ceil), aspect kept; the image processor then floors to 504x364
     assert process_vision_info([{"role": "user", "content": [{"type": "text", "text": "hi"}]}]) == (None, None)
+
+
+def test_fetch_image_sources_of_qwen_vl_utils(tmp_path):
+    """qwen_vl_utils.fetch_image takes a PIL image, a local path, `file://`, a base64 `data:image` URI (and http urls, which
+    need a network): all must give the same resized RGB view."""
+    import base64
+    import io
+
+    import numpy as np
+    from PIL import Image
+
+    from gpt_image_edit_b200.image_io import fetch_image
+
+    im = Image.fromarray(np.random.default_rng(0).integers(0, 256, (60, 90, 3), dtype=np.uint8))
+    path = tmp_path / "a.png"
+    im.save(path)
+    buf = io.BytesIO()
+    im.save(buf, format="PNG")
+    budget = {"min_pixels": 448 * 448, "max_pixels": 448 * 448}
+    views = [fetch_image({"type": "image", "image": src, **budget}) for src in
+             (im, str(path), "file://" + str(path), "data:image;base64," + base64.b64encode(buf.getvalue()).decode())]
+    assert views[0].size == (560, 392) and views[0].mode == "RGB"                 # 28-multiples, ~448*448 pixels, aspect kept
+    assert all(np.array_equal(np.asarray(views[0]), np.asarray(v)) for v in views[1:])
+    with pytest.raises(ValueError, match="Unrecognized image input"):
+        fetch_image({"type": "image", "image": "data:image/png,not-base64"})
