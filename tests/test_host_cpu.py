@@ -592,3 +592,23 @@ def test_which_flux_layers_train_follows_the_reference_rule():
     from pathlib import Path
     conf = load_config(Path(__file__).parent.parent / "scripts" / "denoiser" / "flux_qwen2p5vl_7b_vlm_stage2_512_synthetic.yaml")
     assert trained_flux_layers(conf.model_config) == list(range(57))       # BASELINE.json configs[3] trains all 57 blocks
+
+
+def test_collate_pads_ragged_prompts_like_the_references_collator():
+    """univa/dataset/data_collator.py:113-121: pad_sequence with the pad token on the configured side, mask = ids != pad."""
+    from univa.training.synthetic_data import PAD_TOKEN_ID, SyntheticEditDataset, collate
+
+    a = SyntheticEditDataset(64, 64, seed=1, n_text=5)[0]
+    b = SyntheticEditDataset(64, 64, seed=1, n_text=9)[1]
+    la, lb = a["input_ids"].numel(), b["input_ids"].numel()
+    assert lb == la + 4
+    for side in ("right", "left"):
+        out = collate([a, b], padding_side=side)
+        ids, mask = out["input_ids"], out["attention_mask"]
+        assert ids.shape == (2, lb) and mask.dtype == torch.long and mask.sum().item() == la + lb
+        pad = slice(la, lb) if side == "right" else slice(0, 4)
+        assert torch.all(ids[0, pad] == PAD_TOKEN_ID) and torch.all(mask[0, pad] == 0) and torch.all(mask[1] == 1)
+        real = ids[0, :la] if side == "right" else ids[0, 4:]
+        assert torch.equal(real, a["input_ids"])
+    same = collate([a, a])
+    assert torch.equal(same["input_ids"], torch.stack([a["input_ids"]] * 2)) and bool(same["attention_mask"].all())

@@ -62,13 +62,19 @@ class SyntheticEditDataset(torch.utils.data.Dataset):
                     pixel_values=pix, image_grid_thw=grid[0], weights=weights, prompts="synthetic instruction")
 
 
-def collate(samples: list) -> dict:
-    """Targets of one size are stacked; targets of different sizes stay a LIST of [1, 3, H_i, W_i] tensors (and their
+PAD_TOKEN_ID = 151643          # Qwen2.5-VL's pad token (<|endoftext|>)
+
+
+def collate(samples: list, pad_token_id: int = PAD_TOKEN_ID, padding_side: str = "right") -> dict:
+    """The reference's DataCollator (univa/dataset/data_collator.py:76-156) for these samples: prompts of different
+    lengths are padded with the pad token on `padding_side` and `attention_mask = input_ids.ne(pad_token_id)` (:113-121);
+    targets of one size are stacked, targets of different sizes stay a LIST of [1, 3, H_i, W_i] tensors (and their
     area-mask weights a list of [1, 1, h_i, w_i]), which is what the reference's loop tests for (train_denoiser.py:907,
     :1120)."""
-    out = {}
-    for k in ("ref_pixel_values", "input_ids", "attention_mask"):
-        out[k] = torch.stack([s[k] for s in samples])
+    out = {"ref_pixel_values": torch.stack([s["ref_pixel_values"] for s in samples])}
+    out["input_ids"] = torch.nn.utils.rnn.pad_sequence([s["input_ids"] for s in samples], batch_first=True,
+                                                       padding_value=pad_token_id, padding_side=padding_side)
+    out["attention_mask"] = out["input_ids"].ne(pad_token_id).long()
     mixed = len({tuple(s["generated_image"].shape) for s in samples}) > 1
     for k in ("generated_image", "weights"):
         out[k] = [s[k][None] for s in samples] if mixed else torch.stack([s[k] for s in samples])
