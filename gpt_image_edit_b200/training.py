@@ -511,7 +511,7 @@ class Stage2Trainer:
 
     def lr_at(self, step: int) -> float:
         """The learning rate of optimizer step `step` (0-based) under diffusers' get_scheduler("constant" |
-        "constant_with_warmup" | "linear" | "cosine") as the reference builds it (:707-716): warm-up and total steps are both
+        "constant_with_warmup" | "linear" | "cosine" | "cosine_with_restarts" | "polynomial") as the reference builds it (:707-716): warm-up and total steps are both
         multiplied by the process count there because accelerate steps the scheduler once per process, so in optimizer steps
         the multiplier is step / warmup during the warm-up (0 for the very first update, as LambdaLR gives) and the named
         decay over max_train_steps after it."""
@@ -530,7 +530,17 @@ class Stage2Trainer:
             return base * max(0.0, 1.0 - prog)
         if name == "cosine":
             return base * max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(tc.lr_num_cycles) * 2.0 * prog)))
-        raise _lib.B2FError(f"lr_scheduler={name!r} is not built")
+        if name == "cosine_with_restarts":
+            if prog >= 1.0:
+                return 0.0
+            return base * max(0.0, 0.5 * (1.0 + math.cos(math.pi * ((float(tc.lr_num_cycles) * prog) % 1.0))))
+        if name == "polynomial":                                  # lr_end = 1e-7, power = lr_power (:715)
+            lr_end = 1e-7
+            if step > total:
+                return lr_end
+            return (base - lr_end) * (1.0 - prog) ** float(getattr(tc, "lr_power", 1.0)) + lr_end
+        raise _lib.B2FError(f"lr_scheduler={name!r} is not built (constant, constant_with_warmup, linear, cosine, "
+                            "cosine_with_restarts, polynomial are)")
 
     @torch.no_grad()
     def _vae_latents(self, image, generator=None):

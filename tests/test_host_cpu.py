@@ -386,7 +386,7 @@ def test_sigma_sampling_matches_the_reference_statements():
         assert torch.equal((1.0 - s4) * x + s4 * noise, c["noisy"]), c["name"]
 
 
-@pytest.mark.parametrize("name", ["constant", "constant_with_warmup", "linear", "cosine"])
+@pytest.mark.parametrize("name", ["constant", "constant_with_warmup", "linear", "cosine", "cosine_with_restarts", "polynomial"])
 def test_lr_schedule_follows_diffusers_get_scheduler(name):
     """Stage2Trainer.lr_at against the LambdaLR multipliers of diffusers.optimization.get_scheduler (third party, absent
     here: its published lambdas are restated below) driven the way the reference drives it (train_denoiser.py:707-716:
@@ -397,8 +397,9 @@ def test_lr_schedule_follows_diffusers_get_scheduler(name):
     import torch
     from gpt_image_edit_b200.training import Stage2Trainer
 
-    warm, total, procs, base, cycles = 5, 40, 8, 3e-4, 0.5
+    warm, total, procs, base, cycles = 5, 40, 8, 3e-4, (3 if name == "cosine_with_restarts" else 0.5)
     W, T = warm * procs, total * procs
+    power, lr_end = 2.0, 1e-7
 
     def lam(k):                     # k = scheduler steps taken so far
         if name == "constant":
@@ -410,12 +411,18 @@ def test_lr_schedule_follows_diffusers_get_scheduler(name):
         if name == "linear":
             return max(0.0, (T - k) / max(1, T - W))
         prog = (k - W) / max(1, T - W)
+        if name == "cosine_with_restarts":
+            return 0.0 if prog >= 1.0 else max(0.0, 0.5 * (1.0 + math.cos(math.pi * ((float(cycles) * prog) % 1.0))))
+        if name == "polynomial":
+            if k > T:
+                return lr_end / base
+            return ((base - lr_end) * (1 - (k - W) / (T - W)) ** power + lr_end) / base
         return max(0.0, 0.5 * (1.0 + math.cos(math.pi * cycles * 2.0 * prog)))
 
     opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=base)
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lam)
     me = SimpleNamespace(tc=SimpleNamespace(learning_rate=base, lr_warmup_steps=warm, max_train_steps=total, lr_scheduler=name,
-                                            lr_num_cycles=cycles))
+                                            lr_num_cycles=cycles, lr_power=power))
     for step in range(total):
         want = opt.param_groups[0]["lr"]            # the rate optimizer.step() number `step` runs with
         got = Stage2Trainer.lr_at(me, step)
