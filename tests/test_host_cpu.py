@@ -619,3 +619,43 @@ def test_collate_pads_ragged_prompts_like_the_references_collator():
         assert torch.equal(real, a["input_ids"])
     same = collate([a, a])
     assert torch.equal(same["input_ids"], torch.stack([a["input_ids"]] * 2)) and bool(same["attention_mask"].all())
+
+
+def test_settings_the_engine_cannot_honour_are_refused_not_ignored():
+    """train_denoiser.unsupported_settings: the synthetic stage-2 yaml is clean; the reference's own stage-2 yaml differs only
+    by its dataset (recorded in tests/golden/config_schema_ref.json); every knob that would change what is trained is named."""
+    import json
+    from pathlib import Path
+
+    import train_denoiser as td
+    from univa.training.configuration_denoise import from_mapping, load_config
+
+    root = Path(__file__).parent.parent
+    ours = load_config(root / "scripts" / "denoiser" / "flux_qwen2p5vl_7b_vlm_stage2_512_synthetic.yaml")
+    assert td.unsupported_settings(ours) == []
+    shipped = json.loads((root / "tests" / "golden" / "config_schema_ref.json").read_text())["yamls"]
+    # the yaml's own key / value pairs, without the keys its own schema rejects (mlp3 / siglip leftovers in the shipped files)
+    values = lambda rec: {sec: {k: v for k, v in rec[sec]["values"].items() if k not in rec[sec]["unknown"]} for sec in rec}
+    stage2 = values(next(v for k, v in shipped.items() if "stage2" in k))
+    bad = td.unsupported_settings(from_mapping(stage2))
+    assert len(bad) == 1 and bad[0].startswith("dataset_config.dataset_type")
+    stage1 = values(next(v for k, v in shipped.items() if "stage1" in k))  # MLP2 only: only_tune_image_branch=false is moot
+    assert [b.split("=")[0].split(":")[0] for b in td.unsupported_settings(from_mapping(stage1))] == [
+        "training_config.ema_deepspeed_config_file", "dataset_config.dataset_type"]          # stage 1 also runs the EMA engine
+    base = dict(training_config={}, model_config=dict(synthetic=True, flux_train_layer_idx=[0]),
+                dataset_config=dict(dataset_type="synthetic"))
+    def names(**over):
+        m = {k: dict(v) for k, v in base.items()}
+        for k, v in over.items():
+            sec, field = k.split("__")
+            m[sec][field] = v
+        return [b.split(":")[0].split("=")[0].split(" ")[0] for b in td.unsupported_settings(from_mapping(m))]
+    assert names() == []
+    assert names(training_config__mixed_precision="fp16") == ["training_config.mixed_precision"]
+    assert names(training_config__optimizer="prodigy") == ["training_config.optimizer"]
+    assert names(training_config__ema_deepspeed_config_file="zero3.json") == ["training_config.ema_deepspeed_config_file"]
+    assert names(training_config__drop_condition_rate=0.1, training_config__drop_t5_rate=0.5) == [
+        "training_config.drop_condition_rate", "training_config.drop_t5_rate"]
+    assert names(model_config__only_tune_image_branch=False) == ["model_config.only_tune_image_branch"]
+    assert names(model_config__only_tune_image_branch=False, model_config__only_tune_mlp2=True) == []   # stage 1: MLP2 only
+    assert names(model_config__vlm_residual_image_factor=0.3) == ["model_config.vlm_residual_image_factor"]

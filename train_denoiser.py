@@ -46,6 +46,36 @@ def build_models(conf, device):
     return model, pipe.vae, pipe, empty_pooled.to(torch.bfloat16)
 
 
+def unsupported_settings(conf) -> list:
+    """Settings of the reference's schema this engine would otherwise silently ignore: each is named with the reason, and
+    main() refuses to start rather than train something else than the yaml says."""
+    tc, dc, mc = conf.training_config, conf.dataset_config, conf.model_config
+    bad = []
+    if tc.mixed_precision != "bf16":
+        bad.append(f"training_config.mixed_precision={tc.mixed_precision!r}: the engine computes in bf16 with fp32 master "
+                   "weights and gradients (the reference's stage yamls use bf16)")
+    if tc.optimizer.lower() != "adamw":
+        bad.append(f"training_config.optimizer={tc.optimizer!r}: only AdamW is built")
+    if tc.ema_deepspeed_config_file is not None:
+        bad.append("training_config.ema_deepspeed_config_file: the EMA engine (univa/utils/create_ema.py) is out of scope; "
+                   "the stage-2 yaml leaves it unset")
+    if tc.drop_condition_rate:
+        bad.append("training_config.drop_condition_rate > 0: prompt dropping happens in the reference's dataset code "
+                   "(qwen2vl_dataset.py), which the synthetic triples replace")
+    if tc.drop_t5_rate != 1.0:
+        bad.append("training_config.drop_t5_rate < 1: needs the T5 embeddings of real captions; the stage yamls use 1.0")
+    if dc.dataset_type != "synthetic":
+        bad.append(f"dataset_config.dataset_type={dc.dataset_type!r}: only the synthetic triples of BASELINE.json configs[3] "
+                   "are available offline (the reference's dataset code is out of scope)")
+    if dc.ocr_enhancer:
+        bad.append("dataset_config.ocr_enhancer: needs the paddleocr service of univa/utils/get_ocr.py")
+    if mc.vlm_residual_image_factor:
+        bad.append("model_config.vlm_residual_image_factor > 0 is built for inference only (0.0 in every stage yaml)")
+    if not mc.only_tune_image_branch and not mc.only_tune_mlp2 and mc.flux_train_layer_idx is not None:
+        bad.append("model_config.only_tune_image_branch=false (FF / text-stream / single-block projection weights) is not built")
+    return bad
+
+
 def resolve_resume_checkpoint(tc, log=print):
     """(directory | None, global step it was written at) for `training_config.resume_from_checkpoint`, by the reference's
     rule (train_denoiser.py:347-374): "latest" picks the `checkpoint-<step>` directory of `output_dir` with the largest
@@ -148,9 +178,12 @@ def main(conf):
     torch.cuda.set_device(device)
     D.init_from_env(device=device)
     torch.manual_seed(tc.seed + rank)                                  # set_seed(seed, device_specific=True) (:290)
-    if dc.dataset_type != "synthetic":
-        raise SystemExit(f"dataset_type={dc.dataset_type!r}: only the synthetic triples of BASELINE.json configs[3] are "
-                         "available offline (the reference's dataset code is out of scope)")
+    bad = unsupported_settings(conf)
+    if bad:
+        raise SystemExit("train_denoiser.py cannot honour this configuration:\n  - " + "\n  - ".join(bad))
+    if tc.profile_out_dir is not None and rank == 0:
+        print("profile_out_dir is ignored: use libb2f's CUDA-event profiler (bench.py --workload train512) or ncu "
+              "(scripts/profile_train.py)", flush=True)
     model, vae, pipe, empty_pooled = build_models(conf, device)
     if world > 1:      # every rank starts from rank 0's weights (DeepSpeed broadcasts parameters at initialize())
         D.broadcast_weights(list(model.denoise_tower.denoiser._store.values()) +
