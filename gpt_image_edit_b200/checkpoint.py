@@ -160,9 +160,10 @@ def univa_config_kwargs(raw: dict) -> dict:
     return kw
 
 
-def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_pixels=448 * 448):
+def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_pixels=448 * 448, task_head: bool = True):
     """-> (UnivaQwen2p5VLForConditionalGeneration, task_head, processor) from a Univa checkpoint directory
-    (reference cli.py:30-56)."""
+    (reference cli.py:30-56).  `task_head=False` is the eval drivers' load (gedit/step1_gen_samples.py:45-56: model and
+    processor only; no `task_head_final.pt` is read) and returns None in its place."""
     from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig, UnivaQwen2p5VLForConditionalGeneration
     from univa.serve.cli import TaskHead
 
@@ -183,6 +184,8 @@ def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_p
                                                   if k.startswith("denoise_tower.denoiser.")})
     model.denoise_tower.denoise_projector.load_state_dict({k[len("denoise_tower.denoise_projector."):]: v for k, v in sd.items()
                                                            if k.startswith("denoise_tower.denoise_projector.")})
+    if not task_head:
+        return model, None, processor
     head = TaskHead(cfg.hidden_size, device=device)
     th = root / "task_head_final.pt"
     if not th.exists():      # the reference's torch.load (cli.py:49) fails here; a zero head would answer every turn with text

@@ -30,7 +30,8 @@ def build_models(conf, device):
     from univa.serve import cli
 
     mc = conf.model_config
-    model, _, _ = cli.load_main_model_and_processor(mc.pretrained_lvlm_name_or_path, device, mc.synthetic, mc.small)
+    model, _, _ = cli.load_main_model_and_processor(mc.pretrained_lvlm_name_or_path, device, mc.synthetic, mc.small,
+                                                     task_head=False)        # the training script has no task head
     pipe, tokenizers, text_encoders = cli.load_pipe(model.denoise_tower.denoiser, mc.pretrained_denoiser_name_or_path, device,
                                                     mc.synthetic, mc.small)
     if mc.pretrained_mlp2_path:

@@ -86,7 +86,7 @@ def main(args: EvalConfig):
     np.random.seed(D.rank_seed(args.seed, rank))
     torch.manual_seed(D.rank_seed(args.seed, rank))                           # CPU and every CUDA device
     model, _, processor = cli.load_main_model_and_processor(args.pretrained_lvlm_name_or_path, device, args.synthetic, args.small,
-                                                            min_pixels=args.min_pixels, max_pixels=args.max_pixels)   # :50-54
+                                                            min_pixels=args.min_pixels, max_pixels=args.max_pixels, task_head=False)   # :45-56
     pipe, tokenizers, text_encoders = cli.load_pipe(model.denoise_tower.denoiser, args.pretrained_denoiser_name_or_path, device,
                                                     args.synthetic, args.small)
     state = dict(model=model, pipe=pipe, tokenizers=tokenizers, text_encoders=text_encoders, device=device, processor=processor)

@@ -61,11 +61,12 @@ class TaskHead(torch.nn.Module):
 
 
 def load_main_model_and_processor(model_path, device, synthetic=False, small=False, min_pixels=448 * 448,
-                                  max_pixels=448 * 448, **config_overrides):
-    """-> (model, task_head, processor)  (reference cli.py:30-56).  processor is None only with --synthetic."""
+                                  max_pixels=448 * 448, task_head: bool = True, **config_overrides):
+    """-> (model, task_head, processor)  (reference cli.py:30-56).  processor is None only with --synthetic;
+    `task_head=False` (eval drivers, training) does not read `task_head_final.pt`."""
     if not synthetic:
         from gpt_image_edit_b200.checkpoint import load_univa_checkpoint
-        return load_univa_checkpoint(model_path, device, min_pixels=min_pixels, max_pixels=max_pixels)
+        return load_univa_checkpoint(model_path, device, min_pixels=min_pixels, max_pixels=max_pixels, task_head=task_head)
     kw = {}
     if small:  # plumbing runs: a few layers at full width
         kw = dict(text_config=dict(num_hidden_layers=2), vision_config=dict(depth=2, fullatt_block_indexes=(1,)),
