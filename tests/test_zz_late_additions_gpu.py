@@ -13,7 +13,7 @@ import torch
 
 from test_qwen_gpu import IMG, VSTART, _models, _rel_l2
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
               pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first GPU run pending")]
 
 
