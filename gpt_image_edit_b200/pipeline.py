@@ -458,6 +458,8 @@ class FluxKontextPipeline:
         if self.transformer.config.guidance_embeds:
             guidance = torch.full([1], guidance_scale, device=device, dtype=torch.float32).expand(B)
 
+        if self._joint_attention_kwargs is None:         # reference :1022-1023
+            self._joint_attention_kwargs = {}
         jak = dict(joint_attention_kwargs or {})
         hoist = hasattr(self.transformer, "prepare_schedule")
         if hoist:
