@@ -659,3 +659,63 @@ def test_settings_the_engine_cannot_honour_are_refused_not_ignored():
     assert names(model_config__only_tune_image_branch=False) == ["model_config.only_tune_image_branch"]
     assert names(model_config__only_tune_image_branch=False, model_config__only_tune_mlp2=True) == []   # stage 1: MLP2 only
     assert names(model_config__vlm_residual_image_factor=0.3) == ["model_config.vlm_residual_image_factor"]
+
+
+def test_univa_checkpoint_assembly_from_qwen_and_flux_directories(tmp_path):
+    """scripts/make_univa_qwen2p5vl_weight.py (reference scripts/make_univa_qwen2p5vl_weight.py:35-76): Qwen2.5-VL tensors under
+    their own names, FLUX under `denoise_tower.denoiser.`, a fresh MLP2, the merged config.json and the processor files — the
+    directory layout gpt_image_edit_b200.checkpoint.load_univa_checkpoint reads."""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    from safetensors.torch import save_file
+
+    from gpt_image_edit_b200.checkpoint import PROCESSOR_FILES, load_state_dict_from_dir, univa_config_kwargs
+    from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig
+
+    spec = importlib.util.spec_from_file_location("mk", Path(__file__).parent.parent / "scripts" / "make_univa_qwen2p5vl_weight.py")
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = torch.Generator().manual_seed(0)
+    q, f = tmp_path / "qwen", tmp_path / "flux" / "transformer"
+    q.mkdir()
+    f.mkdir(parents=True)
+    qsd = {"visual.patch_embed.proj.weight": torch.randn(8, 12, generator=g), "model.embed_tokens.weight": torch.randn(50, 16, generator=g),
+           "model.layers.0.self_attn.q_proj.weight": torch.randn(16, 16, generator=g), "lm_head.weight": torch.randn(50, 16, generator=g)}
+    save_file({k: v for k, v in list(qsd.items())[:2]}, str(q / "model-00001-of-00002.safetensors"))
+    save_file({k: v for k, v in list(qsd.items())[2:]}, str(q / "model-00002-of-00002.safetensors"))
+    (q / "config.json").write_text(json.dumps({"model_type": "qwen2_5_vl", "hidden_size": 16, "num_hidden_layers": 1,
+                                               "num_attention_heads": 2, "num_key_value_heads": 1, "intermediate_size": 32,
+                                               "vocab_size": 50, "initializer_range": 0.02, "image_token_id": 45,
+                                               "vision_config": {"depth": 1, "hidden_size": 8, "out_hidden_size": 16}}))
+    (q / "tokenizer_config.json").write_text("{}")
+    (q / "preprocessor_config.json").write_text("{}")
+    fsd = {"transformer_blocks.0.attn.to_q.weight": torch.randn(4, 4, generator=g), "proj_out.bias": torch.randn(4, generator=g)}
+    save_file(fsd, str(f / "diffusion_pytorch_model.safetensors"))
+    (f / "config.json").write_text(json.dumps({"_class_name": "FluxTransformer2DModel", "num_layers": 1, "num_single_layers": 1,
+                                               "guidance_embeds": True}))
+    out = tmp_path / "univa"
+    info = mk.assemble(q, f.parent, out, dtype=torch.bfloat16, seed=3, max_shard_bytes=2000, log=lambda *_: None)
+    sd = load_state_dict_from_dir(out)
+    want = set(qsd) | {"denoise_tower.denoiser." + k for k in fsd} | {f"denoise_tower.denoise_projector.{i}.{p}"
+                                                                      for i in (0, 2) for p in ("weight", "bias")}
+    assert set(sd) == want and info["tensors"] == len(want) and len(info["shards"]) > 1
+    assert all(t.dtype == torch.bfloat16 for t in sd.values())
+    assert torch.equal(sd["model.embed_tokens.weight"], qsd["model.embed_tokens.weight"].bfloat16())
+    assert torch.equal(sd["denoise_tower.denoiser.proj_out.bias"], fsd["proj_out.bias"].bfloat16())
+    assert sd["denoise_tower.denoise_projector.0.weight"].shape == (3 * 4096, 16)          # Linear(hidden, 3 * 4096)
+    assert sd["denoise_tower.denoise_projector.2.weight"].shape == (4096, 3 * 4096)
+    assert float(sd["denoise_tower.denoise_projector.2.bias"].abs().max()) == 0
+    assert abs(float(sd["denoise_tower.denoise_projector.0.weight"].float().std()) - 0.02) < 2e-3
+    index = json.loads((out / "model.safetensors.index.json").read_text())
+    assert set(index["weight_map"]) == want and set(index["weight_map"].values()) == set(info["shards"])
+    cfg = json.loads((out / "config.json").read_text())
+    assert cfg["model_type"] == "univa_qwen2p5vl" and cfg["architectures"] == ["UnivaQwen2p5VLForConditionalGeneration"]
+    assert cfg["denoise_tower"]["input_hidden_size"] == 16 and cfg["denoise_tower"]["denoiser_config"]["num_single_layers"] == 1
+    ucfg = UnivaQwen2p5VLConfig(**univa_config_kwargs(cfg))                                 # what the loader builds from it
+    assert ucfg.hidden_size == 16 and ucfg.image_token_id == 45 and ucfg.denoise_tower.output_hidden_size == 4096
+    assert ucfg.denoise_tower.denoiser_config["guidance_embeds"] is True
+    assert any((out / n).exists() for n in PROCESSOR_FILES) and (out / "preprocessor_config.json").exists()
+    with pytest.raises(KeyError):                                                            # not a plain Qwen2.5-VL directory
+        mk.assemble(out, f.parent, tmp_path / "again", log=lambda *_: None)
