@@ -45,6 +45,75 @@ def save_state_dict(sd: dict, directory, filename: str = "diffusion_pytorch_mode
     save_file({prefix + k: v.detach().cpu().contiguous() for k, v in sd.items()}, str(Path(directory) / filename))
 
 
+class ShardWriter:
+    """Writes tensors to `model.safetensors`, or `model-0000i-of-0000n.safetensors` + `model.safetensors.index.json` when more
+    than `max_bytes` accumulate (the layout `save_pretrained` produces and `from_pretrained` / iter_safetensors read)."""
+
+    def __init__(self, out, max_bytes: int = 5 << 30):
+        self.out, self.max_bytes, self.cur, self.cur_bytes, self.shards, self.total = Path(out), max_bytes, {}, 0, [], 0
+        self.out.mkdir(parents=True, exist_ok=True)
+
+    def add(self, name: str, t: torch.Tensor):
+        n = t.numel() * t.element_size()
+        if self.cur and self.cur_bytes + n > self.max_bytes:
+            self.flush()
+        self.cur[name] = t.detach().cpu().contiguous()
+        self.cur_bytes += n
+        self.total += n
+
+    def flush(self):
+        if self.cur:
+            tmp = self.out / f"model-tmp-{len(self.shards):05d}.safetensors"
+            save_file(self.cur, str(tmp), metadata={"format": "pt"})
+            self.shards.append((tmp, list(self.cur)))
+            self.cur, self.cur_bytes = {}, 0
+
+    def close(self) -> dict:
+        self.flush()
+        n = len(self.shards)
+        weight_map = {}
+        for i, (tmp, names) in enumerate(self.shards):
+            final = "model.safetensors" if n == 1 else f"model-{i + 1:05d}-of-{n:05d}.safetensors"
+            tmp.rename(self.out / final)
+            weight_map.update({k: final for k in names})
+        if n > 1:
+            (self.out / "model.safetensors.index.json").write_text(
+                json.dumps({"metadata": {"total_size": self.total}, "weight_map": weight_map}, indent=2))
+        return weight_map
+
+
+CHECKPOINT_SIDE_FILES = ("config.json", "generation_config.json", "tokenizer.json", "tokenizer_config.json", "vocab.json",
+                         "merges.txt", "added_tokens.json", "special_tokens_map.json", "preprocessor_config.json",
+                         "processor_config.json", "chat_template.json", "chat_template.jinja", "task_head_final.pt")
+
+
+def rewrite_checkpoint(src, dst, updates: dict, max_shard_bytes: int = 5 << 30) -> dict:
+    """A copy of the checkpoint directory `src` at `dst` in which the tensors named in `updates` carry their new values
+    (cast to the stored dtype): what `save_pretrained(checkpoint-N/univa)` + `processor.save_pretrained` leave after a
+    training step in the reference (train_denoiser.py:489-498) — a directory `from_pretrained` / load_univa_checkpoint reads
+    — produced by streaming the source shards instead of serialising a second copy of the model.  Every update must name a
+    tensor of the source.  Returns {name: shard file}."""
+    src, dst = Path(src), Path(dst)
+    w = ShardWriter(dst, max_shard_bytes)
+    seen = set()
+    for k, t in iter_safetensors(src):
+        if k in updates:
+            u = updates[k]
+            if tuple(u.shape) != tuple(t.shape):
+                raise ValueError(f"{k}: the update has shape {tuple(u.shape)}, the checkpoint {tuple(t.shape)}")
+            t = u.detach().to("cpu", t.dtype)
+            seen.add(k)
+        w.add(k, t)
+    missing = sorted(set(updates) - seen)
+    if missing:
+        raise KeyError(f"{src} has no tensors named {missing[:4]} ({len(missing)} updates without a home)")
+    weight_map = w.close()
+    for name in CHECKPOINT_SIDE_FILES:
+        if (src / name).exists():
+            (dst / name).write_bytes((src / name).read_bytes())
+    return weight_map
+
+
 def load_pipeline_components(flux_path, device="cuda"):
     """-> (vae, scheduler) for FluxKontextPipeline.from_pretrained."""
     from .vae import B200AutoencoderKL, VaeConfig

@@ -27,9 +27,13 @@ import json
 import shutil
 from pathlib import Path
 
+import sys
+
 import torch
 from safetensors import safe_open
-from safetensors.torch import save_file
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from gpt_image_edit_b200.checkpoint import ShardWriter  # noqa: E402
 
 PROCESSOR_FILES = ("tokenizer.json", "tokenizer_config.json", "vocab.json", "merges.txt", "added_tokens.json",
                    "special_tokens_map.json", "preprocessor_config.json", "processor_config.json", "chat_template.json",
@@ -45,41 +49,6 @@ def iter_tensors(directory: Path):
         with safe_open(str(f), framework="pt", device="cpu") as sf:
             for k in sf.keys():
                 yield k, sf.get_tensor(k)
-
-
-class ShardWriter:
-    """model-0000i-of-0000n.safetensors + model.safetensors.index.json, at most `max_bytes` per shard."""
-
-    def __init__(self, out: Path, max_bytes: int):
-        self.out, self.max_bytes, self.cur, self.cur_bytes, self.shards, self.total = Path(out), max_bytes, {}, 0, [], 0
-
-    def add(self, name: str, t: torch.Tensor):
-        n = t.numel() * t.element_size()
-        if self.cur and self.cur_bytes + n > self.max_bytes:
-            self.flush()
-        self.cur[name] = t.contiguous()
-        self.cur_bytes += n
-        self.total += n
-
-    def flush(self):
-        if self.cur:
-            tmp = self.out / f"model-tmp-{len(self.shards):05d}.safetensors"
-            save_file(self.cur, str(tmp), metadata={"format": "pt"})
-            self.shards.append((tmp, list(self.cur)))
-            self.cur, self.cur_bytes = {}, 0
-
-    def close(self):
-        self.flush()
-        n = len(self.shards)
-        weight_map = {}
-        for i, (tmp, names) in enumerate(self.shards):
-            final = "model.safetensors" if n == 1 else f"model-{i + 1:05d}-of-{n:05d}.safetensors"
-            tmp.rename(self.out / final)
-            weight_map.update({k: final for k in names})
-        if n > 1:
-            (self.out / "model.safetensors.index.json").write_text(
-                json.dumps({"metadata": {"total_size": self.total}, "weight_map": weight_map}, indent=2))
-        return weight_map
 
 
 def univa_config(qwen_cfg: dict, flux_cfg: dict) -> dict:

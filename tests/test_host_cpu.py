@@ -719,3 +719,48 @@ def test_univa_checkpoint_assembly_from_qwen_and_flux_directories(tmp_path):
     assert any((out / n).exists() for n in PROCESSOR_FILES) and (out / "preprocessor_config.json").exists()
     with pytest.raises(KeyError):                                                            # not a plain Qwen2.5-VL directory
         mk.assemble(out, f.parent, tmp_path / "again", log=lambda *_: None)
+
+
+def test_training_checkpoint_writes_a_loadable_univa_directory(tmp_path):
+    """train_denoiser.write_univa_directory / checkpoint.rewrite_checkpoint (reference save hook, train_denoiser.py:489-498:
+    `save_pretrained(checkpoint-N/univa)` + the processor files): trained tensors replaced, everything else byte-identical to
+    the source checkpoint, side files carried along; a synthetic run writes no such directory."""
+    import json
+    from types import SimpleNamespace
+
+    from safetensors.torch import save_file
+
+    import train_denoiser as td
+    from gpt_image_edit_b200.checkpoint import load_state_dict_from_dir, rewrite_checkpoint
+
+    g = torch.Generator().manual_seed(1)
+    src = tmp_path / "src"
+    src.mkdir()
+    sd = {"model.embed_tokens.weight": torch.randn(10, 4, generator=g).bfloat16(),
+          "denoise_tower.denoiser.transformer_blocks.0.attn.to_q.weight": torch.randn(4, 4, generator=g).bfloat16(),
+          "denoise_tower.denoiser.transformer_blocks.0.ff.net.2.weight": torch.randn(4, 4, generator=g).bfloat16(),
+          "denoise_tower.denoise_projector.0.weight": torch.randn(6, 4, generator=g).bfloat16()}
+    save_file({k: sd[k] for k in list(sd)[:2]}, str(src / "model-00001-of-00002.safetensors"))
+    save_file({k: sd[k] for k in list(sd)[2:]}, str(src / "model-00002-of-00002.safetensors"))
+    (src / "config.json").write_text(json.dumps({"model_type": "univa_qwen2p5vl"}))
+    (src / "tokenizer_config.json").write_text("{}")
+    trained = {"transformer_blocks.0.attn.to_q.weight": torch.full((4, 4), 2.0)}                    # fp32 in, stored dtype out
+    proj = {"denoise_tower.denoise_projector.0.weight": torch.full((6, 4), -1.0)}
+    mc = SimpleNamespace(pretrained_lvlm_name_or_path=str(src), synthetic=False)
+    out = td.write_univa_directory(mc, tmp_path / "checkpoint-5", trained, proj, log=lambda *_: None)
+    assert out == tmp_path / "checkpoint-5" / "univa"
+    got = load_state_dict_from_dir(out)
+    assert set(got) == set(sd) and all(got[k].dtype == torch.bfloat16 for k in got)
+    assert torch.all(got["denoise_tower.denoiser.transformer_blocks.0.attn.to_q.weight"] == 2.0)
+    assert torch.all(got["denoise_tower.denoise_projector.0.weight"] == -1.0)
+    for frozen in ("model.embed_tokens.weight", "denoise_tower.denoiser.transformer_blocks.0.ff.net.2.weight"):
+        assert torch.equal(got[frozen], sd[frozen])
+    assert json.loads((out / "config.json").read_text())["model_type"] == "univa_qwen2p5vl" and (out / "tokenizer_config.json").exists()
+    assert td.write_univa_directory(SimpleNamespace(pretrained_lvlm_name_or_path=str(src), synthetic=True), tmp_path / "c2", trained,
+                                    proj) is None
+    assert td.write_univa_directory(SimpleNamespace(pretrained_lvlm_name_or_path="", synthetic=False), tmp_path / "c3", trained,
+                                    proj) is None
+    with pytest.raises(KeyError):                # a trained tensor the source does not have
+        rewrite_checkpoint(src, tmp_path / "bad", {"denoise_tower.denoiser.nope": torch.zeros(1)})
+    with pytest.raises(ValueError):              # or has with another shape
+        rewrite_checkpoint(src, tmp_path / "bad2", {"model.embed_tokens.weight": torch.zeros(3, 3)})

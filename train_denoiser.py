@@ -122,6 +122,24 @@ def prune_checkpoints(output_dir, limit, log=print):
     return removing
 
 
+def write_univa_directory(mc, save: Path, trained: dict, proj: dict, log=print):
+    """checkpoint-N/univa/: the whole model as a directory `from_pretrained` (and `univa.serve.cli --model_path`) reads, which
+    the reference's save hook writes with `save_pretrained` + `processor.save_pretrained` (train_denoiser.py:489-498).  Here
+    it is the source checkpoint (`pretrained_lvlm_name_or_path`) re-streamed with the trained tensors replaced — the frozen
+    Qwen2.5-VL / FLUX tensors are byte-identical to the source.  A synthetic run has no source directory and writes none
+    (its trained tensors are in `denoiser_trainable/` and `denoise_projector.bin`).  -> the directory or None."""
+    from gpt_image_edit_b200 import checkpoint as ck
+
+    src = Path(mc.pretrained_lvlm_name_or_path or "")
+    if mc.synthetic or not (src.is_dir() and any(src.glob("*.safetensors"))):
+        return None
+    updates = {"denoise_tower.denoiser." + k: v for k, v in trained.items()}
+    updates.update(proj)
+    ck.rewrite_checkpoint(src, save / "univa", updates)
+    log(f"Saved the model to {save / 'univa'} ({len(updates)} trained tensors over {src})")
+    return save / "univa"
+
+
 def load_checkpoint(path: Path, trainer, rank: int, device):
     """accelerator.load_state (:769) for this engine: the rank's optimizer partition — which also restores the bf16
     weights the model computes with (ShardedAdamW.load_state_dict) — and the rank's random streams."""
@@ -154,10 +172,12 @@ def save_checkpoint(conf, trainer, model, step: int, rank: int, world: int):
                                      conf.model_config.only_tune_image_branch)
         trained = {k: v for k, v in den.items() if check_param_is_in_components("denoise_tower.denoiser." + k, comps)}
         ck.save_state_dict(trained, save / "denoiser_trainable")
+        proj = {}
         if conf.model_config.only_tune_mlp2 or conf.model_config.with_tune_mlp2:
             proj = {f"denoise_tower.denoise_projector.{k}": v.cpu() for k, v in
                     model.denoise_tower.denoise_projector.state_dict().items()}
             torch.save(proj, save / "denoise_projector.bin")
+        write_univa_directory(conf.model_config, save, trained, proj)
         (save / "trainer_state.json").write_text(json.dumps({"global_step": step, "world_size": world}))
     torch.save(trainer.opt.state_dict(), save / f"optimizer_rank{rank}.pt")
     gen = getattr(trainer, "gen", None)
