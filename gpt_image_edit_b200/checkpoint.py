@@ -57,7 +57,7 @@ class ShardWriter:
         n = t.numel() * t.element_size()
         if self.cur and self.cur_bytes + n > self.max_bytes:
             self.flush()
-        self.cur[name] = t.detach().cpu().contiguous()
+        self.cur[name] = t.detach().to("cpu", copy=True).contiguous()       # an owned copy: safetensors refuses shared storage
         self.cur_bytes += n
         self.total += n
 
@@ -229,15 +229,56 @@ def univa_config_kwargs(raw: dict) -> dict:
     return kw
 
 
+def univa_state_dict(model) -> dict:
+    """Every tensor of a Univa model under its checkpoint name (the keys `save_pretrained` writes in the reference)."""
+    sd = dict(model.lvlm.state_dict())
+    sd.update({"denoise_tower.denoiser." + k: v for k, v in model.denoise_tower.denoiser.state_dict().items()})
+    proj = getattr(model.denoise_tower, "denoise_projector", None)
+    if proj is not None:
+        sd.update({"denoise_tower.denoise_projector." + k: v for k, v in proj.state_dict().items()})
+    return sd
+
+
+def save_univa_model(model, save_directory, max_shard_bytes: int = 5 << 30) -> dict:
+    """safetensors shards + config.json of a Univa model (`UnivaQwen2p5VLForConditionalGeneration.save_pretrained`)."""
+    out = Path(save_directory)
+    w = ShardWriter(out, max_shard_bytes)
+    for k, v in univa_state_dict(model).items():
+        w.add(k, v)
+    weight_map = w.close()
+    (out / "config.json").write_text(json.dumps(model.config.to_dict(), indent=2))
+    return weight_map
+
+
+def load_univa_model(model_path, device="cuda"):
+    """UnivaQwen2p5VLForConditionalGeneration from a checkpoint directory (config.json + safetensors shards)."""
+    return _load_univa_model(Path(model_path), device)[0]
+
+
 def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_pixels=448 * 448, task_head: bool = True):
     """-> (UnivaQwen2p5VLForConditionalGeneration, task_head, processor) from a Univa checkpoint directory
     (reference cli.py:30-56).  `task_head=False` is the eval drivers' load (gedit/step1_gen_samples.py:45-56: model and
     processor only; no `task_head_final.pt` is read) and returns None in its place."""
-    from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig, UnivaQwen2p5VLForConditionalGeneration
     from univa.serve.cli import TaskHead
 
     root = Path(model_path)
     processor = load_processor(root, min_pixels, max_pixels)
+    model, cfg = _load_univa_model(root, device)
+    if not task_head:
+        return model, None, processor
+    head = TaskHead(cfg.hidden_size, device=device)
+    th = root / "task_head_final.pt"
+    if not th.exists():      # the reference's torch.load (cli.py:49) fails here; a zero head would answer every turn with text
+        raise FileNotFoundError(f"{th}: the generate / understand router of the Univa checkpoint is missing")
+    t = torch.load(th, map_location="cpu")
+    head.w0.copy_(t["0.weight"]); head.b0.copy_(t["0.bias"])
+    head.w3[:2].copy_(t["3.weight"]); head.b3[:2].copy_(t["3.bias"])
+    return model, head, processor
+
+
+def _load_univa_model(root: Path, device):
+    from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig, UnivaQwen2p5VLForConditionalGeneration
+
     raw = json.loads((root / "config.json").read_text()) if (root / "config.json").exists() else {}
     cfg = UnivaQwen2p5VLConfig(**univa_config_kwargs(raw))
     model = UnivaQwen2p5VLForConditionalGeneration(cfg, device=device)
@@ -253,13 +294,4 @@ def load_univa_checkpoint(model_path, device="cuda", min_pixels=448 * 448, max_p
                                                   if k.startswith("denoise_tower.denoiser.")})
     model.denoise_tower.denoise_projector.load_state_dict({k[len("denoise_tower.denoise_projector."):]: v for k, v in sd.items()
                                                            if k.startswith("denoise_tower.denoise_projector.")})
-    if not task_head:
-        return model, None, processor
-    head = TaskHead(cfg.hidden_size, device=device)
-    th = root / "task_head_final.pt"
-    if not th.exists():      # the reference's torch.load (cli.py:49) fails here; a zero head would answer every turn with text
-        raise FileNotFoundError(f"{th}: the generate / understand router of the Univa checkpoint is missing")
-    t = torch.load(th, map_location="cpu")
-    head.w0.copy_(t["0.weight"]); head.b0.copy_(t["0.bias"])
-    head.w3[:2].copy_(t["3.weight"]); head.b3[:2].copy_(t["3.bias"])
-    return model, head, processor
+    return model, cfg

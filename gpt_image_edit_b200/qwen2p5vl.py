@@ -161,28 +161,37 @@ class B200Qwen2p5VL(torch.nn.Module):
             raise _lib.B2FError("B200Qwen2p5VL lives on a CUDA device; there is no CPU path")
         self._dev = dev
         tc, vc = self.tc, self.vc
-        z = lambda *s: torch.zeros(s, device=dev, dtype=torch.bfloat16)
-        o = lambda *s: torch.ones(s, device=dev, dtype=torch.bfloat16)
         self.vhd = vc.hidden_size // vc.num_heads           # 80
         self.vi = _pad8(vc.intermediate_size)                # 3424
-        HPv = vc.num_heads * self.HP
+        self.thd = tc.hidden_size // tc.num_attention_heads
+        W = self.W = self.alloc_weights(tc, vc, dev)
+        for k, t in W.items():
+            self.register_buffer("w__" + k.replace(".", "__"), t, persistent=False)
+
+    @classmethod
+    def alloc_weights(cls, tc, vc, dev) -> "OrderedDict[str, torch.Tensor]":
+        """Zeroed weight storage in kernel layout (fused q|k|v and gate|up, vision heads padded 80 -> 128, padded MLP width)."""
+        z = lambda *s: torch.zeros(s, device=dev, dtype=torch.bfloat16)
+        o = lambda *s: torch.ones(s, device=dev, dtype=torch.bfloat16)
+        vi = _pad8(vc.intermediate_size)
+        HPv = vc.num_heads * cls.HP
         pe_in = vc.in_channels * vc.temporal_patch_size * vc.patch_size ** 2
-        W = self.W = OrderedDict()
+        W = OrderedDict()
         W["visual.patch_embed"] = z(vc.hidden_size, pe_in)
         for i in range(vc.depth):
             p = f"visual.blocks.{i}."
             W[p + "norm1"], W[p + "norm2"] = o(vc.hidden_size), o(vc.hidden_size)
             W[p + "qkv.w"], W[p + "qkv.b"] = z(3 * HPv, vc.hidden_size), z(3 * HPv)
             W[p + "proj.w"], W[p + "proj.b"] = z(vc.hidden_size, HPv), z(vc.hidden_size)
-            W[p + "gu.w"], W[p + "gu.b"] = z(2 * self.vi, vc.hidden_size), z(2 * self.vi)
-            W[p + "down.w"], W[p + "down.b"] = z(vc.hidden_size, self.vi), z(vc.hidden_size)
+            W[p + "gu.w"], W[p + "gu.b"] = z(2 * vi, vc.hidden_size), z(2 * vi)
+            W[p + "down.w"], W[p + "down.b"] = z(vc.hidden_size, vi), z(vc.hidden_size)
         mh = vc.hidden_size * vc.spatial_merge_size ** 2
         W["visual.merger.ln_q"] = o(vc.hidden_size)
         W["visual.merger.0.w"], W["visual.merger.0.b"] = z(mh, mh), z(mh)
         W["visual.merger.2.w"], W["visual.merger.2.b"] = z(vc.out_hidden_size, mh), z(vc.out_hidden_size)
         d = tc.hidden_size
-        self.thd = d // tc.num_attention_heads
-        nq, nkv = tc.num_attention_heads * self.thd, tc.num_key_value_heads * self.thd
+        thd = d // tc.num_attention_heads
+        nq, nkv = tc.num_attention_heads * thd, tc.num_key_value_heads * thd
         W["model.embed_tokens"] = z(tc.vocab_size, d)
         for i in range(tc.num_hidden_layers):
             p = f"model.layers.{i}."
@@ -193,8 +202,7 @@ class B200Qwen2p5VL(torch.nn.Module):
             W[p + "down.w"] = z(d, tc.intermediate_size)
         W["model.norm"] = o(d)
         W["lm_head"] = z(tc.vocab_size, d)                    # text-reply branch (generate)
-        for k, t in W.items():
-            self.register_buffer("w__" + k.replace(".", "__"), t, persistent=False)
+        return W
 
     @property
     def dtype(self):
@@ -256,6 +264,43 @@ class B200Qwen2p5VL(torch.nn.Module):
         else:
             missing.append("lm_head.weight")                 # only the text-reply branch needs it
         return SimpleNamespace(missing_keys=missing, unexpected_keys=[])
+
+    def state_dict(self, *a, **k):
+        """transformers-4.50 key names <- kernel layout: the inverse of `load_state_dict` (fused tensors split, padding slots
+        dropped), so `save_pretrained` writes what `from_pretrained` — here and in the reference — reads."""
+        tc, vc, W, HP, hd = self.tc, self.vc, self.W, self.HP, self.vhd
+        sd = OrderedDict()
+        sd["visual.patch_embed.proj.weight"] = W["visual.patch_embed"].reshape(vc.hidden_size, vc.in_channels, vc.temporal_patch_size,
+                                                                               vc.patch_size, vc.patch_size)
+        nh, H = vc.num_heads, vc.hidden_size
+        I, Ip = vc.intermediate_size, self.vi
+        for i in range(vc.depth):
+            p = f"visual.blocks.{i}."
+            sd[p + "norm1.weight"], sd[p + "norm2.weight"] = W[p + "norm1"], W[p + "norm2"]
+            sd[p + "attn.qkv.weight"] = W[p + "qkv.w"].view(3, nh, HP, H)[:, :, :hd].reshape(3 * nh * hd, H)
+            sd[p + "attn.qkv.bias"] = W[p + "qkv.b"].view(3, nh, HP)[:, :, :hd].reshape(3 * nh * hd)
+            sd[p + "attn.proj.weight"] = W[p + "proj.w"].view(H, nh, HP)[:, :, :hd].reshape(H, nh * hd)
+            sd[p + "attn.proj.bias"] = W[p + "proj.b"]
+            sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"] = W[p + "gu.w"][:I], W[p + "gu.w"][Ip:Ip + I]
+            sd[p + "mlp.gate_proj.bias"], sd[p + "mlp.up_proj.bias"] = W[p + "gu.b"][:I], W[p + "gu.b"][Ip:Ip + I]
+            sd[p + "mlp.down_proj.weight"], sd[p + "mlp.down_proj.bias"] = W[p + "down.w"][:, :I], W[p + "down.b"]
+        sd["visual.merger.ln_q.weight"] = W["visual.merger.ln_q"]
+        for j in ("0", "2"):
+            sd[f"visual.merger.mlp.{j}.weight"], sd[f"visual.merger.mlp.{j}.bias"] = W[f"visual.merger.{j}.w"], W[f"visual.merger.{j}.b"]
+        sd["model.embed_tokens.weight"] = W["model.embed_tokens"]
+        nq, nkv = tc.num_attention_heads * self.thd, tc.num_key_value_heads * self.thd
+        It = tc.intermediate_size
+        for i in range(tc.num_hidden_layers):
+            p = f"model.layers.{i}."
+            sd[p + "input_layernorm.weight"], sd[p + "post_attention_layernorm.weight"] = W[p + "ln1"], W[p + "ln2"]
+            for name, lo, n in (("q_proj", 0, nq), ("k_proj", nq, nkv), ("v_proj", nq + nkv, nkv)):
+                sd[p + f"self_attn.{name}.weight"], sd[p + f"self_attn.{name}.bias"] = W[p + "qkv.w"][lo:lo + n], W[p + "qkv.b"][lo:lo + n]
+            sd[p + "self_attn.o_proj.weight"] = W[p + "o.w"]
+            sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"] = W[p + "gu.w"][:It], W[p + "gu.w"][It:]
+            sd[p + "mlp.down_proj.weight"] = W[p + "down.w"]
+        sd["model.norm.weight"] = W["model.norm"]
+        sd["lm_head.weight"] = W["lm_head"]
+        return sd
 
     @torch.no_grad()
     def randomize_(self, seed: int = 0, std: float = 0.02):

@@ -764,3 +764,48 @@ def test_training_checkpoint_writes_a_loadable_univa_directory(tmp_path):
         rewrite_checkpoint(src, tmp_path / "bad", {"denoise_tower.denoiser.nope": torch.zeros(1)})
     with pytest.raises(ValueError):              # or has with another shape
         rewrite_checkpoint(src, tmp_path / "bad2", {"model.embed_tokens.weight": torch.zeros(3, 3)})
+
+
+def test_save_pretrained_layout_and_config_round_trip(tmp_path):
+    """UnivaQwen2p5VLConfig.to_dict -> config.json -> univa_config_kwargs -> UnivaQwen2p5VLConfig is the identity on every field
+    the engine reads; save_univa_model (what `save_pretrained` calls) writes the checkpoint key names over any object with
+    the model's protocol (`lvlm`, `denoise_tower.denoiser`, `denoise_tower.denoise_projector`, `config`)."""
+    import json
+    from types import SimpleNamespace
+
+    from gpt_image_edit_b200.checkpoint import load_state_dict_from_dir, save_univa_model, univa_config_kwargs
+    from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLConfig, UnivaQwen2p5VLForConditionalGeneration
+
+    cfg = UnivaQwen2p5VLConfig(text_config=dict(hidden_size=64, num_hidden_layers=3, num_attention_heads=2, num_key_value_heads=1,
+                                                intermediate_size=96, vocab_size=321, rope_theta=5e5, mrope_section=(8, 12, 12)),
+                               vision_config=dict(depth=2, hidden_size=32, num_heads=2, intermediate_size=40, out_hidden_size=64,
+                                                  fullatt_block_indexes=(1,)),
+                               denoise_tower=dict(output_hidden_size=128, denoiser_config=dict(num_layers=2, num_single_layers=3,
+                                                                                               axes_dims_rope=(16, 56, 56))),
+                               image_token_id=300, video_token_id=301, vision_start_token_id=302)
+    raw = json.loads(json.dumps(cfg.to_dict()))                                  # through JSON, as config.json
+    assert raw["model_type"] == "univa_qwen2p5vl" and raw["hidden_size"] == 64 and raw["rope_scaling"]["mrope_section"] == [8, 12, 12]
+    back = UnivaQwen2p5VLConfig(**univa_config_kwargs(raw))
+    for k in ("hidden_size", "num_hidden_layers", "num_attention_heads", "num_key_value_heads", "intermediate_size", "vocab_size",
+              "rope_theta", "rms_norm_eps", "image_token_id", "vision_start_token_id"):
+        assert getattr(back.text_config, k) == getattr(cfg.text_config, k), k
+    assert tuple(back.text_config.mrope_section) == (8, 12, 12)
+    for k in ("depth", "hidden_size", "num_heads", "intermediate_size", "out_hidden_size", "in_channels", "patch_size", "window_size"):
+        assert getattr(back.vision_config, k) == getattr(cfg.vision_config, k), k
+    assert tuple(back.vision_config.fullatt_block_indexes) == (1,)
+    assert back.denoise_tower.input_hidden_size == 64 and back.denoise_tower.output_hidden_size == 128
+    assert back.denoise_tower.denoiser_config["num_single_layers"] == 3 and (back.image_token_id, back.video_token_id) == (300, 301)
+    sd_of = lambda d: SimpleNamespace(state_dict=lambda: d)
+    model = SimpleNamespace(config=cfg, lvlm=sd_of({"visual.merger.ln_q.weight": torch.ones(4), "model.norm.weight": torch.ones(4),
+                                                    "lm_head.weight": torch.zeros(2, 4)}),
+                            denoise_tower=SimpleNamespace(denoiser=sd_of({"proj_out.bias": torch.ones(3)}),
+                                                          denoise_projector=sd_of({"0.weight": torch.ones(2, 2)})))
+    wm = save_univa_model(model, tmp_path / "univa")
+    got = load_state_dict_from_dir(tmp_path / "univa")
+    assert set(got) == set(wm) == {"visual.merger.ln_q.weight", "model.norm.weight", "lm_head.weight", "denoise_tower.denoiser.proj_out.bias",
+                                   "denoise_tower.denoise_projector.0.weight"}
+    assert json.loads((tmp_path / "univa" / "config.json").read_text())["denoise_tower"]["output_hidden_size"] == 128
+    assert hasattr(UnivaQwen2p5VLForConditionalGeneration, "from_pretrained") and hasattr(UnivaQwen2p5VLForConditionalGeneration, "save_pretrained")
+    from gpt_image_edit_b200 import _lib
+    with pytest.raises(_lib.B2FError, match="bf16"):
+        UnivaQwen2p5VLForConditionalGeneration.from_pretrained(str(tmp_path / "univa"), torch_dtype=torch.float32)

@@ -100,3 +100,34 @@ def test_qwen_pixel_values_match_transformers_image_processor():
     assert grid.tolist() == ref["image_grid_thw"].tolist() == [[1, 32, 32]]
     assert pv.shape == ref["pixel_values"].shape == (1024, 1176)
     assert torch.allclose(pv, ref["pixel_values"].float(), atol=1e-5)
+
+
+def test_hf_state_dict_round_trips_through_the_kernel_layout():
+    """B200Qwen2p5VL.load_state_dict (HF names -> fused / padded kernel layout) and .state_dict (back) on the weights of a toy
+    transformers Qwen2_5_VLModel: every tensor comes back bit-identical under its 4.50 name, fused tensors sit where the
+    kernels read them (q | k | v rows, gate | up rows, vision heads in 128-wide slots with zero padding)."""
+    from types import SimpleNamespace
+
+    from gpt_image_edit_b200.qwen2p5vl import B200Qwen2p5VL, QwenTextConfig, QwenVisionConfig, _pad8
+
+    model, _ = _hf_model()
+    tc = QwenTextConfig(hidden_size=256, num_hidden_layers=1, num_attention_heads=2, num_key_value_heads=1, intermediate_size=512,
+                        vocab_size=1000, image_token_id=900, video_token_id=901, vision_start_token_id=902)
+    vc = QwenVisionConfig(depth=1, hidden_size=256, num_heads=4, intermediate_size=344, out_hidden_size=256, fullatt_block_indexes=(0,))
+    sd = {k.replace("language_model.", "model."): v.detach() for k, v in model.state_dict().items()}
+    sd["lm_head.weight"] = torch.randn(1000, 256)
+    me = SimpleNamespace(tc=tc, vc=vc, HP=B200Qwen2p5VL.HP, vhd=256 // 4, vi=_pad8(344), thd=128, _dev=torch.device("cpu"),
+                         W=B200Qwen2p5VL.alloc_weights(tc, vc, torch.device("cpu")))
+    res = B200Qwen2p5VL.load_state_dict(me, sd)
+    assert res.missing_keys == []
+    back = B200Qwen2p5VL.state_dict(me)
+    assert set(back) == set(sd), sorted(set(back) ^ set(sd))[:6]
+    for k, v in sd.items():
+        assert back[k].shape == v.shape, k
+        assert torch.equal(back[k], v.to(torch.bfloat16)), k
+    W = me.W
+    q = sd["model.layers.0.self_attn.q_proj.weight"].bfloat16()
+    assert torch.equal(W["model.layers.0.qkv.w"][:256], q) and W["model.layers.0.qkv.w"].shape == (256 + 2 * 128, 256)
+    assert torch.equal(W["model.layers.0.gu.w"][512:], sd["model.layers.0.mlp.up_proj.weight"].bfloat16())
+    vq = W["visual.blocks.0.qkv.w"].view(3, 4, 128, 256)
+    assert float(vq[:, :, 64:].abs().max()) == 0 and float(vq[:, :, :64].abs().max()) > 0      # head_dim 64 in a 128-wide slot

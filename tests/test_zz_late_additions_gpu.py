@@ -2,11 +2,12 @@
 the CPU as far as that goes (the transformers side of the padded-batch test runs here and gives the expected real-token
 equality; the host logic they exercise has CPU tests) but have NOT yet run on a B200.  They sit in a file that sorts last so
 that a surprise here cannot stop `pytest -x` before the tests with GPU history, and they carry a NON-strict xfail marker
-for the same reason: the first GPU run of these four is the driver's round-end tier, where they report as XPASS (they work)
+for the same reason: the first GPU run of these is the driver's round-end tier, where they report as XPASS (they work)
 or XFAIL (they do not) without turning the tier of tests that do have GPU history red.  Remove the marker after that run.
 
   * padded prompt batches in the Qwen2.5-VL prefill (gpt_image_edit_b200/qwen2p5vl.py: padding_spans, _decoder(spans=))
   * VAE slicing (gpt_image_edit_b200/vae.py: enable_slicing), reached through FluxKontextPipeline.enable_vae_slicing
+  * save_pretrained / from_pretrained of the Univa model (the key mapping itself round-trips on the CPU, test_qwen_host_cpu.py)
 """
 import pytest
 import torch
@@ -100,3 +101,24 @@ def test_vae_slicing_runs_one_item_per_pass_with_the_same_results():
     assert got[2].shape == want[2].shape and (got[2].int() - want[2].int()).abs().max().item() <= 1
     with pytest.raises(L.B2FError):
         pipe.enable_vae_tiling()
+
+
+def test_univa_model_save_pretrained_from_pretrained_round_trip(tmp_path):
+    """`model.save_pretrained(dir)` / `UnivaQwen2p5VLForConditionalGeneration.from_pretrained(dir, torch_dtype=bf16,
+    attn_implementation="flash_attention_2")` (reference train_denoiser.py:492-494, cli.py:37-41): every tensor comes back under
+    its checkpoint name and the reloaded model computes the same prompt embeddings."""
+    from univa.models.qwen2p5vl.modeling_univa_qwen2p5vl import UnivaQwen2p5VLForConditionalGeneration
+    from univa.serve import cli
+
+    model, _, _ = cli.load_main_model_and_processor("", torch.device("cuda"), synthetic=True, small=True)
+    model.save_pretrained(tmp_path / "univa")
+    m2 = UnivaQwen2p5VLForConditionalGeneration.from_pretrained(str(tmp_path / "univa"), torch_dtype=torch.bfloat16,
+                                                                attn_implementation="flash_attention_2")
+    from gpt_image_edit_b200.checkpoint import univa_state_dict
+    a, b = univa_state_dict(model), univa_state_dict(m2)
+    assert set(a) == set(b) and "denoise_tower.denoiser.transformer_blocks.0.attn.to_q.weight" in a and "lm_head.weight" in a
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    ids = cli.synthetic_chat_tokens(0).cuda()
+    e1 = model(ids, attention_mask=torch.ones_like(ids), output_type="denoise_embeds")
+    e2 = m2(ids, attention_mask=torch.ones_like(ids), output_type="denoise_embeds")
+    assert torch.equal(e1, e2)

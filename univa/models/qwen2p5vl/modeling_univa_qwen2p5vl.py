@@ -50,6 +50,25 @@ class UnivaQwen2p5VLConfig:
             raise B2FError("shortcut_image_embeds=True is not built")
         self.shortcut_projector_type, self.shortcut_image_embeds = None, False       # :29-31: no projector without the flag
 
+    def to_dict(self) -> dict:
+        """config.json content in the layout the reference's config class writes (transformers 4.50: language-model fields at
+        the top level, M-RoPE under `rope_scaling`, `vision_config` and `denoise_tower` sub-dicts)."""
+        tc, vc, dt = self.text_config, self.vision_config, self.denoise_tower
+        d = {"model_type": self.model_type, "architectures": ["UnivaQwen2p5VLForConditionalGeneration"], "torch_dtype": "bfloat16"}
+        for k in ("hidden_size", "num_hidden_layers", "num_attention_heads", "num_key_value_heads", "intermediate_size", "vocab_size",
+                  "rms_norm_eps", "rope_theta"):
+            d[k] = getattr(tc, k)
+        d["rope_scaling"] = {"type": "mrope", "mrope_section": list(tc.mrope_section)}
+        d.update(image_token_id=self.image_token_id, video_token_id=self.video_token_id,
+                 vision_start_token_id=self.vision_start_token_id, shortcut_image_embeds=False)
+        d["vision_config"] = {k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(vc).items()}
+        d["vision_config"]["in_chans"] = vc.in_channels
+        d["denoise_tower"] = {"model_type": dt.model_type, "denoiser_type": dt.denoiser_type,
+                              "denoise_projector_type": dt.denoise_projector_type, "input_hidden_size": dt.input_hidden_size,
+                              "output_hidden_size": dt.output_hidden_size,
+                              "denoiser_config": {k: (list(v) if isinstance(v, tuple) else v) for k, v in dict(dt.denoiser_config).items()}}
+        return d
+
 
 class UnivaQwen2p5VLForConditionalGeneration(torch.nn.Module):
     config_class = UnivaQwen2p5VLConfig
@@ -69,6 +88,25 @@ class UnivaQwen2p5VLForConditionalGeneration(torch.nn.Module):
     @property
     def device(self):
         return self.lvlm.device
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype=torch.bfloat16, attn_implementation=None, device="cuda",
+                        **kwargs):
+        """The reference's loading call (cli.py:37-41, gedit/step1_gen_samples.py:47-50, train_denoiser.py:1633):
+        `from_pretrained(path, torch_dtype=torch.bfloat16, attn_implementation="flash_attention_2")`.  The engine computes in
+        bf16 and has one attention implementation (its padding semantics are flash_attention_2's), so `torch_dtype` must be
+        bf16 (or None) and `attn_implementation` is accepted for the signature's sake."""
+        if torch_dtype not in (None, torch.bfloat16):
+            raise B2FError(f"torch_dtype={torch_dtype}: the libb2f engine computes in bf16")
+        from gpt_image_edit_b200.checkpoint import load_univa_model
+        return load_univa_model(pretrained_model_name_or_path, device=device)
+
+    def save_pretrained(self, save_directory, max_shard_size: int = 5 << 30, **kwargs):
+        """`model.save_pretrained(dir)` of the reference's save hook (train_denoiser.py:492-494): safetensors shards with the
+        checkpoint's key names (`visual.*`, `model.*`, `lm_head.weight`, `denoise_tower.denoiser.*`,
+        `denoise_tower.denoise_projector.*`) and config.json."""
+        from gpt_image_edit_b200.checkpoint import save_univa_model
+        return save_univa_model(self, save_directory, max_shard_size)
 
     def get_rope_index(self, input_ids, image_grid_thw=None, video_grid_thw=None, second_per_grid_ts=None,
                        attention_mask=None):
