@@ -28,8 +28,10 @@ def _doubles():
             y = y + bias.float()
         if epilogue == ops.EPI_RESID:
             y = y + resid.float()
+        elif epilogue == ops.EPI_GELU_ERF:
+            y = torch.nn.functional.gelu(y.to(BF).float())
         elif epilogue != ops.EPI_BIAS:
-            raise AssertionError(f"epilogue {epilogue} is not used by the decoder")
+            raise AssertionError(f"epilogue {epilogue} is not used by the Qwen2.5-VL host code")
         y = y.to(BF)
         if out is not None:
             out.copy_(y)
@@ -37,10 +39,14 @@ def _doubles():
         return y
 
     def rope_half_(x, heads, head_pitch, cos, sin, *, fp32_math):
+        # cos / sin hold `rot` columns (the rotary width: the whole head for the decoder, 80 of a 128-wide slot for the ViT);
+        # columns beyond it are padding and stay untouched
+        rot = cos.shape[-1]
         v = x[:, : heads * head_pitch].float().reshape(x.shape[0], heads, head_pitch)
-        half = head_pitch // 2
-        rot = torch.cat((-v[..., half:], v[..., :half]), dim=-1)
-        x[:, : heads * head_pitch] = (v * cos[:, None, :] + rot * sin[:, None, :]).reshape(x.shape[0], -1).to(BF)
+        a = v[..., :rot]
+        r = torch.cat((-a[..., rot // 2:], a[..., : rot // 2]), dim=-1)
+        v = torch.cat((a * cos[:, None, :] + r * sin[:, None, :], v[..., rot:]), dim=-1)
+        x[:, : heads * head_pitch] = v.reshape(x.shape[0], -1).to(BF)
         return x
 
     def attention(q, k, v, *, out=None, causal=False, scale=None, bias=None):
@@ -63,7 +69,12 @@ def _doubles():
     def gather_rows(table, idx, *, out=None):
         return table[idx].clone()
 
-    return dict(rmsnorm=rmsnorm, linear=linear, rope_half_=rope_half_, attention=attention, swiglu=swiglu, gather_rows=gather_rows)
+    def scatter_rows_(dst, idx, src):
+        dst[idx] = src
+        return dst
+
+    return dict(rmsnorm=rmsnorm, linear=linear, rope_half_=rope_half_, attention=attention, swiglu=swiglu, gather_rows=gather_rows,
+                scatter_rows_=scatter_rows_)
 
 
 @pytest.fixture()
@@ -168,3 +179,53 @@ def test_padding_spans_and_refusals():
             padding_spans(torch.tensor(bad))
     with pytest.raises(_lib.B2FError):
         padding_spans(torch.ones(4))
+
+
+def test_vision_tower_and_image_prefill_orchestration(monkeypatch):
+    """forward_visual (patch embed, 2-D rope in window order, windowed / full block-diagonal attention launched per run of
+    equal segments, 80-wide heads in 128-wide slots, padded MLP width, 2x2 merger, un-windowing) and the scatter of the image
+    embeddings into the prompt, on the CPU over the torch doubles, against transformers' Qwen2_5_VLModel with the weights
+    loaded through the product's own load_state_dict."""
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLConfig
+
+    from gpt_image_edit_b200 import ops
+    from gpt_image_edit_b200.qwen2p5vl import B200Qwen2p5VL, QwenTextConfig, QwenVisionConfig, _pad8, get_rope_index
+
+    for name, fn in _doubles().items():
+        monkeypatch.setattr(ops, name, fn)
+    tcd = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1, intermediate_size=512,
+               vocab_size=1000, rms_norm_eps=1e-6)
+    vcd = dict(depth=3, hidden_size=320, num_heads=4, intermediate_size=340, out_hidden_size=256, fullatt_block_indexes=[1])
+    cfg = Qwen2_5_VLConfig(text_config=dict(tcd, rope_parameters=dict(rope_type="default", rope_theta=1e6, mrope_section=[16, 24, 24])),
+                           vision_config=vcd, image_token_id=900, video_token_id=901, vision_start_token_id=902, vision_end_token_id=903)
+    torch.manual_seed(0)
+    ref = hf.Qwen2_5_VLModel(cfg).eval().float()
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+            p.copy_(p.to(BF).float())
+    tc = QwenTextConfig(**tcd, image_token_id=900, video_token_id=901, vision_start_token_id=902)
+    vc = QwenVisionConfig(**{**vcd, "fullatt_block_indexes": (1,)})
+    me = types.SimpleNamespace(tc=tc, vc=vc, HP=B200Qwen2p5VL.HP, vhd=320 // 4, vi=_pad8(340), thd=128, _dev=torch.device("cpu"),
+                               W=B200Qwen2p5VL.alloc_weights(tc, vc, torch.device("cpu")))
+    sd = {k.replace("language_model.", "model."): v.detach() for k, v in ref.state_dict().items()}
+    B200Qwen2p5VL.load_state_dict(me, sd)
+    for name in ("_rope_tables", "_decoder", "_segment_attention", "forward_visual"):
+        setattr(me, name, types.MethodType(getattr(B200Qwen2p5VL, name), me))
+    g = torch.Generator().manual_seed(3)
+    grid = torch.tensor([[1, 16, 8], [1, 4, 4]])                      # two images: 32 + 4 merged tokens, windows of unequal sizes
+    pix = torch.randn(128 + 16, 1176, generator=g).to(BF)
+    with torch.no_grad():
+        v_ref = ref.visual(pix.float(), grid_thw=grid).pooler_output
+    v = me.forward_visual(pix, grid)
+    assert v.shape == v_ref.shape == (36, 256)
+    assert _rel(v, v_ref) < 2e-2
+    ids = torch.tensor([[1, 2, 902] + [900] * 32 + [903, 5, 902] + [900] * 4 + [903] + list(range(10, 22))])
+    h = B200Qwen2p5VL.forward(me, ids, pixel_values=pix, image_grid_thw=grid)
+    pos, _ = get_rope_index(ids, grid, None, spatial_merge_size=2, image_token_id=900, vision_start_token_id=902)
+    with torch.no_grad():
+        h_ref = ref(input_ids=ids, pixel_values=pix.float(), image_grid_thw=grid, position_ids=pos).last_hidden_state
+    assert h.shape == h_ref.shape and _rel(h, h_ref) < 2e-2
+    with pytest.raises(ValueError, match="do not match"):
+        B200Qwen2p5VL.forward(me, ids[:, :-8 - 6], pixel_values=pix, image_grid_thw=grid)     # the second image's tokens cut off
