@@ -229,3 +229,57 @@ def test_vision_tower_and_image_prefill_orchestration(monkeypatch):
     assert h.shape == h_ref.shape and _rel(h, h_ref) < 2e-2
     with pytest.raises(ValueError, match="do not match"):
         B200Qwen2p5VL.forward(me, ids[:, :-8 - 6], pixel_values=pix, image_grid_thw=grid)     # the second image's tokens cut off
+
+
+def test_kv_cache_decode_orchestration(monkeypatch):
+    """generate() — prefill into the KV cache, then one token per step with single-query attention over the cached prefix,
+    M-RoPE positions continued at past + delta, lm_head, greedy pick, eos / padding handling — on the CPU over the torch doubles:
+    teacher-forced with transformers' greedy reply, the per-step logits must match its scores."""
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLConfig
+
+    from gpt_image_edit_b200 import ops
+    from gpt_image_edit_b200.qwen2p5vl import B200Qwen2p5VL, QwenTextConfig, QwenVisionConfig, _pad8
+
+    for name, fn in _doubles().items():
+        monkeypatch.setattr(ops, name, fn)
+    tcd = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1, intermediate_size=512,
+               vocab_size=1000, rms_norm_eps=1e-6)
+    vcd = dict(depth=1, hidden_size=256, num_heads=4, intermediate_size=340, out_hidden_size=256, fullatt_block_indexes=[0])
+    cfg = Qwen2_5_VLConfig(text_config=dict(tcd, rope_parameters=dict(rope_type="default", rope_theta=1e6, mrope_section=[16, 24, 24])),
+                           vision_config=vcd, image_token_id=900, video_token_id=901, vision_start_token_id=902, vision_end_token_id=903)
+    torch.manual_seed(1)
+    ref = hf.Qwen2_5_VLForConditionalGeneration(cfg).eval().float()
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+        ref.lm_head.weight.normal_(0, 0.2)
+        for p in ref.parameters():
+            p.copy_(p.to(BF).float())
+    tc = QwenTextConfig(**tcd, image_token_id=900, video_token_id=901, vision_start_token_id=902)
+    vc = QwenVisionConfig(**{**vcd, "fullatt_block_indexes": (0,)})
+    me = types.SimpleNamespace(tc=tc, vc=vc, HP=B200Qwen2p5VL.HP, vhd=64, vi=_pad8(340), thd=128, _dev=torch.device("cpu"),
+                               W=B200Qwen2p5VL.alloc_weights(tc, vc, torch.device("cpu")))
+    sd = {k.replace("model.language_model.", "model.").replace("model.visual.", "visual."): v.detach() for k, v in ref.state_dict().items()}
+    assert B200Qwen2p5VL.load_state_dict(me, sd).missing_keys == []
+    for name in ("_rope_tables", "_decoder", "forward", "lm_logits"):
+        setattr(me, name, types.MethodType(getattr(B200Qwen2p5VL, name), me))
+    ids = torch.tensor([[1, 2, 3] + list(range(10, 30))])
+    steps = 8
+    with torch.no_grad():
+        gen = ref.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=steps, min_new_tokens=steps, do_sample=False,
+                           output_scores=True, return_dict_in_generate=True, repetition_penalty=1.0, eos_token_id=None, pad_token_id=0)
+    want_tokens = gen.sequences[:, ids.shape[1]:]
+    want_logits = torch.stack(gen.scores, dim=1).float()
+    seq, scores = B200Qwen2p5VL.generate(me, ids, forced_tokens=want_tokens, output_scores=True, eos_token_id=(999999,))
+    got = torch.stack(scores, dim=1)
+    assert torch.equal(seq[:, ids.shape[1]:], want_tokens) and got.shape == want_logits.shape
+    assert _rel(got, want_logits) < 2e-2
+    top2 = want_logits.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 8 * (got - want_logits).abs().max()
+    assert int(clear.sum()) >= 1 and torch.equal(got.argmax(-1)[clear], want_tokens[clear])      # same pick wherever it is not a tie
+    # eos: the reply stops at the first eos token and the sequence ends there
+    eos_tok = int(want_tokens[0, 1])
+    short = B200Qwen2p5VL.generate(me, ids, forced_tokens=None, max_new_tokens=steps, eos_token_id=(eos_tok,))
+    if bool(clear[0, :2].all()):
+        assert short.shape[1] == ids.shape[1] + 2 and int(short[0, -1]) == eos_tok
