@@ -424,8 +424,8 @@ class B200Qwen2p5VL(torch.nn.Module):
         train_denoiser.py:1633)."""
         tc, W, hd = self.tc, self.W, self.thd
         nq, nkv = tc.num_attention_heads, tc.num_key_value_heads
-        # padded batch: the rows no launch writes must read as zeros in every layer
-        o = (torch.zeros if spans is not None else torch.empty)((B * L, nq * hd), device=self._dev, dtype=torch.bfloat16)
+        # padded prefill: the rows no launch writes must read as zeros in every layer
+        o = (torch.zeros if (spans is not None and not past) else torch.empty)((B * L, nq * hd), device=self._dev, dtype=torch.bfloat16)
         if past and L != 1:
             raise _lib.B2FError("chunked prefill is not implemented: use past == 0 (prefill) or one new token (decode)")
         for i in range(tc.num_hidden_layers):
@@ -440,12 +440,14 @@ class B200Qwen2p5VL(torch.nn.Module):
                 kv_cache[i, 0, :, past:past + L].copy_(k)
                 kv_cache[i, 1, :, past:past + L].copy_(v)
             if past:
-                # decode: the new token attends to every cached position (no mask needed); one launch per sequence
-                # because the cache's batch pitch (Lmax rows) differs from the attended length
+                # decode: the new token attends to every cached position of its own sequence (no mask needed: a left-padded
+                # prompt's padding slots lie before `lo`); one launch per sequence because the cache's batch pitch (Lmax
+                # rows) differs from the attended length
                 for b in range(B):
-                    ops.attention(q[b:b + 1], kv_cache[i, 0, b:b + 1, :past + 1], kv_cache[i, 1, b:b + 1, :past + 1],
+                    lo = spans[b][0] if spans is not None else 0
+                    ops.attention(q[b:b + 1], kv_cache[i, 0, b:b + 1, lo:past + 1], kv_cache[i, 1, b:b + 1, lo:past + 1],
                                   out=o.unflatten(0, (B, L))[b:b + 1])
-            elif spans is not None:
+            elif spans is not None:                      # padded prefill
                 o3 = o.unflatten(0, (B, L))
                 for b, (lo, hi) in enumerate(spans):
                     ops.attention(q[b:b + 1, lo:hi], k[b:b + 1, lo:hi], v[b:b + 1, lo:hi], out=o3[b:b + 1, lo:hi], causal=True)
@@ -479,8 +481,8 @@ class B200Qwen2p5VL(torch.nn.Module):
         steps = int(forced_tokens.shape[1]) if forced_tokens is not None else int(max_new_tokens)
         cache = torch.empty((tc.num_hidden_layers, 2, B, L + steps, tc.num_key_value_heads, self.thd), device=self._dev,
                             dtype=torch.bfloat16)
-        hidden, deltas = self.forward(ids, pixel_values=pixel_values, attention_mask=attention_mask,
-                                      image_grid_thw=image_grid_thw, kv_cache=cache, return_rope_deltas=True)
+        hidden, deltas, spans = self.forward(ids, pixel_values=pixel_values, attention_mask=attention_mask,
+                                             image_grid_thw=image_grid_thw, kv_cache=cache, return_rope_deltas=True)
         last = hidden[:, -1]                                            # [B, hidden]
         eos = torch.tensor(list(eos_token_id) if not isinstance(eos_token_id, int) else [eos_token_id], device=self._dev)
         out = [ids]
@@ -507,7 +509,7 @@ class B200Qwen2p5VL(torch.nn.Module):
             pos = (torch.full((B, 1), L + t, dtype=torch.long) + deltas.cpu().view(B, 1))[None].expand(3, B, 1)
             cos, sin = self._rope_tables(pos)
             x = ops.gather_rows(self.W["model.embed_tokens"], nxt.contiguous())
-            last = self._decoder(x, cos, sin, B, 1, cache, past=L + t)
+            last = self._decoder(x, cos, sin, B, 1, cache, past=L + t, spans=spans)
         seq = torch.cat(out, dim=1)
         return (seq, scores) if output_scores else seq
 
@@ -520,9 +522,9 @@ class B200Qwen2p5VL(torch.nn.Module):
         spans = None
         if attention_mask is not None and not bool((attention_mask == 1).all()):
             spans = padding_spans(attention_mask)
-            if kv_cache is not None:
-                raise _lib.B2FError("generate() with a padded batch is not built (the KV-cache decode attends to every cached "
-                                    "position): decode one prompt per call, as cli.py does")
+            if kv_cache is not None and any(hi != L for _, hi in spans):
+                raise _lib.B2FError("generate() takes left-padded prompt batches (every prompt ends at the last column, as the "
+                                    "processor pads for generation); this batch is padded on the right")
         ids = input_ids.to(self._dev)
         x = ops.gather_rows(W["model.embed_tokens"], ids.reshape(-1).contiguous())
         image_embeds = None
@@ -539,5 +541,5 @@ class B200Qwen2p5VL(torch.nn.Module):
         cos, sin = self._rope_tables(pos)
         h = self._decoder(x, cos, sin, B, L, kv_cache, spans=spans).view(B, L, tc.hidden_size)
         if return_rope_deltas:
-            return h, deltas
+            return h, deltas, spans
         return (h, image_embeds) if return_image_embeds else h

@@ -278,6 +278,26 @@ def test_kv_cache_decode_orchestration(monkeypatch):
     top2 = want_logits.topk(2, dim=-1).values
     clear = (top2[..., 0] - top2[..., 1]) > 8 * (got - want_logits).abs().max()
     assert int(clear.sum()) >= 1 and torch.equal(got.argmax(-1)[clear], want_tokens[clear])      # same pick wherever it is not a tie
+    # a left-padded batch of two prompts (what the processor produces for generation): each row must reproduce ITS OWN
+    # unpadded reply's logits; right-padded batches are refused
+    from gpt_image_edit_b200 import _lib
+    short_prompt = torch.tensor([[7, 8, 9, 40, 41, 42, 43]])
+    with torch.no_grad():
+        gen_b = ref.generate(input_ids=short_prompt, attention_mask=torch.ones_like(short_prompt), max_new_tokens=steps,
+                             min_new_tokens=steps, do_sample=False, output_scores=True, return_dict_in_generate=True,
+                             repetition_penalty=1.0, eos_token_id=None, pad_token_id=0)
+    tok_b = gen_b.sequences[:, short_prompt.shape[1]:]
+    n, nb = ids.shape[1], short_prompt.shape[1]
+    batch = torch.cat([ids, torch.cat([torch.zeros(1, n - nb, dtype=torch.long), short_prompt], dim=1)])
+    mask = torch.cat([torch.ones(1, n, dtype=torch.long), torch.cat([torch.zeros(1, n - nb, dtype=torch.long),
+                                                                     torch.ones(1, nb, dtype=torch.long)], dim=1)])
+    seq2, scores2 = B200Qwen2p5VL.generate(me, batch, attention_mask=mask, forced_tokens=torch.cat([want_tokens, tok_b]),
+                                           output_scores=True, eos_token_id=(999999,))
+    got2 = torch.stack(scores2, dim=1)                                   # [2, steps, vocab]
+    assert _rel(got2[0], want_logits[0]) < 2e-2
+    assert _rel(got2[1], torch.stack(gen_b.scores, dim=1).float()[0]) < 2e-2
+    with pytest.raises(_lib.B2FError, match="left-padded"):
+        B200Qwen2p5VL.generate(me, batch.flip(1), attention_mask=mask.flip(1), max_new_tokens=2)
     # eos: the reply stops at the first eos token and the sequence ends there
     eos_tok = int(want_tokens[0, 1])
     short = B200Qwen2p5VL.generate(me, ids, forced_tokens=None, max_new_tokens=steps, eos_token_id=(eos_tok,))

@@ -5,7 +5,8 @@ that a surprise here cannot stop `pytest -x` before the tests with GPU history, 
 for the same reason: the first GPU run of these is the driver's round-end tier, where they report as XPASS (they work)
 or XFAIL (they do not) without turning the tier of tests that do have GPU history red.  Remove the marker after that run.
 
-  * padded prompt batches in the Qwen2.5-VL prefill (gpt_image_edit_b200/qwen2p5vl.py: padding_spans, _decoder(spans=))
+  * padded prompt batches in the Qwen2.5-VL prefill and left-padded batches in generate() (gpt_image_edit_b200/qwen2p5vl.py:
+    padding_spans, _decoder(spans=))
   * VAE slicing (gpt_image_edit_b200/vae.py: enable_slicing), reached through FluxKontextPipeline.enable_vae_slicing
   * save_pretrained / from_pretrained of the Univa model (the key mapping itself round-trips on the CPU, test_qwen_host_cpu.py)
 """
@@ -69,13 +70,25 @@ def test_padded_batch_prefill(side):
     assert all(_rel_l2(r, want) < 2e-2 for r in pad_rows)
 
 
-def test_generate_refuses_padded_batches():
+def test_generate_takes_left_padded_batches_and_refuses_right_padded_ones():
+    """KV-cache decode of a left-padded prompt batch: each row's forced-token logits equal those of the prompt decoded alone
+    (the orchestration is checked against transformers' generate on the CPU, tests/test_qwen_decoder_host_cpu.py)."""
     from gpt_image_edit_b200 import _lib
 
     _, mine = _models()
-    ids = torch.tensor([[1, 2, 3, 4], [5, 6, 7, 7]]).cuda()
-    with pytest.raises(_lib.B2FError):
-        mine.generate(ids, attention_mask=torch.tensor([[1, 1, 1, 1], [1, 1, 1, 0]]).cuda(), max_new_tokens=2)
+    mine.W["lm_head"].copy_((torch.randn(mine.W["lm_head"].shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+                             * 0.2).bfloat16())
+    a, b = list(range(10, 33)), [5, 6, 7, 40, 41, 42, 43]
+    forced = torch.tensor([[11, 12, 13, 14], [21, 22, 23, 24]]).cuda()
+    batch = torch.tensor([a, [0] * (len(a) - len(b)) + b]).cuda()
+    mask = torch.tensor([[1] * len(a), [0] * (len(a) - len(b)) + [1] * len(b)]).cuda()
+    _, sc = mine.generate(batch, attention_mask=mask, forced_tokens=forced, output_scores=True, eos_token_id=(999999,))
+    _, sa = mine.generate(torch.tensor([a]).cuda(), forced_tokens=forced[:1], output_scores=True, eos_token_id=(999999,))
+    _, sb = mine.generate(torch.tensor([b]).cuda(), forced_tokens=forced[1:], output_scores=True, eos_token_id=(999999,))
+    got = torch.stack(sc, dim=1)
+    assert _rel_l2(got[0], torch.stack(sa, dim=1)[0]) < 5e-3 and _rel_l2(got[1], torch.stack(sb, dim=1)[0]) < 5e-3
+    with pytest.raises(_lib.B2FError, match="left-padded"):
+        mine.generate(batch.flip(1), attention_mask=mask.flip(1), max_new_tokens=2)
 
 
 def test_vae_slicing_runs_one_item_per_pass_with_the_same_results():
