@@ -19,7 +19,7 @@ kernels when they check the sharding logic; the product never passes it.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import torch
 import torch.distributed as dist

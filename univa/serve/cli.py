@@ -25,7 +25,6 @@ Differences, all forced by this environment and all explicit:
 from __future__ import annotations
 
 import argparse
-import os
 
 import numpy as np
 import torch
